@@ -1,0 +1,130 @@
+"""The CPU oracle against fixtures produced by the reference's own Python modules.
+
+Fixtures come from tests/golden/make_golden.py, which imports the unmodified
+ffn/inference/{inference,movement,seed,storage}.py from the reference checkout.
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import flood_fill as ff
+from oracle.toy_net import toy_image, toy_net
+
+
+def _load(golden_dir, name):
+  return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_thresholds_match_reference(golden_dir):
+  g = _load(golden_dir, 'flood_fill_64.npz')
+  init, pad, move, seg = g['thresholds']
+  assert float(ff.f32_logit(0.95)) == init
+  assert float(ff.f32_logit(0.05)) == pad
+  assert float(ff.f32_logit(0.9)) == move
+  assert float(ff.f32_logit(0.6)) == seg
+  assert ff.policy_threshold(0.9) == float(g['policy_threshold'])
+  # the f64 policy threshold and the f32 canvas threshold select the same scores.
+  assert np.float32(move).view(np.uint32) == 0x400c9f53
+  assert np.nextafter(np.float32(move), np.float32(0)) < g['policy_threshold'] <= move
+
+
+def test_quantize_probability(golden_dir):
+  g = _load(golden_dir, 'qprob.npz')
+  np.testing.assert_array_equal(ff.quantize_probability(g['prob']), g['q'])
+  np.testing.assert_array_equal(
+      ff.quantize_probability(np.array([0, .003, .5, .6, .999, 1.0])), [1, 1, 128, 153, 254, 255])
+
+
+def test_scored_moves(golden_dir):
+  g = _load(golden_dir, 'moves.npz')
+  th = float(g['threshold'])
+  for i in range(int(g['n'])):
+    deltas, logits, want = g['deltas_%d' % i], g['logits_%d' % i], g['moves_%d' % i]
+    got = ff.scored_moves(deltas, logits, th)
+    got.sort(reverse=True)
+    arr = np.asarray([(float(s),) + r for s, r in got], dtype=np.float64).reshape(-1, 4)
+    np.testing.assert_array_equal(arr, want)
+
+
+def test_grid_seeds_match_policy_grid3d(golden_dir):
+  g = _load(golden_dir, 'toy_flood_fill.npz')
+  shape = g['cells'].shape
+  seeds = ff.grid_seeds(shape)
+  margin = np.array([16, 16, 16])
+  keep = np.all((seeds - margin >= 0) & (seeds + margin < np.array(shape)), axis=1)
+  np.testing.assert_array_equal(seeds[keep], g['seeds'])   # after the border filter seed.py:81-88
+
+
+def _check_canvas(canvas, g, exact_seed=True):
+  np.testing.assert_array_equal(np.asarray(canvas.trace, dtype=np.int32).reshape(-1, 3), g['trace'])
+  np.testing.assert_array_equal(canvas.segmentation, g['segmentation'])
+  if exact_seed:
+    np.testing.assert_array_equal(canvas.seed, g['seed_canvas'])
+    np.testing.assert_array_equal(canvas.seg_prob, g['seg_prob'])
+  else:
+    np.testing.assert_allclose(canvas.seed, g['seed_canvas'], atol=2e-3, rtol=0, equal_nan=True)
+    assert np.abs(canvas.seg_prob.astype(int) - g['seg_prob'].astype(int)).max() <= 1
+  origins = np.array([(k,) + v[0] + (v[1],) for k, v in sorted(canvas.origins.items())],
+                     dtype=np.int64).reshape(-1, 5)
+  np.testing.assert_array_equal(origins, g['origins'])
+  owner, ids, cnt = [], [], []
+  for k, v in sorted(canvas.overlaps.items()):
+    for i, c in zip(v[0], v[1]):
+      owner.append(k); ids.append(int(i)); cnt.append(int(c))
+  np.testing.assert_array_equal(np.asarray([owner, ids, cnt], dtype=np.int64).reshape(3, -1),
+                                g['overlaps'].reshape(3, -1))
+  want = json.loads(str(g['counters']))
+  for name in ('skip_threshold', 'skip_invalid_pos', 'voxels-segmented', 'voxels-overlapping',
+               'inference-calls', 'seed_got_too_weak'):
+    assert canvas.counters.get(name, 0) == want.get(name, 0), name
+  assert canvas.counters['segment_at-calls'] == want['segment_at-loop-calls']
+
+
+def test_toy_flood_fill_bit_exact(golden_dir):
+  """Loop logic pinned machine-independently (elementwise-only toy network)."""
+  g = _load(golden_dir, 'toy_flood_fill.npz')
+  image = toy_image(g['cells'])
+  opts = ff.Options(min_segment_size=int(g['min_segment_size']),
+                    min_boundary_dist=tuple(int(v) for v in g['min_boundary_dist']))
+  canvas = ff.Canvas(toy_net, image, (33, 33, 33), (8, 8, 8), opts)
+  canvas.segment_all(g['seeds'])
+  _check_canvas(canvas, g, exact_seed=True)
+
+
+@pytest.mark.slow
+def test_real_net_flood_fill(golden_dir):
+  """Same loop with the FIB-25 conv stack (torch CPU).  Exactness is qualified by the decision
+  margin because conv3d rounding may differ between CPUs."""
+  ckpt = os.environ.get('FFN_CKPT', '/root/reference/models/fib25/model.ckpt-27465036')
+  if not os.path.exists(ckpt + '.index'):
+    ckpt = os.path.join(golden_dir, 'fib25', 'model.ckpt-27465036')
+  if not os.path.exists(ckpt + '.index'):
+    pytest.skip('FIB-25 checkpoint not available')
+  from ffn_b200 import tf_checkpoint
+  from oracle.network import ConvStackOracle
+  g = _load(golden_dir, 'flood_fill_64.npz')
+  w, b = tf_checkpoint.load_convstack_weights(ckpt, 12)
+  image = (g['volume'].astype(np.float32) - 128.0) / 33.0
+  canvas = ff.Canvas(ConvStackOracle(w, b), image, (33, 33, 33), (8, 8, 8), ff.Options())
+  canvas.segment_all(g['seeds'])
+  if canvas.min_margin < 1e-4:
+    pytest.skip('knife-edge decision (margin %g): trajectory not comparable across CPUs' % canvas.min_margin)
+  _check_canvas(canvas, g, exact_seed=False)
+
+
+def test_canonical_relabel():
+  seg = np.array([[0, 7, 7], [3, 3, -1], [7, 9, 0]])
+  np.testing.assert_array_equal(ff.canonical_relabel(seg), [[0, 1, 1], [2, 2, 0], [1, 3, 0]])
+
+
+def test_golden_sample_summary(golden_dir):
+  """Sanity ranges of the reference's shipped 250^3 result (input volume is not available)."""
+  with open(os.path.join(golden_dir, 'sample_training2_summary.json')) as f:
+    s = json.load(f)
+  assert s['shape'] == [250, 250, 250]
+  assert s['num_segments'] == 254 == s['num_origins'] == s['origins_carry_own_id']
+  assert s['counters']['inference-calls'] == 25799
+  assert s['counters']['voxels-segmented'] == 13867123

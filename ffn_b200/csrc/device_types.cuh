@@ -1,0 +1,188 @@
+// device_types.cuh — plain structs shared by the host engine and the persistent kernel.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ffn_b200.h"
+
+namespace ffn {
+
+constexpr int kThreads = 256;     // 8 warps: two epilogue quads (TMEM lane quarters x 2 tiles)
+constexpr int kTileM = 128;       // UMMA M: FoV rows per tensor-core tile
+constexpr int kFeat = 32;         // feature maps of every hidden layer (UMMA N)
+constexpr int kGroupTiles = 3;    // tiles whose operands are staged in shared memory together
+constexpr int kMaxConv = 32;      // 2 * depth limit
+constexpr int kTmemCols = 128;    // >= kGroupTiles * kFeat, power of two
+
+// Field-of-view geometry in the "row" space the kernels work in.
+//
+// A FoV voxel (z, y, x) lives at row  r = z * pp + y * xp + x  with xp = fx + 1 and
+// pp = (fy + 1) * xp: every x-line is followed by ONE zero column and every z-plane by ONE zero
+// line, so the SAME-padding halo of a 3x3x3 tap is always a stored zero and a tap is a constant
+// row offset dz*pp + dy*xp + dx.  Rows are cut into tiles of 128 consecutive rows = one UMMA M.
+struct Geom {
+  int fz, fy, fx;   // FoV size (z, y, x)
+  int mz, my, mx;   // margin = size // 2
+  int dz, dy, dx;   // movement deltas
+  int nconv;        // number of 3x3x3 convolutions (2 * depth)
+  int xp, pp;       // row pitches
+  int nr;           // rows spanned by the FoV: (fz-1)*pp + (fy-1)*xp + fx
+  int nt;           // tiles: ceil(nr / 128)
+  int halo;         // xp + 1: in-plane reach of a tap, in rows
+  int guard;        // zero rows before row 0 / after the last tile in global activation buffers
+  int rows_alloc;   // guard + nt*128 + guard
+  int V;            // fz*fy*fx voxels
+};
+
+struct Weights {
+  const __half* w16;   // per layer [27][kchunk][4 n-groups][8 n][8 k] fp16 (UMMA K-major, no swizzle)
+  const float* w32;    // per layer [27][cin_padded][32] fp32
+  const float* bias;   // [nconv][32]
+  const float* w_lom;  // [32]
+  float b_lom;
+};
+
+struct Workspace {
+  __half* act0_h;      // [2][rows_alloc][8] (chunk 1 stays zero)
+  __half* act_h[2];    // [4][rows_alloc][8]
+  float4* act0_f;      // [1][rows_alloc]  (image, seed, 0, 0)
+  float4* act_f[2];    // [8][rows_alloc]
+  float4* res;         // [8][rows_alloc] fp32 residual stream
+  float* seed_raw;     // [nt*128] seed FoV as read from the canvas (NaN preserved)
+  float* logits;       // [nt*128] network output (seed + update), before the disco merge
+  unsigned* bar;       // grid barrier counter
+  unsigned* count;     // voxels with logit >= move threshold in the current step
+  int* abort_flag;     // != 0: a wait timed out, everybody bails
+};
+
+struct CanvasDev {
+  const void* image;
+  int image_is_u8;
+  float mean, stddev;
+  float* seed;
+  int* seg;
+  uint8_t* qprob;             // may be null
+  const uint8_t* mask;        // may be null
+  const uint8_t* seed_mask;   // may be null
+  int sz, sy, sx;
+  FfnOptions opt;
+  float policy_th_f32;        // smallest float32 >= opt.policy_score_threshold
+  // movement policy storage
+  float* q_score;
+  int* q_pos;                 // [cap][3]
+  int q_cap;
+  unsigned* lattice;          // epoch stamps over the quantised lattice
+  int lat_dim[3], lat_off[3];
+};
+
+enum Phase : int {
+  PH_IDLE = 0,
+  PH_START_SEGMENT,    // segment_at entry: clear + init (if reset) then pop
+  PH_AFTER_CLEAR,
+  PH_AFTER_STEP,
+  PH_POP,              // resume point inside an object (budget pause)
+  PH_NEXT_SEED,
+  PH_AFTER_COUNT,
+  PH_AFTER_WRITE,
+  PH_SEGMENT_DONE,
+  PH_ALL_DONE,
+  PH_FORCE_STEP,       // update_at: run exactly one step at `cur`
+};
+
+// Persistent per-canvas state (global memory) — what the reference keeps in the Canvas and
+// FaceMaxMovementPolicy objects between FoV steps.
+struct CanvasState {
+  int phase;
+  int q_head, q_tail;
+  unsigned epoch;
+  int start[3];
+  int cur[3];
+  int have_cur;               // cur is the FoV of the step whose logits are in the workspace
+  int min_pos[3], max_pos[3];
+  long long iters;            // steps of the current object
+  int dirty_lo[3], dirty_hi[3];   // box of the seed canvas that may hold non-NaN values (hi exclusive)
+  long long seed_idx;
+  int max_id;
+  int reset_seed;             // segment_at: init_seed before starting
+  int seg_all;                // 1: segment_all mode, 0: segment_at mode
+  int weak;                   // last object ended by 'seed_got_too_weak'
+  // commit scratch
+  int box_lo[3], box_hi[3];
+  unsigned long long cnt_raw, cnt_actual;
+  int cur_sid;
+  int n_touched;
+  unsigned long long seg_t0;  // globaltimer at segment start
+  long long n_origins, n_overlaps;
+  int overflow;               // origins / overlaps / queue capacity exceeded
+  FfnCounters ctr;
+};
+
+enum Mode : int { MODE_PREDICT = 0, MODE_UPDATE_AT = 1, MODE_SEGMENT = 2 };
+enum Action : int { ACT_EXIT = 0, ACT_STEP, ACT_CLEAR, ACT_COUNT, ACT_WRITE };
+
+struct Job {
+  int mode;
+  // predict
+  const float* in_seed;
+  const float* in_image;
+  float* out_logits;
+  int batch;
+  // update_at
+  int pos[3];
+  float* pred_out;
+  // segment
+  long long step_budget;
+  const int* seeds;
+  long long n_seeds;
+  FfnOrigin* origins;
+  long long origins_cap;
+  FfnOverlap* overlaps;
+  long long overlaps_cap;
+  int* ovl_count;      // [ovl_ids]
+  int* ovl_touched;    // [ovl_ids]
+  int ovl_ids;
+  int* action;         // broadcast slot written by the leader
+};
+
+struct KParams {
+  Geom g;
+  Weights w;
+  Workspace ws;
+  CanvasDev cv;
+  CanvasState* st;
+  Job job;
+  int compute_mode;
+  int act_smem_bytes;   // 3 * 4 * seg_rows_max * 16
+};
+
+// Shared-memory carve-up (bytes from the 1024-aligned base).
+struct SmemLayout {
+  int wbuf;        // tc: 2 x 55296 ; fp32: 1 x 110592
+  int act;         // tc activation segments
+  int bias;        // (nconv + 1) * 32 floats + 4
+  int bars;        // mbarriers + scalars
+  int total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(const Geom& g) {
+  SmemLayout s;
+  s.wbuf = 0;
+  s.act = 2 * 27 * 4 * 512;   // 110592
+  const int seg_rows = kGroupTiles * kTileM + 2 * g.halo;
+  const int act_bytes = 3 * 4 * seg_rows * 16;
+  s.bias = s.act + act_bytes;
+  s.bars = s.bias + (kMaxConv + 1) * 32 * 4 + 16;
+  s.total = s.bars + 512;
+  return s;
+}
+
+__host__ __device__ inline size_t w16_layer_offset_halfs(int layer) {
+  return layer == 0 ? 0 : (size_t)27 * 2 * 256 + (size_t)(layer - 1) * 27 * 4 * 256;
+}
+__host__ __device__ inline size_t w32_layer_offset_floats(int layer) {
+  return layer == 0 ? 0 : (size_t)27 * 4 * 32 + (size_t)(layer - 1) * 27 * 32 * 32;
+}
+
+}  // namespace ffn

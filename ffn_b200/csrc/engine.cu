@@ -1,0 +1,828 @@
+// engine.cu — host side of libffn_b200.so: device context, weight packing, canvases, launches,
+// and the extern "C" entry points declared in include/ffn_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "device_types.cuh"
+#include "flood_kernel.cuh"
+#include "selftest.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const std::string& msg) {
+  g_error = msg;
+  return 1;
+}
+
+#define CUDA_OK(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                  std::to_string(__LINE__) + ")");                                             \
+  } while (0)
+
+template <typename T>
+int dev_alloc(T** p, size_t n, bool zero = true) {
+  CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)));
+  if (zero) CUDA_OK(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  return 0;
+}
+
+}  // namespace
+
+struct FfnEngine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 0;
+  int grid = 0;
+  int smem_bytes = 0;
+  int compute_mode = FFN_COMPUTE_FP16_TC;
+  ffn::Geom g{};
+  ffn::Weights w{};
+  ffn::Workspace ws{};
+  int* d_action = nullptr;
+  ffn::CanvasState* d_dummy_state = nullptr;
+  // predict staging
+  float* d_in_seed = nullptr;
+  float* d_in_image = nullptr;
+  float* d_out = nullptr;
+  int predict_cap = 0;
+  std::vector<void*> owned;
+  double last_kernel_seconds = 0.0;
+  long long launches = 0;
+};
+
+struct FfnCanvas {
+  FfnEngine* eng = nullptr;
+  ffn::CanvasDev cv{};
+  ffn::CanvasState* d_state = nullptr;
+  ffn::CanvasState h_state{};
+  void* d_image = nullptr;
+  uint8_t* d_mask = nullptr;
+  uint8_t* d_seed_mask = nullptr;
+  float* d_pred = nullptr;
+  size_t nvox = 0;
+  size_t lattice_cells = 0;
+};
+
+namespace {
+
+using namespace ffn;
+
+int set_device(const FfnEngine* e) {
+  CUDA_OK(cudaSetDevice(e->device));
+  return 0;
+}
+
+Geom make_geom(const FfnModelDesc& m) {
+  Geom g{};
+  g.fz = m.fov_zyx[0];
+  g.fy = m.fov_zyx[1];
+  g.fx = m.fov_zyx[2];
+  g.mz = g.fz / 2;
+  g.my = g.fy / 2;
+  g.mx = g.fx / 2;
+  g.dz = m.deltas_zyx[0];
+  g.dy = m.deltas_zyx[1];
+  g.dx = m.deltas_zyx[2];
+  g.nconv = 2 * m.depth;
+  g.xp = g.fx + 1;
+  g.pp = (g.fy + 1) * g.xp;
+  g.nr = (g.fz - 1) * g.pp + (g.fy - 1) * g.xp + g.fx;
+  g.nt = (g.nr + kTileM - 1) / kTileM;
+  g.halo = g.xp + 1;
+  g.guard = ((g.pp + g.halo + 7) / 8) * 8;
+  g.rows_alloc = g.guard + g.nt * kTileM + g.guard;
+  g.V = g.fz * g.fy * g.fx;
+  return g;
+}
+
+// Launches the persistent kernel once and waits for it.
+int launch(FfnEngine* e, const CanvasDev& cv, CanvasState* d_state, const Job& job) {
+  KParams p{};
+  p.g = e->g;
+  p.w = e->w;
+  p.ws = e->ws;
+  p.cv = cv;
+  p.st = d_state ? d_state : e->d_dummy_state;
+  p.job = job;
+  p.job.action = e->d_action;
+  p.compute_mode = e->compute_mode;
+  CUDA_OK(cudaMemsetAsync(e->ws.bar, 0, sizeof(unsigned), e->stream));
+  CUDA_OK(cudaMemsetAsync(e->ws.abort_flag, 0, sizeof(int), e->stream));
+  CUDA_OK(cudaMemsetAsync(e->d_action, 0, sizeof(int), e->stream));
+  void* args[] = {&p};
+  CUDA_OK(cudaEventRecord(e->ev0, e->stream));
+  CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(ffn_flood_kernel), dim3(e->grid),
+                                      dim3(kThreads), args, (size_t)e->smem_bytes, e->stream));
+  CUDA_OK(cudaEventRecord(e->ev1, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->last_kernel_seconds = ms * 1e-3;
+  e->launches++;
+  int abort_flag = 0;
+  CUDA_OK(cudaMemcpy(&abort_flag, e->ws.abort_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (abort_flag != 0)
+    return fail("device-side wait timed out (abort code " + std::to_string(abort_flag) +
+                "): 1 = grid barrier, 2 = mbarrier");
+  return 0;
+}
+
+int pull_state(FfnCanvas* c) {
+  CUDA_OK(cudaMemcpy(&c->h_state, c->d_state, sizeof(CanvasState), cudaMemcpyDeviceToHost));
+  return 0;
+}
+int push_state(FfnCanvas* c) {
+  CUDA_OK(cudaMemcpy(c->d_state, &c->h_state, sizeof(CanvasState), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void pack_weights(const Geom& g, const float* const* w, std::vector<__half>& w16, std::vector<float>& w32) {
+  const int nconv = g.nconv;
+  w16.assign(w16_layer_offset_halfs(nconv), __float2half(0.f));
+  w32.assign(w32_layer_offset_floats(nconv), 0.f);
+  for (int l = 0; l < nconv; ++l) {
+    const int cin = l == 0 ? 2 : 32;
+    const int nch = l == 0 ? 2 : 4;
+    const int cin_pad = l == 0 ? 4 : 32;
+    __half* d16 = w16.data() + w16_layer_offset_halfs(l);
+    float* d32 = w32.data() + w32_layer_offset_floats(l);
+    for (int tap = 0; tap < 27; ++tap)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < 32; ++co) {
+          const float v = w[l][((size_t)tap * cin + ci) * 32 + co];   // DHWIO: tap = kz*9 + ky*3 + kx
+          d16[(((size_t)tap * nch + ci / 8) * 4 + co / 8) * 64 + (co % 8) * 8 + (ci % 8)] = __float2half_rn(v);
+          d32[((size_t)tap * cin_pad + ci) * 32 + co] = v;
+        }
+  }
+}
+
+int box_copy(FfnCanvas* c, int which, const int32_t lo[3], const int32_t sz[3], void* host, bool to_host) {
+  const CanvasDev& cv = c->cv;
+  for (int k = 0; k < 3; ++k) {
+    const int dim = k == 0 ? cv.sz : k == 1 ? cv.sy : cv.sx;
+    if (lo[k] < 0 || sz[k] <= 0 || lo[k] + sz[k] > dim) return fail("box out of canvas bounds");
+  }
+  size_t esz = 0;
+  char* base = nullptr;
+  switch (which) {
+    case FFN_ARRAY_SEED: esz = 4; base = reinterpret_cast<char*>(cv.seed); break;
+    case FFN_ARRAY_SEGMENTATION: esz = 4; base = reinterpret_cast<char*>(cv.seg); break;
+    case FFN_ARRAY_QPROB:
+      if (!cv.qprob) return fail("canvas was created without probability maps");
+      esz = 1; base = reinterpret_cast<char*>(cv.qprob); break;
+    default: return fail("unknown array id");
+  }
+  cudaMemcpy3DParms prm{};
+  cudaPitchedPtr dev = make_cudaPitchedPtr(base, (size_t)cv.sx * esz, (size_t)cv.sx * esz, cv.sy);
+  cudaPitchedPtr hst = make_cudaPitchedPtr(host, (size_t)sz[2] * esz, (size_t)sz[2] * esz, sz[1]);
+  prm.extent = make_cudaExtent((size_t)sz[2] * esz, sz[1], sz[0]);
+  if (to_host) {
+    prm.srcPtr = dev;
+    prm.srcPos = make_cudaPos((size_t)lo[2] * esz, lo[1], lo[0]);
+    prm.dstPtr = hst;
+    prm.kind = cudaMemcpyDeviceToHost;
+  } else {
+    prm.dstPtr = dev;
+    prm.dstPos = make_cudaPos((size_t)lo[2] * esz, lo[1], lo[0]);
+    prm.srcPtr = hst;
+    prm.kind = cudaMemcpyHostToDevice;
+  }
+  CUDA_OK(cudaMemcpy3D(&prm));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ffn_last_error(void) { return g_error.c_str(); }
+
+int ffn_engine_create(int device, const FfnModelDesc* model, const float* const* weights_dhwio,
+                      const float* const* biases, int compute_mode, FfnEngine** out) {
+  if (!model || !weights_dhwio || !biases || !out) return fail("null argument");
+  if (model->features != kFeat) return fail("only 32 feature maps are supported");
+  if (model->depth < 1 || 2 * model->depth > kMaxConv) return fail("unsupported depth");
+  for (int k = 0; k < 3; ++k) {
+    if (model->fov_zyx[k] < 3 || model->fov_zyx[k] % 2 == 0) return fail("fov sizes must be odd and >= 3");
+    if (model->deltas_zyx[k] < 0 || model->deltas_zyx[k] > model->fov_zyx[k] / 2)
+      return fail("deltas must lie in [0, fov // 2]");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: libffn_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail("bad device index");
+  cudaDeviceProp prop{};
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                "; this library only contains sm_100a code");
+  std::unique_ptr<FfnEngine> e(new FfnEngine());
+  e->device = device;
+  CUDA_OK(cudaSetDevice(device));
+  CUDA_OK(cudaStreamCreate(&e->stream));   // blocking: ordered after legacy-stream memcpys
+  CUDA_OK(cudaEventCreate(&e->ev0));
+  CUDA_OK(cudaEventCreate(&e->ev1));
+  e->sm_count = prop.multiProcessorCount;
+  e->compute_mode = compute_mode;
+  e->g = make_geom(*model);
+  const Geom& g = e->g;
+  const SmemLayout L = smem_layout(g);
+  e->smem_bytes = L.total;
+  if ((size_t)L.total > prop.sharedMemPerBlockOptin)
+    return fail("field of view too large for the shared-memory operand staging");
+  CUDA_OK(cudaFuncSetAttribute(ffn_flood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  int per_sm = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffn_flood_kernel, kThreads, L.total));
+  if (per_sm < 1) return fail("persistent kernel does not fit on an SM");
+  e->grid = std::min(e->sm_count, g.nt);
+
+  // weights
+  std::vector<__half> w16;
+  std::vector<float> w32;
+  pack_weights(g, weights_dhwio, w16, w32);
+  __half* d_w16 = nullptr;
+  float *d_w32 = nullptr, *d_bias = nullptr, *d_wlom = nullptr;
+  if (dev_alloc(&d_w16, w16.size())) return 1;
+  if (dev_alloc(&d_w32, w32.size())) return 1;
+  if (dev_alloc(&d_bias, (size_t)g.nconv * 32)) return 1;
+  if (dev_alloc(&d_wlom, 32)) return 1;
+  CUDA_OK(cudaMemcpy(d_w16, w16.data(), w16.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d_w32, w32.data(), w32.size() * sizeof(float), cudaMemcpyHostToDevice));
+  std::vector<float> hb((size_t)g.nconv * 32);
+  for (int l = 0; l < g.nconv; ++l) std::memcpy(&hb[(size_t)l * 32], biases[l], 32 * sizeof(float));
+  CUDA_OK(cudaMemcpy(d_bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d_wlom, weights_dhwio[g.nconv], 32 * sizeof(float), cudaMemcpyHostToDevice));
+  e->w.w16 = d_w16;
+  e->w.w32 = d_w32;
+  e->w.bias = d_bias;
+  e->w.w_lom = d_wlom;
+  e->w.b_lom = biases[g.nconv][0];
+  e->owned = {d_w16, d_w32, d_bias, d_wlom};
+
+  // workspace (all buffers zero-initialised: pad rows / guards must stay zero forever)
+  Workspace& ws = e->ws;
+  const size_t ra = (size_t)g.rows_alloc;
+  if (dev_alloc(&ws.act0_h, 2 * ra * 8)) return 1;
+  if (dev_alloc(&ws.act_h[0], 4 * ra * 8)) return 1;
+  if (dev_alloc(&ws.act_h[1], 4 * ra * 8)) return 1;
+  if (dev_alloc(&ws.act0_f, ra)) return 1;
+  if (dev_alloc(&ws.act_f[0], 8 * ra)) return 1;
+  if (dev_alloc(&ws.act_f[1], 8 * ra)) return 1;
+  if (dev_alloc(&ws.res, 8 * ra)) return 1;
+  if (dev_alloc(&ws.seed_raw, (size_t)g.nt * kTileM)) return 1;
+  if (dev_alloc(&ws.logits, (size_t)g.nt * kTileM)) return 1;
+  if (dev_alloc(&ws.bar, 1)) return 1;
+  if (dev_alloc(&ws.count, 1)) return 1;
+  if (dev_alloc(&ws.abort_flag, 1)) return 1;
+  if (dev_alloc(&e->d_action, 1)) return 1;
+  if (dev_alloc(&e->d_dummy_state, 1)) return 1;
+  for (void* p : std::vector<void*>{ws.act0_h, ws.act_h[0], ws.act_h[1], ws.act0_f, ws.act_f[0], ws.act_f[1],
+                                    ws.res, ws.seed_raw, ws.logits, ws.bar, ws.count, ws.abort_flag,
+                                    e->d_action, e->d_dummy_state})
+    e->owned.push_back(p);
+  *out = e.release();
+  return 0;
+}
+
+void ffn_engine_destroy(FfnEngine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (void* p : e->owned) cudaFree(p);
+  cudaFree(e->d_in_seed);
+  cudaFree(e->d_in_image);
+  cudaFree(e->d_out);
+  cudaEventDestroy(e->ev0);
+  cudaEventDestroy(e->ev1);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int ffn_engine_set_compute_mode(FfnEngine* e, int mode) {
+  if (!e) return fail("null engine");
+  if (mode != FFN_COMPUTE_FP16_TC && mode != FFN_COMPUTE_FP32) return fail("unknown compute mode");
+  e->compute_mode = mode;
+  return 0;
+}
+
+int ffn_engine_info(FfnEngine* e, int64_t info[8]) {
+  if (!e || !info) return fail("null argument");
+  info[0] = e->sm_count;
+  info[1] = e->grid;
+  info[2] = e->smem_bytes;
+  info[3] = e->g.nt;
+  info[4] = e->g.nr;
+  info[5] = e->g.V;
+  info[6] = e->launches;
+  info[7] = (int64_t)(e->last_kernel_seconds * 1e9);
+  return 0;
+}
+
+int ffn_predict(FfnEngine* e, const float* seed, const float* image, int batch, float* logits_out) {
+  if (!e || !seed || !image || !logits_out || batch < 1) return fail("bad argument");
+  if (set_device(e)) return 1;
+  const size_t n = (size_t)batch * e->g.V;
+  if (batch > e->predict_cap) {
+    cudaFree(e->d_in_seed);
+    cudaFree(e->d_in_image);
+    cudaFree(e->d_out);
+    e->d_in_seed = e->d_in_image = e->d_out = nullptr;
+    if (dev_alloc(&e->d_in_seed, n, false)) return 1;
+    if (dev_alloc(&e->d_in_image, n, false)) return 1;
+    if (dev_alloc(&e->d_out, n, false)) return 1;
+    e->predict_cap = batch;
+  }
+  CUDA_OK(cudaMemcpyAsync(e->d_in_seed, seed, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  CUDA_OK(cudaMemcpyAsync(e->d_in_image, image, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  Job job{};
+  job.mode = MODE_PREDICT;
+  job.in_seed = e->d_in_seed;
+  job.in_image = e->d_in_image;
+  job.out_logits = e->d_out;
+  job.batch = batch;
+  CanvasDev cv{};
+  if (launch(e, cv, nullptr, job)) return 1;
+  CUDA_OK(cudaMemcpy(logits_out, e->d_out, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int ffn_canvas_create(FfnEngine* e, const void* image, int image_dtype, const int32_t shape_zyx[3],
+                      float image_mean, float image_stddev, const FfnOptions* options,
+                      int keep_probability_maps, FfnCanvas** out) {
+  if (!e || !image || !shape_zyx || !options || !out) return fail("null argument");
+  if (image_dtype != FFN_IMAGE_U8 && image_dtype != FFN_IMAGE_F32) return fail("unknown image dtype");
+  if (set_device(e)) return 1;
+  const Geom& g = e->g;
+  for (int k = 0; k < 3; ++k)
+    if (shape_zyx[k] < 1) return fail("bad canvas shape");
+  if ((size_t)shape_zyx[0] * shape_zyx[1] * shape_zyx[2] > (size_t)1 << 33) return fail("canvas too large");
+  std::unique_ptr<FfnCanvas> c(new FfnCanvas());
+  c->eng = e;
+  CanvasDev& cv = c->cv;
+  cv.sz = shape_zyx[0];
+  cv.sy = shape_zyx[1];
+  cv.sx = shape_zyx[2];
+  c->nvox = (size_t)cv.sz * cv.sy * cv.sx;
+  cv.opt = *options;
+  {
+    // smallest float32 >= the float64 policy threshold: `score < th64` (float64 compare of a
+    // float32 score, movement.py:84) <=> `score < th32` in float32.
+    float t = (float)options->policy_score_threshold;
+    if ((double)t < options->policy_score_threshold) t = std::nextafterf(t, INFINITY);
+    cv.policy_th_f32 = t;
+  }
+  cv.image_is_u8 = image_dtype == FFN_IMAGE_U8;
+  cv.mean = image_mean;
+  cv.stddev = image_stddev;
+  const size_t ibytes = c->nvox * (cv.image_is_u8 ? 1 : 4);
+  CUDA_OK(cudaMalloc(&c->d_image, ibytes));
+  CUDA_OK(cudaMemcpy(c->d_image, image, ibytes, cudaMemcpyHostToDevice));
+  cv.image = c->d_image;
+  if (dev_alloc(&cv.seed, c->nvox, false)) return 1;
+  if (dev_alloc(&cv.seg, c->nvox)) return 1;
+  if (keep_probability_maps) {
+    if (dev_alloc(&cv.qprob, c->nvox)) return 1;
+  }
+  fill_f32_kernel<<<e->sm_count * 8, 256, 0, e->stream>>>(cv.seed, c->nvox, NAN);
+  CUDA_OK(cudaGetLastError());
+  // movement policy storage
+  const int del[3] = {std::max(g.dz, 1), std::max(g.dy, 1), std::max(g.dx, 1)};
+  const int shp[3] = {cv.sz, cv.sy, cv.sx};
+  size_t cells = 1, qcells = 1;
+  for (int k = 0; k < 3; ++k) {
+    const int n = (shp[k] + del[k] - 1) / del[k];
+    cv.lat_off[k] = n + 1;
+    cv.lat_dim[k] = 2 * n + 3;
+    cells *= (size_t)cv.lat_dim[k];
+    qcells *= (size_t)(n + 2);
+  }
+  c->lattice_cells = cells;
+  if (dev_alloc(&cv.lattice, cells)) return 1;
+  const size_t qcap = std::min<size_t>(6 * qcells + 16, (size_t)1 << 30);
+  cv.q_cap = (int)qcap;
+  if (dev_alloc(&cv.q_score, qcap, false)) return 1;
+  if (dev_alloc(&cv.q_pos, qcap * 3, false)) return 1;
+  if (dev_alloc(&c->d_state, 1)) return 1;
+  if (dev_alloc(&c->d_pred, (size_t)g.V, false)) return 1;
+  std::memset(&c->h_state, 0, sizeof(CanvasState));
+  for (int k = 0; k < 3; ++k) {   // nothing dirty yet
+    c->h_state.dirty_lo[k] = 0;
+    c->h_state.dirty_hi[k] = 0;
+  }
+  if (push_state(c.get())) return 1;
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  *out = c.release();
+  return 0;
+}
+
+void ffn_canvas_destroy(FfnCanvas* c) {
+  if (!c) return;
+  cudaSetDevice(c->eng->device);
+  cudaFree(c->d_image);
+  cudaFree(c->cv.seed);
+  cudaFree(c->cv.seg);
+  cudaFree(c->cv.qprob);
+  cudaFree(c->cv.lattice);
+  cudaFree(c->cv.q_score);
+  cudaFree(c->cv.q_pos);
+  cudaFree(c->d_state);
+  cudaFree(c->d_pred);
+  cudaFree(c->d_mask);
+  cudaFree(c->d_seed_mask);
+  delete c;
+}
+
+int ffn_canvas_set_mask(FfnCanvas* c, int which, const uint8_t* mask) {
+  if (!c) return fail("null canvas");
+  if (set_device(c->eng)) return 1;
+  uint8_t** slot = which == FFN_MASK_MOVEMENT ? &c->d_mask : which == FFN_MASK_SEED ? &c->d_seed_mask : nullptr;
+  if (!slot) return fail("unknown mask id");
+  if (!mask) {
+    cudaFree(*slot);
+    *slot = nullptr;
+  } else {
+    if (!*slot) CUDA_OK(cudaMalloc(reinterpret_cast<void**>(slot), c->nvox));
+    CUDA_OK(cudaMemcpy(*slot, mask, c->nvox, cudaMemcpyHostToDevice));
+  }
+  c->cv.mask = c->d_mask;
+  c->cv.seed_mask = c->d_seed_mask;
+  return 0;
+}
+
+int ffn_canvas_init_seed(FfnCanvas* c, const int32_t pos[3]) {
+  if (!c || !pos) return fail("null argument");
+  if (set_device(c->eng)) return 1;
+  if (pos[0] < 0 || pos[1] < 0 || pos[2] < 0 || pos[0] >= c->cv.sz || pos[1] >= c->cv.sy || pos[2] >= c->cv.sx)
+    return fail("seed position outside the canvas");
+  if (pull_state(c)) return 1;
+  CanvasState& st = c->h_state;
+  // clear only what can be non-NaN (== NumpyArray.clear), then place the seed
+  for (int z = std::max(st.dirty_lo[0], 0); z < std::min(st.dirty_hi[0], c->cv.sz); ++z)
+    for (int y = std::max(st.dirty_lo[1], 0); y < std::min(st.dirty_hi[1], c->cv.sy); ++y) {
+      const int x0 = std::max(st.dirty_lo[2], 0), x1 = std::min(st.dirty_hi[2], c->cv.sx);
+      if (x1 > x0) {
+        fill_f32_kernel<<<1, 128, 0, c->eng->stream>>>(c->cv.seed + ((size_t)z * c->cv.sy + y) * c->cv.sx + x0,
+                                                       (size_t)(x1 - x0), NAN);
+      }
+    }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(c->cv.seed + ((size_t)pos[0] * c->cv.sy + pos[1]) * c->cv.sx + pos[2],
+                          &c->cv.opt.init_activation, sizeof(float), cudaMemcpyHostToDevice, c->eng->stream));
+  CUDA_OK(cudaStreamSynchronize(c->eng->stream));
+  for (int k = 0; k < 3; ++k) {
+    st.dirty_lo[k] = pos[k];
+    st.dirty_hi[k] = pos[k] + 1;
+  }
+  return push_state(c);
+}
+
+int ffn_canvas_segment_at(FfnCanvas* c, const int32_t start[3], int reset, int64_t max_steps, FfnSegStats* out) {
+  if (!c || !start || !out) return fail("null argument");
+  FfnEngine* e = c->eng;
+  if (set_device(e)) return 1;
+  if (start[0] < 0 || start[1] < 0 || start[2] < 0 || start[0] >= c->cv.sz || start[1] >= c->cv.sy ||
+      start[2] >= c->cv.sx)
+    return fail("start position outside the canvas");
+  if (pull_state(c)) return 1;
+  CanvasState& st = c->h_state;
+  st.seg_all = 0;
+  const long long steps0 = st.ctr.inference_calls;
+  const long long weak0 = st.ctr.seed_got_too_weak;
+  if (reset) {
+    for (int k = 0; k < 3; ++k) st.start[k] = start[k];
+    st.reset_seed = 1;
+    st.phase = PH_START_SEGMENT;
+  } else {
+    if (st.phase != PH_POP) return fail("no object in flight to resume");
+  }
+  if (push_state(c)) return 1;
+  Job job{};
+  job.mode = MODE_SEGMENT;
+  double secs = 0;
+  for (;;) {
+    const long long done = st.ctr.inference_calls - steps0;
+    long long chunk = 1 << 15;
+    if (max_steps > 0) chunk = std::min<long long>(chunk, max_steps - done);
+    job.step_budget = st.ctr.inference_calls + chunk;
+    if (launch(e, c->cv, c->d_state, job)) return 1;
+    secs += e->last_kernel_seconds;
+    if (pull_state(c)) return 1;
+    if (st.phase == PH_SEGMENT_DONE) break;
+    if (st.phase != PH_POP) return fail("unexpected device phase " + std::to_string(st.phase));
+    if (max_steps > 0 && st.ctr.inference_calls - steps0 >= max_steps) break;
+  }
+  if (st.overflow) return fail("movement queue capacity exceeded");
+  out->iters = st.iters;
+  for (int k = 0; k < 3; ++k) {
+    out->min_pos[k] = st.min_pos[k];
+    out->max_pos[k] = st.max_pos[k];
+  }
+  out->seed_got_too_weak = (int)(st.ctr.seed_got_too_weak - weak0);
+  out->queue_len = st.q_tail - st.q_head;
+  out->finished = st.phase == PH_SEGMENT_DONE;
+  out->reserved = 0;
+  st.ctr.device_seconds += secs;
+  return push_state(c);
+}
+
+int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, FfnOrigin* origins_out,
+                           int64_t origins_cap, int64_t* n_origins, FfnOverlap* overlaps_out,
+                           int64_t overlaps_cap, int64_t* n_overlaps, FfnCounters* counters_out) {
+  if (!c || (n_seeds > 0 && !seeds) || !n_origins || !n_overlaps) return fail("null argument");
+  FfnEngine* e = c->eng;
+  if (set_device(e)) return 1;
+  if (pull_state(c)) return 1;
+  CanvasState& st = c->h_state;
+  int* d_seeds = nullptr;
+  FfnOrigin* d_orig = nullptr;
+  FfnOverlap* d_ovl = nullptr;
+  int *d_cnt = nullptr, *d_touched = nullptr;
+  const int ovl_ids = (int)std::min<int64_t>((int64_t)st.max_id + n_seeds + 2, (int64_t)1 << 30);
+  auto cleanup = [&]() {
+    cudaFree(d_seeds);
+    cudaFree(d_orig);
+    cudaFree(d_ovl);
+    cudaFree(d_cnt);
+    cudaFree(d_touched);
+  };
+  if (dev_alloc(&d_seeds, (size_t)n_seeds * 3, false) || dev_alloc(&d_orig, (size_t)origins_cap, false) ||
+      dev_alloc(&d_ovl, (size_t)overlaps_cap, false) || dev_alloc(&d_cnt, (size_t)ovl_ids) ||
+      dev_alloc(&d_touched, (size_t)ovl_ids)) {
+    cleanup();
+    return 1;
+  }
+  if (n_seeds) CUDA_OK(cudaMemcpy(d_seeds, seeds, (size_t)n_seeds * 3 * sizeof(int), cudaMemcpyHostToDevice));
+  st.seg_all = 1;
+  st.seed_idx = 0;
+  st.n_origins = st.n_overlaps = 0;
+  st.overflow = 0;
+  st.phase = PH_NEXT_SEED;
+  const FfnCounters before = st.ctr;
+  if (push_state(c)) {
+    cleanup();
+    return 1;
+  }
+  Job job{};
+  job.mode = MODE_SEGMENT;
+  job.seeds = d_seeds;
+  job.n_seeds = n_seeds;
+  job.origins = d_orig;
+  job.origins_cap = origins_cap;
+  job.overlaps = d_ovl;
+  job.overlaps_cap = overlaps_cap;
+  job.ovl_count = d_cnt;
+  job.ovl_touched = d_touched;
+  job.ovl_ids = ovl_ids;
+  double secs = 0;
+  long long launches = 0;
+  for (;;) {
+    job.step_budget = st.ctr.inference_calls + (1 << 15);
+    if (launch(e, c->cv, c->d_state, job)) {
+      cleanup();
+      return 1;
+    }
+    secs += e->last_kernel_seconds;
+    ++launches;
+    if (pull_state(c)) {
+      cleanup();
+      return 1;
+    }
+    if (st.phase == PH_ALL_DONE) break;
+    if (st.phase != PH_POP) {
+      cleanup();
+      return fail("unexpected device phase " + std::to_string(st.phase));
+    }
+  }
+  *n_origins = st.n_origins;
+  *n_overlaps = st.n_overlaps;
+  int rc = 0;
+  if (st.overflow & 1) rc = fail("movement queue capacity exceeded");
+  if (!rc && origins_out && st.n_origins)
+    if (cudaMemcpy(origins_out, d_orig, (size_t)std::min<long long>(st.n_origins, origins_cap) * sizeof(FfnOrigin),
+                   cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = fail("origins copy failed");
+  if (!rc && overlaps_out && st.n_overlaps)
+    if (cudaMemcpy(overlaps_out, d_ovl, (size_t)std::min<long long>(st.n_overlaps, overlaps_cap) * sizeof(FfnOverlap),
+                   cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = fail("overlaps copy failed");
+  cleanup();
+  st.ctr.device_seconds += secs;
+  st.ctr.kernel_launches += launches;
+  st.phase = PH_IDLE;
+  if (counters_out) {
+    *counters_out = st.ctr;
+    (void)before;
+  }
+  if (push_state(c)) return 1;
+  return rc;
+}
+
+int ffn_canvas_update_at(FfnCanvas* c, const int32_t pos[3], float* pred_out) {
+  if (!c || !pos) return fail("null argument");
+  FfnEngine* e = c->eng;
+  if (set_device(e)) return 1;
+  const Geom& g = e->g;
+  if (pos[0] - g.mz < 0 || pos[1] - g.my < 0 || pos[2] - g.mx < 0 || pos[0] + g.mz >= c->cv.sz ||
+      pos[1] + g.my >= c->cv.sy || pos[2] + g.mx >= c->cv.sx)
+    return fail("field of view leaves the canvas");
+  if (pull_state(c)) return 1;
+  CanvasState& st = c->h_state;
+  const int saved_phase = st.phase;
+  for (int k = 0; k < 3; ++k) st.cur[k] = pos[k];
+  st.phase = PH_FORCE_STEP;
+  if (push_state(c)) return 1;
+  Job job{};
+  job.mode = MODE_UPDATE_AT;
+  job.pred_out = c->d_pred;
+  if (launch(e, c->cv, c->d_state, job)) return 1;
+  if (pull_state(c)) return 1;
+  st.phase = saved_phase;
+  st.ctr.device_seconds += e->last_kernel_seconds;
+  if (push_state(c)) return 1;
+  if (pred_out) CUDA_OK(cudaMemcpy(pred_out, c->d_pred, (size_t)g.V * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int ffn_canvas_read(FfnCanvas* c, int which, const int32_t lo[3], const int32_t sz[3], void* dst) {
+  if (!c || !lo || !sz || !dst) return fail("null argument");
+  if (set_device(c->eng)) return 1;
+  if (which == FFN_ARRAY_IMAGE) {
+    // always float32, normalised like runner.py:383-385
+    const CanvasDev& cv = c->cv;
+    if (lo[0] != 0 || lo[1] != 0 || lo[2] != 0 || sz[0] != cv.sz || sz[1] != cv.sy || sz[2] != cv.sx)
+      return fail("image reads must cover the whole canvas");
+    if (!cv.image_is_u8) {
+      CUDA_OK(cudaMemcpy(dst, cv.image, c->nvox * 4, cudaMemcpyDeviceToHost));
+      return 0;
+    }
+    float* tmp = nullptr;
+    if (dev_alloc(&tmp, c->nvox, false)) return 1;
+    normalize_u8_kernel<<<c->eng->sm_count * 8, 256, 0, c->eng->stream>>>(
+        reinterpret_cast<const uint8_t*>(cv.image), tmp, c->nvox, cv.mean, cv.stddev);
+    cudaError_t err = cudaMemcpy(dst, tmp, c->nvox * 4, cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    if (err != cudaSuccess) return fail(cudaGetErrorString(err));
+    return 0;
+  }
+  return box_copy(c, which, lo, sz, dst, true);
+}
+
+int ffn_canvas_write(FfnCanvas* c, int which, const int32_t lo[3], const int32_t sz[3], const void* src) {
+  if (!c || !lo || !sz || !src) return fail("null argument");
+  if (set_device(c->eng)) return 1;
+  if (which == FFN_ARRAY_IMAGE) return fail("the image is immutable");
+  if (box_copy(c, which, lo, sz, const_cast<void*>(src), false)) return 1;
+  if (which == FFN_ARRAY_SEED) {
+    if (pull_state(c)) return 1;
+    CanvasState& st = c->h_state;
+    const bool empty = st.dirty_hi[0] <= st.dirty_lo[0];
+    for (int k = 0; k < 3; ++k) {
+      st.dirty_lo[k] = empty ? lo[k] : std::min(st.dirty_lo[k], lo[k]);
+      st.dirty_hi[k] = empty ? lo[k] + sz[k] : std::max(st.dirty_hi[k], lo[k] + sz[k]);
+    }
+    return push_state(c);
+  }
+  return 0;
+}
+
+int ffn_canvas_policy_state_size(FfnCanvas* c, int64_t* queue_len, int64_t* done_len) {
+  if (!c || !queue_len || !done_len) return fail("null argument");
+  if (set_device(c->eng)) return 1;
+  if (pull_state(c)) return 1;
+  *queue_len = c->h_state.q_tail - c->h_state.q_head;
+  std::vector<unsigned> lat(c->lattice_cells);
+  CUDA_OK(cudaMemcpy(lat.data(), c->cv.lattice, lat.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  int64_t n = 0;
+  if (c->h_state.epoch)
+    for (unsigned v : lat) n += v == c->h_state.epoch;
+  *done_len = n;
+  return 0;
+}
+
+int ffn_canvas_policy_state_get(FfnCanvas* c, double* queue_szyx, int32_t* done_zyx, int32_t start[3]) {
+  if (!c || !start) return fail("null argument");
+  if (set_device(c->eng)) return 1;
+  if (pull_state(c)) return 1;
+  const CanvasState& st = c->h_state;
+  const int n = st.q_tail - st.q_head;
+  if (n > 0 && queue_szyx) {
+    std::vector<float> sc(n);
+    std::vector<int> ps((size_t)n * 3);
+    CUDA_OK(cudaMemcpy(sc.data(), c->cv.q_score + st.q_head, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(ps.data(), c->cv.q_pos + (size_t)st.q_head * 3, (size_t)n * 3 * sizeof(int),
+                       cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+      queue_szyx[4 * i] = sc[i];
+      for (int k = 0; k < 3; ++k) queue_szyx[4 * i + 1 + k] = ps[3 * i + k];
+    }
+  }
+  if (done_zyx && st.epoch) {
+    std::vector<unsigned> lat(c->lattice_cells);
+    CUDA_OK(cudaMemcpy(lat.data(), c->cv.lattice, lat.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    size_t o = 0;
+    const int* d = c->cv.lat_dim;
+    for (size_t i = 0; i < lat.size(); ++i)
+      if (lat[i] == st.epoch) {
+        const int qx = (int)(i % d[2]), qy = (int)((i / d[2]) % d[1]), qz = (int)(i / ((size_t)d[1] * d[2]));
+        done_zyx[o++] = qz - c->cv.lat_off[0];
+        done_zyx[o++] = qy - c->cv.lat_off[1];
+        done_zyx[o++] = qx - c->cv.lat_off[2];
+      }
+  }
+  for (int k = 0; k < 3; ++k) start[k] = st.start[k];
+  return 0;
+}
+
+int ffn_canvas_policy_state_set(FfnCanvas* c, const double* queue_szyx, int64_t queue_len, const int32_t* done_zyx,
+                                int64_t done_len, const int32_t start[3]) {
+  if (!c || !start) return fail("null argument");
+  if (set_device(c->eng)) return 1;
+  if (queue_len > c->cv.q_cap) return fail("queue larger than device capacity");
+  if (pull_state(c)) return 1;
+  CanvasState& st = c->h_state;
+  st.epoch++;
+  st.q_head = 0;
+  st.q_tail = (int)queue_len;
+  for (int k = 0; k < 3; ++k) st.start[k] = start[k];
+  if (queue_len > 0) {
+    std::vector<float> sc(queue_len);
+    std::vector<int> ps((size_t)queue_len * 3);
+    for (int64_t i = 0; i < queue_len; ++i) {
+      sc[i] = (float)queue_szyx[4 * i];
+      for (int k = 0; k < 3; ++k) ps[3 * i + k] = (int)queue_szyx[4 * i + 1 + k];
+    }
+    CUDA_OK(cudaMemcpy(c->cv.q_score, sc.data(), sc.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->cv.q_pos, ps.data(), ps.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  const int* d = c->cv.lat_dim;
+  for (int64_t i = 0; i < done_len; ++i) {
+    const int qz = done_zyx[3 * i] + c->cv.lat_off[0], qy = done_zyx[3 * i + 1] + c->cv.lat_off[1],
+              qx = done_zyx[3 * i + 2] + c->cv.lat_off[2];
+    if (qz < 0 || qy < 0 || qx < 0 || qz >= d[0] || qy >= d[1] || qx >= d[2]) return fail("done-set entry outside lattice");
+    CUDA_OK(cudaMemcpy(c->cv.lattice + ((size_t)qz * d[1] + qy) * d[2] + qx, &st.epoch, sizeof(unsigned),
+                       cudaMemcpyHostToDevice));
+  }
+  st.phase = PH_POP;
+  st.have_cur = 0;
+  return push_state(c);
+}
+
+int ffn_canvas_set_max_id(FfnCanvas* c, int64_t max_id) {
+  if (!c) return fail("null canvas");
+  if (set_device(c->eng)) return 1;
+  if (pull_state(c)) return 1;
+  c->h_state.max_id = (int)max_id;
+  c->h_state.ctr.max_id = max_id;
+  return push_state(c);
+}
+
+int ffn_canvas_get_counters(FfnCanvas* c, FfnCounters* out) {
+  if (!c || !out) return fail("null argument");
+  if (set_device(c->eng)) return 1;
+  if (pull_state(c)) return 1;
+  *out = c->h_state.ctr;
+  out->max_id = c->h_state.max_id;
+  return 0;
+}
+
+int ffn_canvas_device_ptr(FfnCanvas* c, int which, void** ptr, int64_t* bytes) {
+  if (!c || !ptr || !bytes) return fail("null argument");
+  switch (which) {
+    case FFN_ARRAY_SEED: *ptr = c->cv.seed; *bytes = (int64_t)c->nvox * 4; return 0;
+    case FFN_ARRAY_SEGMENTATION: *ptr = c->cv.seg; *bytes = (int64_t)c->nvox * 4; return 0;
+    case FFN_ARRAY_QPROB:
+      if (!c->cv.qprob) return fail("canvas was created without probability maps");
+      *ptr = c->cv.qprob; *bytes = (int64_t)c->nvox; return 0;
+    case FFN_ARRAY_IMAGE: *ptr = c->d_image; *bytes = (int64_t)c->nvox * (c->cv.image_is_u8 ? 1 : 4); return 0;
+  }
+  return fail("unknown array id");
+}
+
+int ffn_canvas_add_id_offset(FfnCanvas* c, int32_t offset) {
+  if (!c) return fail("null canvas");
+  if (set_device(c->eng)) return 1;
+  relabel_offset_kernel<<<c->eng->sm_count * 8, 256, 0, c->eng->stream>>>(c->cv.seg, c->nvox, offset);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(c->eng->stream));
+  return 0;
+}
+
+int ffn_selftest_umma(int device, int variant, double* out, int n_out) {
+  if (!out || n_out < 8) return fail("need >= 8 output slots");
+  std::string err;
+  if (ffn::selftest::run(device, variant, out, n_out, &err)) return fail(err);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1073 @@
+// flood_kernel.cuh — the persistent flood-fill kernel.
+//
+// ONE cooperative launch runs whole objects (or a whole canvas): per FoV step it stages the
+// (image, seed) tile from the HBM-resident canvas, evaluates the residual conv stack with the
+// field of view spread over all CTAs (tcgen05 implicit GEMM, or fp32 FMA in the parity mode),
+// fuses bias / ReLU / residual / conv_lom / seed-add as epilogues, applies the disco merge,
+// pastes into the seed canvas, evaluates the face-max movement policy and pops the next position
+// from the device-side queue — without returning to the host.
+//
+// Reference semantics restated here (file:line in the reference checkout):
+//   stage        ffn/inference/inference.py:348-354 (_get_image), :399-407 (seed copy, NaN -> pad),
+//                ffn/inference/runner.py:383-385 (normalisation)
+//   network      ffn/training/models/convstack_3d.py:26-56, :83-95; ffn/training/model.py:168-183
+//   tail         ffn/inference/inference.py:416-439 (disco merge, paste)
+//   policy       ffn/inference/movement.py:42-100, :166-222
+//   validity     ffn/inference/inference.py:312-346
+//   object loop  ffn/inference/inference.py:460-533
+//   canvas loop  ffn/inference/inference.py:538-683; ffn/inference/storage.py:137-143
+#pragma once
+
+#include <math_constants.h>
+
+#include "device_types.cuh"
+#include "sm100.cuh"
+
+namespace ffn {
+
+// ------------------------------------------------------------------------------------------
+// Per-CTA context
+// ------------------------------------------------------------------------------------------
+struct Ctx {
+  const KParams* p;
+  int tid, warp, lane, cta, G;
+  int t_begin, t_end;          // tiles owned by this CTA
+  unsigned bar_target;
+  unsigned char* smem;
+  float* s_bias;               // [(nconv)*32] biases, then w_lom[32], b_lom
+  uint64_t* mb_w;              // [2]
+  uint64_t* mb_act;            // [1]
+  uint64_t* mb_mma;            // [kGroupTiles]
+  uint32_t* s_tmem;            // TMEM base address
+  int* s_misc;                 // [0] step count>=th accumulator, [1..] leader scratch
+  uint32_t par_w[2], par_act, par_mma[kGroupTiles];
+  int w_pending[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ bool aborted(const Ctx& c) {
+  return sm100::ld_volatile_s32(c.p->ws.abort_flag) != 0;
+}
+
+// Bounded spin on an mbarrier phase; a timeout raises the abort flag instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(const Ctx& c, uint64_t* bar, uint32_t parity) {
+  if (sm100::mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while (!sm100::mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FF) == 0) {
+      if (aborted(c)) return;
+      if (clock64() - t0 > (1ll << 32)) {   // ~2 s
+        atomicExch(c.p->ws.abort_flag, 2);
+        return;
+      }
+    }
+  }
+}
+
+// Grid-wide barrier (all CTAs are co-resident: cooperative launch, one CTA per SM).
+__device__ __forceinline__ void grid_barrier(Ctx& c) {
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (c.tid == 0) {
+    c.bar_target += c.G;
+    __threadfence();
+    atomicAdd(c.p->ws.bar, 1u);
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (sm100::ld_acquire_u32(c.p->ws.bar) < c.bar_target) {
+      if ((++spins & 0xFF) == 0) {
+        if (aborted(c)) break;
+        if (clock64() - t0 > (1ll << 32)) {
+          atomicExch(c.p->ws.abort_flag, 1);
+          break;
+        }
+      }
+    }
+    __threadfence();
+    sm100::fence_proxy_async();   // later TMA reads must see what other CTAs wrote
+  }
+  __syncthreads();
+  sm100::tc_fence_after();
+}
+
+// row -> (z, y, x); false for the zero pad column / pad line / rows past the FoV.
+__device__ __forceinline__ bool row_to_zyx(const Geom& g, int r, int& z, int& y, int& x) {
+  if (r >= g.nr) return false;
+  z = r / g.pp;
+  const int rem = r - z * g.pp;
+  y = rem / g.xp;
+  x = rem - y * g.xp;
+  return y < g.fy && x < g.fx;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage: canvas (or host-provided patch) -> layer-0 operands + raw seed copy
+// ------------------------------------------------------------------------------------------
+__device__ void stage_fov(Ctx& c, int pz, int py, int px, int batch_idx) {
+  const KParams& p = *c.p;
+  const Geom& g = p.g;
+  const bool predict = p.job.mode == MODE_PREDICT;
+  for (int r = c.t_begin * kTileM + c.tid; r < c.t_end * kTileM; r += kThreads) {
+    int z, y, x;
+    if (!row_to_zyx(g, r, z, y, x)) continue;
+    float img, s, fed;
+    if (predict) {
+      const size_t i = (size_t)batch_idx * g.V + ((size_t)z * g.fy + y) * g.fx + x;
+      img = __ldg(p.job.in_image + i);
+      s = __ldg(p.job.in_seed + i);
+      fed = s;
+    } else {
+      const size_t i =
+          ((size_t)(pz - g.mz + z) * p.cv.sy + (py - g.my + y)) * p.cv.sx + (px - g.mx + x);
+      if (p.cv.image_is_u8) {
+        const float raw = (float)__ldg(reinterpret_cast<const uint8_t*>(p.cv.image) + i);
+        img = __fdiv_rn(__fsub_rn(raw, p.cv.mean), p.cv.stddev);
+      } else {
+        img = __ldg(reinterpret_cast<const float*>(p.cv.image) + i);
+      }
+      s = __ldcg(p.cv.seed + i);
+      fed = isnan(s) ? p.cv.opt.pad_value : s;
+    }
+    p.ws.seed_raw[r] = predict ? fed : s;
+    if (p.compute_mode == FFN_COMPUTE_FP16_TC) {
+      const __half2 h01 = __floats2half2_rn(img, fed);
+      uint4 v;
+      v.x = *reinterpret_cast<const uint32_t*>(&h01);
+      v.y = v.z = v.w = 0u;
+      *reinterpret_cast<uint4*>(p.ws.act0_h + ((size_t)g.guard + r) * 8) = v;
+    } else {
+      p.ws.act0_f[(size_t)g.guard + r] = make_float4(img, fed, 0.f, 0.f);
+    }
+  }
+  if (c.cta == 0 && c.tid == 0) *p.ws.count = 0u;
+  if (c.tid == 0) c.s_misc[0] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Epilogue shared by both compute modes: v[32] = conv accumulators of one FoV row.
+//   even layers ("_a"): out = relu(v + b)                         (convstack_3d.py:38,45)
+//   odd  layers ("_b"): net = v + b (+ residual); out = relu(net) (convstack_3d.py:39,46-49)
+//   last layer        : logits = seed + b_lom + <relu(net), w_lom> (convstack_3d.py:51-54,
+//                       model.py:176-177)
+// `out` feeds the next convolution: the pre-activation ReLU of the next residual module and the
+// ReLU before conv_lom are applied here, once, when the value is produced.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_row(const Ctx& c, int layer, int r, float (&v)[32], int& hit) {
+  const KParams& p = *c.p;
+  const Geom& g = p.g;
+  const float* b = c.s_bias + layer * 32;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] += b[k];
+  const bool is_b = (layer & 1) != 0;
+  const bool last = layer == g.nconv - 1;
+  const size_t ra = (size_t)g.guard + r;
+  if (is_b) {
+    if (layer > 1) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 o = __ldcg(p.ws.res + (size_t)q * g.rows_alloc + ra);
+        v[4 * q + 0] += o.x;
+        v[4 * q + 1] += o.y;
+        v[4 * q + 2] += o.z;
+        v[4 * q + 3] += o.w;
+      }
+    }
+    if (!last) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        p.ws.res[(size_t)q * g.rows_alloc + ra] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
+  if (last) {
+    const float* wl = c.s_bias + g.nconv * 32;
+    float upd = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) upd = fmaf(v[k], wl[k], upd);
+    upd += wl[32];
+    const float raw = p.ws.seed_raw[r];
+    const float fed = isnan(raw) ? p.cv.opt.pad_value : raw;
+    const float logit = fed + upd;
+    p.ws.logits[r] = logit;
+    hit += (logit >= p.cv.opt.move_threshold) ? 1 : 0;
+    return;
+  }
+  if (p.compute_mode == FFN_COMPUTE_FP16_TC) {
+    __half* dst = p.ws.act_h[layer & 1];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 o;
+      __half2 h;
+      h = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+      *reinterpret_cast<uint4*>(dst + ((size_t)q * g.rows_alloc + ra) * 8) = o;
+    }
+  } else {
+    float4* dst = p.ws.act_f[layer & 1];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      dst[(size_t)q * g.rows_alloc + ra] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Tensor-core layer: implicit GEMM, M = 128 FoV rows, N = 32 features, K = 27 taps x Cin.
+// A = activation rows (K-major, no swizzle: [k-chunk][row] 16-byte units, so a tap is a shifted
+// start address), B = packed weights, D = fp32 accumulators in TMEM (32 columns per tile).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_issue_weight_load(Ctx& c, int layer) {
+  const KParams& p = *c.p;
+  const int buf = layer & 1;
+  const uint32_t bytes = (layer == 0 ? 27 * 2 : 27 * 4) * 512;
+  sm100::mbar_expect_tx(&c.mb_w[buf], bytes);
+  sm100::bulk_g2s(c.smem + buf * (27 * 4 * 512), p.w.w16 + w16_layer_offset_halfs(layer), bytes, &c.mb_w[buf]);
+}
+
+__device__ void tc_layer(Ctx& c, int layer) {
+  const KParams& p = *c.p;
+  const Geom& g = p.g;
+  const int nch = layer == 0 ? 2 : 4;
+  const __half* in = layer == 0 ? p.ws.act0_h : p.ws.act_h[(layer - 1) & 1];
+  const int buf = layer & 1;
+  unsigned char* act_smem = c.smem + 2 * 27 * 4 * 512;
+  const uint32_t idesc = sm100::umma_idesc_f16(kTileM, kFeat);
+
+  // Prefetch the next layer's weights (next step's layer 0 after the last layer) into the other
+  // buffer: its previous user (layer - 1) has completed all MMAs.
+  if (c.tid == 0) {
+    const int nxt = (layer + 1 == g.nconv) ? 0 : layer + 1;
+    tc_issue_weight_load(c, nxt);
+  }
+  c.w_pending[(layer + 1) & 1] = 1;
+
+  int hit = 0;
+  for (int g0 = c.t_begin; g0 < c.t_end; g0 += kGroupTiles) {
+    const int ng = min(kGroupTiles, c.t_end - g0);
+    const int r0 = g0 * kTileM;
+    const int seg_rows = ng * kTileM + 2 * g.halo;
+    if (c.tid == 0) {
+      sm100::fence_proxy_async();
+      sm100::mbar_expect_tx(c.mb_act, (uint32_t)(3 * nch * seg_rows * 16));
+      for (int dzi = 0; dzi < 3; ++dzi) {
+        for (int ch = 0; ch < nch; ++ch) {
+          const __half* src =
+              in + ((size_t)ch * g.rows_alloc + g.guard + r0 + (dzi - 1) * g.pp - g.halo) * 8;
+          sm100::bulk_g2s(act_smem + (size_t)(dzi * nch + ch) * seg_rows * 16, src, (uint32_t)seg_rows * 16,
+                          c.mb_act);
+        }
+      }
+    }
+    mbar_wait(c, c.mb_act, c.par_act);
+    c.par_act ^= 1;
+    if (g0 == c.t_begin) {
+      mbar_wait(c, &c.mb_w[buf], c.par_w[buf]);
+      c.par_w[buf] ^= 1;
+      c.w_pending[buf] = 0;
+    }
+    sm100::tc_fence_after();
+
+    if (c.tid == 0) {
+      const uint32_t a_base = sm100::smem_u32(act_smem);
+      const uint32_t b_base = sm100::smem_u32(c.smem + buf * (27 * 4 * 512));
+      const uint32_t a_lbo = (uint32_t)seg_rows * 16;
+      for (int i = 0; i < ng; ++i) {
+        const uint32_t d = c.tmem_base + (uint32_t)(i * kFeat);
+        uint32_t acc = 0;
+        for (int tap = 0; tap < 27; ++tap) {
+          const int tz = tap / 9, ty = (tap / 3) % 3, tx = tap % 3;
+          const int a_row = i * kTileM + g.halo + (ty - 1) * g.xp + (tx - 1);
+          for (int j = 0; j < nch / 2; ++j) {
+            const uint32_t a_addr = a_base + (uint32_t)(((tz * nch + 2 * j) * seg_rows + a_row) * 16);
+            const uint32_t b_addr = b_base + (uint32_t)((tap * nch + 2 * j) * 512);
+            sm100::umma_f16(d, sm100::umma_desc(a_addr, a_lbo, 128), sm100::umma_desc(b_addr, 512, 128), idesc,
+                            acc);
+            acc = 1;
+          }
+        }
+        sm100::umma_commit(&c.mb_mma[i]);
+      }
+    }
+    __syncwarp();
+
+    // Epilogue: warps 0-3 take tiles 0 and 2, warps 4-7 tile 1; warp w reads TMEM lanes 32*(w%4)...
+    for (int i = c.warp >> 2; i < ng; i += 2) {
+      mbar_wait(c, &c.mb_mma[i], c.par_mma[i]);
+      sm100::tc_fence_after();
+      uint32_t raw[32];
+      sm100::tmem_ld32(c.tmem_base + ((uint32_t)((c.warp & 3) * 32) << 16) + (uint32_t)(i * kFeat), raw);
+      sm100::tmem_ld_wait();
+      const int r = r0 + i * kTileM + (c.warp & 3) * 32 + c.lane;
+      int z, y, x;
+      if (row_to_zyx(g, r, z, y, x)) {
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+        epilogue_row(c, layer, r, v, hit);
+      }
+    }
+    for (int i = 0; i < ng; ++i) c.par_mma[i] ^= 1;
+    sm100::tc_fence_before();
+    __syncthreads();   // act smem / TMEM are reused by the next group or layer
+  }
+  if (layer == g.nconv - 1) {
+    hit = __reduce_add_sync(0xffffffffu, hit);
+    if (c.lane == 0 && hit) atomicAdd(&c.s_misc[0], hit);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 layer ("precise" parity mode): one thread per FoV row, 32 accumulators, weights
+// broadcast from shared memory, activations through L1.
+// ------------------------------------------------------------------------------------------
+__device__ void f32_layer(Ctx& c, int layer) {
+  const KParams& p = *c.p;
+  const Geom& g = p.g;
+  const int ngrp = layer == 0 ? 1 : 8;           // input groups of 4 channels
+  const int cin = ngrp * 4;
+  const float4* in = layer == 0 ? p.ws.act0_f : p.ws.act_f[(layer - 1) & 1];
+  float* wsm = reinterpret_cast<float*>(c.smem);
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.w.w32 + w32_layer_offset_floats(layer));
+    float4* dst = reinterpret_cast<float4*>(wsm);
+    const int n4 = 27 * cin * 32 / 4;
+    for (int i = c.tid; i < n4; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  int hit = 0;
+  for (int r = c.t_begin * kTileM + c.tid; r < c.t_end * kTileM; r += kThreads) {
+    int z, y, x;
+    if (!row_to_zyx(g, r, z, y, x)) continue;
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = 0.f;
+    for (int tap = 0; tap < 27; ++tap) {
+      const int off = (tap / 9 - 1) * g.pp + ((tap / 3) % 3 - 1) * g.xp + (tap % 3 - 1);
+      const float4* a = in + (size_t)g.guard + r + off;
+      const float* wt = wsm + (size_t)tap * cin * 32;
+      for (int q = 0; q < ngrp; ++q) {
+        const float4 av = a[(size_t)q * g.rows_alloc];
+        const float ain[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4* w4 = reinterpret_cast<const float4*>(wt + (q * 4 + e) * 32);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 w = w4[k];
+            v[4 * k + 0] = fmaf(ain[e], w.x, v[4 * k + 0]);
+            v[4 * k + 1] = fmaf(ain[e], w.y, v[4 * k + 1]);
+            v[4 * k + 2] = fmaf(ain[e], w.z, v[4 * k + 2]);
+            v[4 * k + 3] = fmaf(ain[e], w.w, v[4 * k + 3]);
+          }
+        }
+      }
+    }
+    epilogue_row(c, layer, r, v, hit);
+  }
+  if (layer == g.nconv - 1) {
+    hit = __reduce_add_sync(0xffffffffu, hit);
+    if (c.lane == 0 && hit) atomicAdd(&c.s_misc[0], hit);
+  }
+  __syncthreads();
+}
+
+// Runs the conv stack on the staged FoV; on return (after a grid barrier) ws.logits and ws.count
+// are complete and visible to every CTA.
+__device__ void run_network(Ctx& c) {
+  const KParams& p = *c.p;
+  grid_barrier(c);   // staged operands visible
+  for (int layer = 0; layer < p.g.nconv; ++layer) {
+    if (p.compute_mode == FFN_COMPUTE_FP16_TC) {
+      tc_layer(c, layer);
+    } else {
+      f32_layer(c, layer);
+    }
+    if (layer == p.g.nconv - 1) {
+      __syncthreads();
+      if (c.tid == 0 && c.s_misc[0]) atomicAdd(p.ws.count, (unsigned)c.s_misc[0]);
+    }
+    grid_barrier(c);
+  }
+}
+
+__device__ __forceinline__ bool disco_active(const KParams& p) {
+  // inference.py:416-424: np.mean(logits >= move_threshold) > disco_seed_threshold (float64 compare)
+  if (!(p.cv.opt.disco_seed_threshold >= 0.f)) return false;
+  const unsigned cnt = __ldcg(p.ws.count);
+  return (double)cnt / (double)p.g.V > (double)p.cv.opt.disco_seed_threshold;
+}
+
+// Merged logit of FoV row r (what Canvas.update_at writes back and returns).
+__device__ __forceinline__ float merged_row(const KParams& p, int r, bool disco) {
+  float l = __ldcg(p.ws.logits + r);
+  if (disco) {
+    const float o = __ldcg(p.ws.seed_raw + r);
+    if (o < 0.f && l > o) l = o;   // NaN old value: both compares false (inference.py:427-433)
+  }
+  return l;
+}
+
+// Paste this CTA's rows into the seed canvas (inference.py:439) / the prediction output.
+__device__ void tail_paste(Ctx& c, int pz, int py, int px, int batch_idx) {
+  const KParams& p = *c.p;
+  const Geom& g = p.g;
+  const bool predict = p.job.mode == MODE_PREDICT;
+  const bool disco = predict ? false : disco_active(p);
+  for (int r = c.t_begin * kTileM + c.tid; r < c.t_end * kTileM; r += kThreads) {
+    int z, y, x;
+    if (!row_to_zyx(g, r, z, y, x)) continue;
+    const size_t fi = ((size_t)z * g.fy + y) * g.fx + x;
+    if (predict) {
+      p.job.out_logits[(size_t)batch_idx * g.V + fi] = __ldcg(p.ws.logits + r);
+      continue;
+    }
+    const float m = merged_row(p, r, disco);
+    const size_t i = ((size_t)(pz - g.mz + z) * p.cv.sy + (py - g.my + y)) * p.cv.sx + (px - g.mx + x);
+    p.cv.seed[i] = m;
+    if (p.job.mode == MODE_UPDATE_AT && p.job.pred_out) p.job.pred_out[fi] = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Leader logic (CTA 0): movement policy, validity, object / canvas loops
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t cv_index(const CanvasDev& cv, int z, int y, int x) {
+  return ((size_t)z * cv.sy + y) * cv.sx + x;
+}
+
+__device__ __forceinline__ int floordiv(int a, int b) {
+  int q = a / b;
+  if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+  return q;
+}
+
+// movement.py:200-208 quantize_pos -> index into the epoch-stamped lattice.
+__device__ __forceinline__ size_t lattice_index(const KParams& p, const CanvasState* st, int z, int y, int x) {
+  const Geom& g = p.g;
+  const int qz = floordiv(z - st->start[0] + g.dz / 2, max(g.dz, 1)) + p.cv.lat_off[0];
+  const int qy = floordiv(y - st->start[1] + g.dy / 2, max(g.dy, 1)) + p.cv.lat_off[1];
+  const int qx = floordiv(x - st->start[2] + g.dx / 2, max(g.dx, 1)) + p.cv.lat_off[2];
+  return ((size_t)qz * p.cv.lat_dim[1] + qy) * p.cv.lat_dim[2] + qx;
+}
+
+// Current value of canvas.seed[z,y,x] as the reference would see it after the paste of the step
+// at `cur` (which other CTAs may still be writing): inside that FoV use the merged logits.
+__device__ __forceinline__ float seed_value(const KParams& p, const CanvasState* st, bool disco, int z, int y, int x) {
+  const Geom& g = p.g;
+  if (st->have_cur) {
+    const int fz = z - (st->cur[0] - g.mz), fy = y - (st->cur[1] - g.my), fx = x - (st->cur[2] - g.mx);
+    if (fz >= 0 && fz < g.fz && fy >= 0 && fy < g.fy && fx >= 0 && fx < g.fx)
+      return merged_row(p, fz * g.pp + fy * g.xp + fx, disco);
+  }
+  return __ldcg(p.cv.seed + cv_index(p.cv, z, y, x));
+}
+
+__device__ __forceinline__ void push_move(const KParams& p, CanvasState* st, float score, int z, int y, int x) {
+  if (st->q_tail >= p.cv.q_cap) {
+    st->overflow |= 1;
+    return;
+  }
+  const int t = st->q_tail++;
+  p.cv.q_score[t] = score;
+  p.cv.q_pos[3 * t + 0] = z;
+  p.cv.q_pos[3 * t + 1] = y;
+  p.cv.q_pos[3 * t + 2] = x;
+}
+
+// FaceMaxMovementPolicy.update (movement.py:210-222) for the step just executed at st->cur.
+// All threads of CTA 0 call this; warps 0-5 each reduce one face.
+__device__ void policy_update(Ctx& c, CanvasState* st, bool disco) {
+  const KParams& p = *c.p;
+  const Geom& g = p.g;
+  float* s_score = reinterpret_cast<float*>(c.s_misc + 8);
+  int* s_rel = c.s_misc + 16;   // [6][3]
+  int* s_ok = c.s_misc + 40;    // [6]
+  const int cz = g.fz / 2, cy = g.fy / 2, cx = g.fx / 2;
+  const int del[3] = {g.dz, g.dy, g.dx};
+  const int cen[3] = {cz, cy, cx};
+  if (c.warp < 6) {
+    const int axis = c.warp >> 1;
+    const int off = (c.warp & 1) ? del[axis] : -del[axis];
+    int ok = 0;
+    if (del[axis] != 0) {
+      // the two in-face axes in their original (C) order
+      const int a0 = axis == 0 ? 1 : 0;
+      const int a1 = axis == 2 ? 1 : 2;
+      const int n0 = 2 * del[a0] + 1, n1 = 2 * del[a1] + 1;
+      float best = -CUDART_INF_F;
+      int best_i = 0x7fffffff;
+      for (int e = c.lane; e < n0 * n1; e += 32) {
+        const int i0 = e / n1, i1 = e - i0 * n1;
+        int zyx[3];
+        zyx[axis] = cen[axis] + off;
+        zyx[a0] = cen[a0] - del[a0] + i0;
+        zyx[a1] = cen[a1] - del[a1] + i1;
+        const float v = merged_row(p, zyx[0] * g.pp + zyx[1] * g.xp + zyx[2], disco);
+        if (v > best || best_i == 0x7fffffff) {
+          best = v;
+          best_i = e;
+        }
+      }
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, s);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, s);
+        if (oi != 0x7fffffff && (best_i == 0x7fffffff || ov > best || (ov == best && oi < best_i))) {
+          best = ov;
+          best_i = oi;
+        }
+      }
+      if (c.lane == 0) {
+        // movement.py:84-86: skip when score < threshold (float64 compare == f32 compare against
+        // the smallest float32 >= threshold)
+        ok = (best >= p.cv.policy_th_f32) ? 1 : 0;
+        const int i0 = best_i / n1, i1 = best_i - i0 * n1;
+        int rel[3];
+        rel[axis] = off;
+        rel[a0] = i0 - n0 / 2;
+        rel[a1] = i1 - n1 / 2;
+        s_score[c.warp] = best;
+        s_rel[3 * c.warp + 0] = rel[0];
+        s_rel[3 * c.warp + 1] = rel[1];
+        s_rel[3 * c.warp + 2] = rel[2];
+      }
+    }
+    if (c.lane == 0) s_ok[c.warp] = ok;
+  }
+  __syncthreads();
+  if (c.tid == 0) {
+    p.cv.lattice[lattice_index(p, st, st->cur[0], st->cur[1], st->cur[2])] = st->epoch;
+    int order[6], n = 0;
+    for (int f = 0; f < 6; ++f)
+      if (s_ok[f]) order[n++] = f;
+    // sorted(..., reverse=True) on (score, (dz, dy, dx)) tuples (movement.py:218)
+    for (int i = 1; i < n; ++i) {
+      const int f = order[i];
+      int j = i - 1;
+      while (j >= 0) {
+        const int h = order[j];
+        bool greater = s_score[f] > s_score[h];
+        if (s_score[f] == s_score[h]) {
+          greater = false;
+          for (int k = 0; k < 3; ++k) {
+            if (s_rel[3 * f + k] != s_rel[3 * h + k]) {
+              greater = s_rel[3 * f + k] > s_rel[3 * h + k];
+              break;
+            }
+          }
+        }
+        if (!greater) break;
+        order[j + 1] = h;
+        --j;
+      }
+      order[j + 1] = f;
+    }
+    for (int i = 0; i < n; ++i) {
+      const int f = order[i];
+      push_move(p, st, s_score[f], st->cur[0] + s_rel[3 * f], st->cur[1] + s_rel[3 * f + 1],
+                st->cur[2] + s_rel[3 * f + 2]);
+    }
+  }
+  __syncthreads();
+}
+
+// Canvas.is_valid_pos (inference.py:312-346); thread 0 only.
+__device__ bool is_valid_pos(const KParams& p, CanvasState* st, bool disco, int z, int y, int x,
+                             bool ignore_move_threshold) {
+  const Geom& g = p.g;
+  const bool inside = z >= 0 && y >= 0 && x >= 0 && z < p.cv.sz && y < p.cv.sy && x < p.cv.sx;
+  if (!ignore_move_threshold && inside) {
+    const float v = seed_value(p, st, disco, z, y, x);
+    if (v < p.cv.opt.move_threshold) {
+      st->ctr.skip_threshold++;
+      return false;
+    }
+  }
+  if (z - g.mz < 0 || y - g.my < 0 || x - g.mx < 0 || z + g.mz >= p.cv.sz || y + g.my >= p.cv.sy ||
+      x + g.mx >= p.cv.sx) {
+    st->ctr.skip_invalid_pos++;
+    return false;
+  }
+  if (__ldcg(p.cv.seg + cv_index(p.cv, z, y, x)) > 0) {
+    st->ctr.skip_invalid_pos++;
+    return false;
+  }
+  return true;
+}
+
+// FaceMaxMovementPolicy.__next__ (movement.py:186-198); thread 0 only.
+__device__ bool pop_next(const KParams& p, CanvasState* st, bool disco, int& z, int& y, int& x) {
+  while (st->q_head < st->q_tail) {
+    const int h = st->q_head++;
+    z = p.cv.q_pos[3 * h];
+    y = p.cv.q_pos[3 * h + 1];
+    x = p.cv.q_pos[3 * h + 2];
+    if (p.cv.lattice[lattice_index(p, st, z, y, x)] == st->epoch) continue;
+    if (is_valid_pos(p, st, disco, z, y, x, false)) return true;
+  }
+  return false;
+}
+
+// quantize_probability(expit(v)) (storage.py:137-143, inference.py:655-657).
+__device__ __forceinline__ uint8_t quantize_prob(float logit) {
+  const float pf = 1.0f / (1.0f + expf(-logit));
+  const double pd = (double)pf;
+  int k = (int)(pd * 254.0);
+  if (k > 254) k = 254;
+  if (k < 0) k = 0;
+  const double step = 1.0 / 254.0;
+  // bins[j] = j * step for j < 254, bins[254] = 1.0 ; result = #bins <= p
+  while (k < 254 && ((k + 1 == 254) ? 1.0 : (double)(k + 1) * step) <= pd) ++k;
+  while (k > 0 && ((k == 254) ? 1.0 : (double)k * step) > pd) --k;
+  return (uint8_t)(k + 1);
+}
+
+// Decides the next collective action; executed by all threads of CTA 0, serial parts on thread 0.
+// Writes *job.action (read by every CTA after the following grid barrier).
+__device__ void leader_decide(Ctx& c) {
+  const KParams& p = *c.p;
+  const Geom& g = p.g;
+  CanvasState* st = p.st;
+  int* s_phase = c.s_misc + 4;
+  int* s_disco = c.s_misc + 5;
+  if (c.tid == 0) {
+    *s_phase = st->phase;
+    *s_disco = (st->phase == PH_AFTER_STEP) ? (disco_active(p) ? 1 : 0) : 0;
+  }
+  __syncthreads();
+  const bool disco = *s_disco != 0;
+  if (*s_phase == PH_AFTER_STEP && p.job.mode != MODE_UPDATE_AT) policy_update(c, st, disco);   // movement.py:210-222
+  if (c.tid != 0) return;
+
+  int action = ACT_EXIT;
+  int phase = st->phase;
+  const CanvasDev& cv = p.cv;
+  for (;;) {
+    if (phase == PH_FORCE_STEP) {   // Canvas.update_at driven from the host: one step at st->cur
+      st->have_cur = 1;
+      for (int k = 0; k < 3; ++k) {
+        const int m = k == 0 ? g.mz : k == 1 ? g.my : g.mx;
+        st->dirty_lo[k] = min(st->dirty_lo[k], st->cur[k] - m);
+        st->dirty_hi[k] = max(st->dirty_hi[k], st->cur[k] + m + 1);
+      }
+      phase = PH_AFTER_STEP;
+      action = ACT_STEP;
+      break;
+    }
+    if (phase == PH_AFTER_STEP && p.job.mode == MODE_UPDATE_AT) {
+      st->ctr.inference_calls++;
+      st->have_cur = 0;
+      phase = PH_SEGMENT_DONE;
+      action = ACT_EXIT;
+      break;
+    }
+    if (phase == PH_AFTER_STEP) {
+      // inference.py:511-514
+      for (int k = 0; k < 3; ++k) {
+        st->min_pos[k] = min(st->min_pos[k], st->cur[k]);
+        st->max_pos[k] = max(st->max_pos[k], st->cur[k]);
+      }
+      st->iters++;
+      st->ctr.inference_calls++;
+      phase = PH_POP;
+      continue;
+    }
+    if (phase == PH_START_SEGMENT) {
+      st->ctr.segment_at_calls++;
+      st->seg_t0 = sm100::globaltimer_ns();
+      if (st->reset_seed) {
+        phase = PH_AFTER_CLEAR;
+        action = ACT_CLEAR;
+        break;
+      }
+      phase = PH_POP;
+      continue;
+    }
+    if (phase == PH_AFTER_CLEAR) {
+      // init_seed (inference.py:443-450) + reset_state (:291-310) + first queue item (:492-496)
+      cv.seed[cv_index(cv, st->start[0], st->start[1], st->start[2])] = cv.opt.init_activation;
+      for (int k = 0; k < 3; ++k) {
+        st->dirty_lo[k] = st->start[k];
+        st->dirty_hi[k] = st->start[k] + 1;
+        st->min_pos[k] = st->max_pos[k] = st->start[k];
+      }
+      st->epoch++;
+      st->q_head = st->q_tail = 0;
+      st->iters = 0;
+      st->have_cur = 0;
+      st->weak = 0;
+      push_move(p, st, (float)(cv.opt.policy_score_threshold * 2.0), st->start[0], st->start[1], st->start[2]);
+      phase = PH_POP;
+      continue;
+    }
+    if (phase == PH_POP) {
+      if (p.job.step_budget > 0 && st->ctr.inference_calls >= p.job.step_budget) {
+        action = ACT_EXIT;   // pause: host relaunches with a fresh budget
+        st->have_cur = 0;    // by then every paste has landed in the canvas
+        break;
+      }
+      bool run = false;
+      int z = 0, y = 0, x = 0;
+      for (;;) {
+        if (!pop_next(p, st, disco, z, y, x)) break;
+        // inference.py:503-505
+        if (seed_value(p, st, disco, st->start[0], st->start[1], st->start[2]) < cv.opt.move_threshold) {
+          st->ctr.seed_got_too_weak++;
+          st->weak = 1;
+          break;
+        }
+        // inference.py:507-509
+        if (cv.mask && cv.mask[cv_index(cv, z, y, x)]) {
+          st->ctr.skip_restricted_pos++;
+          continue;
+        }
+        run = true;
+        break;
+      }
+      if (run) {
+        st->cur[0] = z;
+        st->cur[1] = y;
+        st->cur[2] = x;
+        st->have_cur = 1;
+        for (int k = 0; k < 3; ++k) {
+          st->dirty_lo[k] = min(st->dirty_lo[k], st->cur[k] - (k == 0 ? g.mz : k == 1 ? g.my : g.mx));
+          st->dirty_hi[k] = max(st->dirty_hi[k], st->cur[k] + (k == 0 ? g.mz : k == 1 ? g.my : g.mx) + 1);
+        }
+        phase = PH_AFTER_STEP;
+        action = ACT_STEP;
+        break;
+      }
+      // object finished
+      if (!st->seg_all) {
+        phase = PH_SEGMENT_DONE;
+        action = ACT_EXIT;
+        break;
+      }
+      // segment_all post-processing (inference.py:593-620)
+      const size_t si = cv_index(cv, st->start[0], st->start[1], st->start[2]);
+      if (st->iters <= 0) {
+        st->ctr.invalid_other++;
+        phase = PH_NEXT_SEED;
+        continue;
+      }
+      if (seed_value(p, st, disco, st->start[0], st->start[1], st->start[2]) < cv.opt.move_threshold) {
+        if (cv.seg[si] == 0) cv.seg[si] = -1;
+        st->ctr.invalid_weak++;
+        phase = PH_NEXT_SEED;
+        continue;
+      }
+      const int half[3] = {g.fz / 2, g.fy / 2, g.fx / 2};
+      const int shp[3] = {cv.sz, cv.sy, cv.sx};
+      for (int k = 0; k < 3; ++k) {
+        st->box_lo[k] = max(st->min_pos[k] - half[k], 0);
+        st->box_hi[k] = min(st->max_pos[k] + half[k] + 1, shp[k]);
+      }
+      st->cnt_raw = st->cnt_actual = 0ull;
+      st->n_touched = 0;
+      phase = PH_AFTER_COUNT;
+      action = ACT_COUNT;
+      break;
+    }
+    if (phase == PH_AFTER_COUNT) {
+      const size_t si = cv_index(cv, st->start[0], st->start[1], st->start[2]);
+      const long long raw = (long long)st->cnt_raw, actual = (long long)st->cnt_actual;
+      if (actual < (long long)cv.opt.min_segment_size) {   // inference.py:639-646
+        if (cv.seg[si] == 0) cv.seg[si] = -1;
+        st->ctr.invalid_small++;
+        for (int i = 0; i < st->n_touched; ++i) p.job.ovl_count[p.job.ovl_touched[i]] = 0;
+        st->n_touched = 0;
+        phase = PH_NEXT_SEED;
+        continue;
+      }
+      st->ctr.voxels_segmented += actual;
+      st->ctr.voxels_overlapping += raw - actual;
+      st->max_id++;
+      st->cur_sid = st->max_id;
+      st->ctr.max_id = st->max_id;
+      st->ctr.segments++;
+      for (int i = 0; i < st->n_touched; ++i) {       // Canvas.overlaps (inference.py:668)
+        const int id = p.job.ovl_touched[i];
+        if (st->n_overlaps < p.job.overlaps_cap) {
+          FfnOverlap o;
+          o.id = st->cur_sid;
+          o.other_id = id;
+          o.count = p.job.ovl_count[id];
+          p.job.overlaps[st->n_overlaps] = o;
+        } else {
+          st->overflow |= 2;
+        }
+        st->n_overlaps++;
+        p.job.ovl_count[id] = 0;
+      }
+      st->n_touched = 0;
+      if (st->n_origins < p.job.origins_cap) {        // Canvas.origins (inference.py:671)
+        FfnOrigin o;
+        o.id = st->cur_sid;
+        o.start_zyx[0] = st->start[0];
+        o.start_zyx[1] = st->start[1];
+        o.start_zyx[2] = st->start[2];
+        o.iters = st->iters;
+        o.walltime_sec = (double)(sm100::globaltimer_ns() - st->seg_t0) * 1e-9;
+        p.job.origins[st->n_origins] = o;
+      } else {
+        st->overflow |= 4;
+      }
+      st->n_origins++;
+      phase = PH_AFTER_WRITE;
+      action = ACT_WRITE;
+      break;
+    }
+    if (phase == PH_AFTER_WRITE) {
+      phase = PH_NEXT_SEED;
+      continue;
+    }
+    if (phase == PH_NEXT_SEED) {
+      bool found = false;
+      while (st->seed_idx < p.job.n_seeds) {
+        const long long k = st->seed_idx++;
+        const int z = p.job.seeds[3 * k], y = p.job.seeds[3 * k + 1], x = p.job.seeds[3 * k + 2];
+        // seed.py:81-88 border filter (BaseSeedPolicy.__next__)
+        if (z - g.mz < 0 || y - g.my < 0 || x - g.mx < 0 || z + g.mz >= cv.sz || y + g.my >= cv.sy ||
+            x + g.mx >= cv.sx)
+          continue;
+        st->ctr.seeds_examined++;
+        st->have_cur = 0;
+        if (!is_valid_pos(p, st, false, z, y, x, true)) continue;       // inference.py:562-568
+        const size_t i = cv_index(cv, z, y, x);
+        if (cv.mask && cv.mask[i]) continue;
+        if (cv.seed_mask && cv.seed_mask[i]) continue;
+        // inference.py:573-581 (numpy slice semantics: negative start would wrap; positions here
+        // are >= margin >= min_boundary_dist is NOT guaranteed, so clamp like a slice that is
+        // empty-safe: the reference would index from the end — unreachable for mbd <= margin)
+        bool close = false;
+        const int* mbd = cv.opt.min_boundary_dist_zyx;
+        for (int zz = max(z - mbd[0], 0); zz < min(z + mbd[0] + 1, cv.sz) && !close; ++zz)
+          for (int yy = max(y - mbd[1], 0); yy < min(y + mbd[1] + 1, cv.sy) && !close; ++yy)
+            for (int xx = max(x - mbd[2], 0); xx < min(x + mbd[2] + 1, cv.sx); ++xx)
+              if (__ldcg(cv.seg + cv_index(cv, zz, yy, xx)) > 0) {
+                close = true;
+                break;
+              }
+        if (close) {
+          cv.seg[i] = -1;
+          continue;
+        }
+        st->start[0] = z;
+        st->start[1] = y;
+        st->start[2] = x;
+        st->reset_seed = 1;
+        found = true;
+        break;
+      }
+      if (!found) {
+        phase = PH_ALL_DONE;
+        action = ACT_EXIT;
+        break;
+      }
+      phase = PH_START_SEGMENT;
+      continue;
+    }
+    // PH_IDLE / PH_SEGMENT_DONE / PH_ALL_DONE
+    action = ACT_EXIT;
+    break;
+  }
+  st->phase = phase;
+  *p.job.action = action;
+  __threadfence();
+}
+
+// ------------------------------------------------------------------------------------------
+// Collective helpers over a canvas box
+// ------------------------------------------------------------------------------------------
+__device__ void clear_dirty(Ctx& c) {   // NumpyArray.clear restricted to the touched box
+  const KParams& p = *c.p;
+  const CanvasState* st = p.st;
+  const int lo[3] = {max(st->dirty_lo[0], 0), max(st->dirty_lo[1], 0), max(st->dirty_lo[2], 0)};
+  const int hi[3] = {min(st->dirty_hi[0], p.cv.sz), min(st->dirty_hi[1], p.cv.sy), min(st->dirty_hi[2], p.cv.sx)};
+  const int nz = hi[0] - lo[0], ny = hi[1] - lo[1], nx = hi[2] - lo[2];
+  if (nz <= 0 || ny <= 0 || nx <= 0) return;
+  const long long lines = (long long)nz * ny;
+  const float nanv = CUDART_NAN_F;
+  for (long long l = (long long)c.cta * (kThreads / 32) + c.warp; l < lines; l += (long long)c.G * (kThreads / 32)) {
+    const int z = lo[0] + (int)(l / ny), y = lo[1] + (int)(l % ny);
+    float* row = p.cv.seed + cv_index(p.cv, z, y, lo[2]);
+    for (int x = c.lane; x < nx; x += 32) row[x] = nanv;
+  }
+}
+
+__device__ void commit_count(Ctx& c) {   // inference.py:624-636
+  const KParams& p = *c.p;
+  CanvasState* st = p.st;
+  const int* lo = st->box_lo;
+  const int* hi = st->box_hi;
+  const int nz = hi[0] - lo[0], ny = hi[1] - lo[1], nx = hi[2] - lo[2];
+  const long long lines = (long long)nz * ny;
+  unsigned raw = 0, actual = 0;
+  for (long long l = (long long)c.cta * (kThreads / 32) + c.warp; l < lines; l += (long long)c.G * (kThreads / 32)) {
+    const int z = lo[0] + (int)(l / ny), y = lo[1] + (int)(l % ny);
+    const size_t base = cv_index(p.cv, z, y, lo[2]);
+    for (int x = c.lane; x < nx; x += 32) {
+      const float s = __ldcg(p.cv.seed + base + x);
+      if (!(s >= p.cv.opt.segment_threshold)) continue;
+      ++raw;
+      const int sg = __ldcg(p.cv.seg + base + x);
+      if (sg > 0) {
+        if (sg < p.job.ovl_ids) {
+          if (atomicAdd(p.job.ovl_count + sg, 1) == 0) {
+            const int t = atomicAdd(&st->n_touched, 1);
+            if (t < p.job.ovl_ids) p.job.ovl_touched[t] = sg;
+          }
+        }
+      } else {
+        ++actual;
+      }
+    }
+  }
+  raw = __reduce_add_sync(0xffffffffu, raw);
+  actual = __reduce_add_sync(0xffffffffu, actual);
+  if (c.lane == 0 && raw) {
+    atomicAdd(&st->cnt_raw, (unsigned long long)raw);
+    atomicAdd(&st->cnt_actual, (unsigned long long)actual);
+  }
+}
+
+__device__ void commit_write(Ctx& c) {   // inference.py:653-658
+  const KParams& p = *c.p;
+  const CanvasState* st = p.st;
+  const int* lo = st->box_lo;
+  const int* hi = st->box_hi;
+  const int nz = hi[0] - lo[0], ny = hi[1] - lo[1], nx = hi[2] - lo[2];
+  const long long lines = (long long)nz * ny;
+  const int sid = st->cur_sid;
+  for (long long l = (long long)c.cta * (kThreads / 32) + c.warp; l < lines; l += (long long)c.G * (kThreads / 32)) {
+    const int z = lo[0] + (int)(l / ny), y = lo[1] + (int)(l % ny);
+    const size_t base = cv_index(p.cv, z, y, lo[2]);
+    for (int x = c.lane; x < nx; x += 32) {
+      const float s = __ldcg(p.cv.seed + base + x);
+      if (!(s >= p.cv.opt.segment_threshold)) continue;
+      if (__ldcg(p.cv.seg + base + x) > 0) continue;
+      p.cv.seg[base + x] = sid;
+      if (p.cv.qprob) p.cv.qprob[base + x] = quantize_prob(s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Ctx c;
+  c.p = &p;
+  c.tid = threadIdx.x;
+  c.warp = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
+  c.cta = blockIdx.x;
+  c.G = gridDim.x;
+  c.t_begin = (int)(((long long)c.cta * p.g.nt) / c.G);
+  c.t_end = (int)(((long long)(c.cta + 1) * p.g.nt) / c.G);
+  c.bar_target = 0;
+  c.smem = smem_raw;
+  const SmemLayout L = smem_layout(p.g);
+  c.s_bias = reinterpret_cast<float*>(smem_raw + L.bias);
+  c.mb_w = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
+  c.mb_act = c.mb_w + 2;
+  c.mb_mma = c.mb_w + 3;
+  c.s_tmem = reinterpret_cast<uint32_t*>(c.mb_w + 3 + kGroupTiles);
+  c.s_misc = reinterpret_cast<int*>(c.s_tmem + 2);
+  c.par_w[0] = c.par_w[1] = c.par_act = 0;
+  for (int i = 0; i < kGroupTiles; ++i) c.par_mma[i] = 0;
+  c.w_pending[0] = c.w_pending[1] = 0;
+  c.tmem_base = 0;
+  const bool tc = p.compute_mode == FFN_COMPUTE_FP16_TC;
+
+  for (int i = c.tid; i < p.g.nconv * 32; i += kThreads) c.s_bias[i] = p.w.bias[i];
+  if (c.tid < 32) c.s_bias[p.g.nconv * 32 + c.tid] = p.w.w_lom[c.tid];
+  if (c.tid == 0) c.s_bias[p.g.nconv * 32 + 32] = p.w.b_lom;
+  if (tc) {
+    if (c.tid == 0) {
+      sm100::mbar_init(&c.mb_w[0], 1);
+      sm100::mbar_init(&c.mb_w[1], 1);
+      sm100::mbar_init(c.mb_act, 1);
+      for (int i = 0; i < kGroupTiles; ++i) sm100::mbar_init(&c.mb_mma[i], 1);
+      sm100::fence_mbar_init();
+    }
+    __syncwarp();
+    if (c.warp == 0) sm100::tmem_alloc<kTmemCols>(c.s_tmem);
+    sm100::tc_fence_before();
+    __syncthreads();
+    sm100::tc_fence_after();
+    c.tmem_base = *c.s_tmem;
+    if (c.tid == 0) tc_issue_weight_load(c, 0);
+    c.w_pending[0] = 1;
+  }
+  __syncthreads();
+
+  if (p.job.mode == MODE_PREDICT) {
+    for (int b = 0; b < p.job.batch; ++b) {
+      stage_fov(c, 0, 0, 0, b);
+      run_network(c);
+      tail_paste(c, 0, 0, 0, b);
+      grid_barrier(c);
+      if (aborted(c)) break;
+    }
+  } else {
+    for (;;) {
+      if (c.cta == 0) leader_decide(c);
+      grid_barrier(c);
+      if (aborted(c)) break;
+      const int action = sm100::ld_volatile_s32(p.job.action);
+      if (action == ACT_EXIT) break;
+      if (action == ACT_STEP) {
+        const int pz = sm100::ld_volatile_s32(&p.st->cur[0]);
+        const int py = sm100::ld_volatile_s32(&p.st->cur[1]);
+        const int px = sm100::ld_volatile_s32(&p.st->cur[2]);
+        stage_fov(c, pz, py, px, 0);
+        run_network(c);
+        tail_paste(c, pz, py, px, 0);
+      } else {
+        // The leader's next decision reads what these collectives produce (counts, labels,
+        // the cleared seed), so every CTA must be done before CTA 0 runs leader_decide again.
+        if (action == ACT_CLEAR) clear_dirty(c);
+        if (action == ACT_COUNT) commit_count(c);
+        if (action == ACT_WRITE) commit_write(c);
+        grid_barrier(c);
+      }
+    }
+  }
+
+  // Teardown: no bulk copy may be in flight into this CTA's shared memory at exit.
+  if (tc) {
+    for (int b = 0; b < 2; ++b)
+      if (c.w_pending[b]) mbar_wait(c, &c.mb_w[b], c.par_w[b]);
+    sm100::tc_fence_before();
+    __syncthreads();
+    if (c.warp == 0) sm100::tmem_dealloc<kTmemCols>(c.tmem_base);
+  }
+}
+
+// Adds `offset` to every label > 0 (multi-GPU merge). HBM-bound, grid-stride.
+__global__ void relabel_offset_kernel(int* seg, size_t n, int offset) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int v = seg[i];
+    if (v > 0) seg[i] = v + offset;
+  }
+}
+
+// u8 -> normalised float32 (runner.py:383-385), for ffn_canvas_read(FFN_ARRAY_IMAGE).
+__global__ void normalize_u8_kernel(const uint8_t* src, float* dst, size_t n, float mean, float stddev) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __fdiv_rn(__fsub_rn((float)src[i], mean), stddev);
+}
+
+__global__ void fill_f32_kernel(float* dst, size_t n, float v) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
+}
+
+}  // namespace ffn

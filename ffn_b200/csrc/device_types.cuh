@@ -9,7 +9,8 @@
 
 namespace ffn {
 
-constexpr int kThreads = 256;     // 8 warps: two epilogue quads (TMEM lane quarters x 2 tiles)
+constexpr int kThreads = 288;     // warps 0-7: two epilogue quads (TMEM lane quarters x 2 tiles); warp 8: TMA + UMMA issue
+constexpr int kIssueWarp = 8;
 constexpr int kTileM = 128;       // UMMA M: FoV rows per tensor-core tile
 constexpr int kFeat = 32;         // feature maps of every hidden layer (UMMA N)
 constexpr int kGroupTiles = 3;    // tiles whose operands are staged in shared memory together
@@ -55,6 +56,7 @@ struct Workspace {
   unsigned* bar;       // grid barrier counter
   unsigned* count;     // voxels with logit >= move threshold in the current step
   int* abort_flag;     // != 0: a wait timed out, everybody bails
+  long long* prof;     // [2][16] cycle counters of CTA 0 and CTA G-1 (debug/profiling)
 };
 
 struct CanvasDev {
@@ -174,7 +176,7 @@ __host__ __device__ inline SmemLayout smem_layout(const Geom& g) {
   const int act_bytes = 3 * 4 * seg_rows * 16;
   s.bias = s.act + act_bytes;
   s.bars = s.bias + (kMaxConv + 1) * 32 * 4 + 16;
-  s.total = s.bars + 512;
+  s.total = s.bars + 1024;
   return s;
 }
 

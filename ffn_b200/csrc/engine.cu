@@ -72,6 +72,7 @@ struct FfnCanvas {
   float* d_pred = nullptr;
   size_t nvox = 0;
   size_t lattice_cells = 0;
+  bool resume_pending = false;
 };
 
 namespace {
@@ -285,10 +286,11 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   if (dev_alloc(&ws.bar, 1)) return 1;
   if (dev_alloc(&ws.count, 1)) return 1;
   if (dev_alloc(&ws.abort_flag, 1)) return 1;
+  if (dev_alloc(&ws.prof, 32)) return 1;
   if (dev_alloc(&e->d_action, 1)) return 1;
   if (dev_alloc(&e->d_dummy_state, 1)) return 1;
   for (void* p : std::vector<void*>{ws.act0_h, ws.act_h[0], ws.act_h[1], ws.act0_f, ws.act_f[0], ws.act_f[1],
-                                    ws.res, ws.seed_raw, ws.logits, ws.bar, ws.count, ws.abort_flag,
+                                    ws.res, ws.seed_raw, ws.logits, ws.bar, ws.count, ws.abort_flag, ws.prof,
                                     e->d_action, e->d_dummy_state})
     e->owned.push_back(p);
   *out = e.release();
@@ -326,6 +328,16 @@ int ffn_engine_info(FfnEngine* e, int64_t info[8]) {
   info[5] = e->g.V;
   info[6] = e->launches;
   info[7] = (int64_t)(e->last_kernel_seconds * 1e9);
+  return 0;
+}
+
+int ffn_engine_profile(FfnEngine* e, int64_t out[32], int reset) {
+  if (!e || !out) return fail("null argument");
+  if (set_device(e)) return 1;
+  long long h[32];
+  CUDA_OK(cudaMemcpy(h, e->ws.prof, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 32; ++i) out[i] = h[i];
+  if (reset) CUDA_OK(cudaMemset(e->ws.prof, 0, sizeof(h)));
   return 0;
 }
 
@@ -496,6 +508,7 @@ int ffn_canvas_segment_at(FfnCanvas* c, const int32_t start[3], int reset, int64
     return fail("start position outside the canvas");
   if (pull_state(c)) return 1;
   CanvasState& st = c->h_state;
+  c->resume_pending = false;   // driving the object by hand consumes a pending checkpoint resume
   st.seg_all = 0;
   const long long steps0 = st.ctr.inference_calls;
   const long long weak0 = st.ctr.seed_got_too_weak;
@@ -567,7 +580,8 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   st.seed_idx = 0;
   st.n_origins = st.n_overlaps = 0;
   st.overflow = 0;
-  st.phase = PH_NEXT_SEED;
+  st.phase = c->resume_pending ? PH_POP : PH_NEXT_SEED;   // PH_POP: finish the restored in-flight object first
+  c->resume_pending = false;
   const FfnCounters before = st.ctr;
   if (push_state(c)) {
     cleanup();
@@ -775,6 +789,23 @@ int ffn_canvas_policy_state_set(FfnCanvas* c, const double* queue_szyx, int64_t 
   }
   st.phase = PH_POP;
   st.have_cur = 0;
+  return push_state(c);
+}
+
+int ffn_canvas_set_resume(FfnCanvas* c, int64_t iters, const int32_t min_pos[3], const int32_t max_pos[3]) {
+  if (!c || !min_pos || !max_pos) return fail("null argument");
+  if (set_device(c->eng)) return 1;
+  if (pull_state(c)) return 1;
+  CanvasState& st = c->h_state;
+  st.iters = iters;
+  for (int k = 0; k < 3; ++k) {
+    st.min_pos[k] = min_pos[k];
+    st.max_pos[k] = max_pos[k];
+  }
+  st.phase = PH_POP;
+  st.have_cur = 0;
+  st.seg_t0 = 0;
+  c->resume_pending = true;
   return push_state(c);
 }
 

@@ -40,6 +40,8 @@ struct Ctx {
   uint64_t* mb_mma;            // [kGroupTiles]
   uint32_t* s_tmem;            // TMEM base address
   int* s_misc;                 // [0] step count>=th accumulator, [1..] leader scratch
+  int* s_aoff;                 // UMMA A-descriptor row offsets per (tap, k-pair): [27] for layer 0, [54] others
+  long long* prof;             // profiling slots of this CTA (null unless CTA 0 / G-1)
   uint32_t par_w[2], par_act, par_mma[kGroupTiles];
   int w_pending[2];
   uint32_t tmem_base;
@@ -47,6 +49,10 @@ struct Ctx {
 
 __device__ __forceinline__ bool aborted(const Ctx& c) {
   return sm100::ld_volatile_s32(c.p->ws.abort_flag) != 0;
+}
+
+__device__ __forceinline__ void prof_add(const Ctx& c, int slot, long long dt) {
+  if (c.prof) c.prof[slot] += dt;
 }
 
 // Bounded spin on an mbarrier phase; a timeout raises the abort flag instead of hanging the GPU.
@@ -71,9 +77,9 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
   __syncthreads();
   if (c.tid == 0) {
     c.bar_target += c.G;
+    const long long t0 = clock64();
     __threadfence();
     atomicAdd(c.p->ws.bar, 1u);
-    const long long t0 = clock64();
     unsigned spins = 0;
     while (sm100::ld_acquire_u32(c.p->ws.bar) < c.bar_target) {
       if ((++spins & 0xFF) == 0) {
@@ -86,6 +92,7 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
     }
     __threadfence();
     sm100::fence_proxy_async();   // later TMA reads must see what other CTAs wrote
+    prof_add(c, 0, clock64() - t0);
   }
   __syncthreads();
   sm100::tc_fence_after();
@@ -153,7 +160,8 @@ __device__ void stage_fov(Ctx& c, int pz, int py, int px, int batch_idx) {
 // `out` feeds the next convolution: the pre-activation ReLU of the next residual module and the
 // ReLU before conv_lom are applied here, once, when the value is produced.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_row(const Ctx& c, int layer, int r, float (&v)[32], int& hit) {
+__device__ __forceinline__ void epilogue_row(const Ctx& c, int layer, int r, float (&v)[32], int& hit,
+                                             const float4* pre_res = nullptr) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
   const float* b = c.s_bias + layer * 32;
@@ -166,7 +174,7 @@ __device__ __forceinline__ void epilogue_row(const Ctx& c, int layer, int r, flo
     if (layer > 1) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 o = __ldcg(p.ws.res + (size_t)q * g.rows_alloc + ra);
+        const float4 o = pre_res ? pre_res[q] : __ldcg(p.ws.res + (size_t)q * g.rows_alloc + ra);
         v[4 * q + 0] += o.x;
         v[4 * q + 1] += o.y;
         v[4 * q + 2] += o.z;
@@ -227,87 +235,116 @@ __device__ __forceinline__ void tc_issue_weight_load(Ctx& c, int layer) {
   sm100::bulk_g2s(c.smem + buf * (27 * 4 * 512), p.w.w16 + w16_layer_offset_halfs(layer), bytes, &c.mb_w[buf]);
 }
 
+// Issues the 27 * NCH/2 UMMAs (128 x 32 x 16) of one tile.  Fully unrolled: every A start-address
+// offset is (const * seg_rows + const * xp + const), so the loop body is two adds and the UMMA.
+template <int NCH>
+__device__ __forceinline__ void tc_issue_tile(uint32_t d, uint32_t a_lo, uint32_t b_lo, int seg_rows, int halo,
+                                              int xp) {
+  const uint32_t idesc = sm100::umma_idesc_f16(kTileM, kFeat);
+  const uint64_t hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
+#pragma unroll
+  for (int tap = 0; tap < 27; ++tap) {
+    const int tz = tap / 9, ty = (tap / 3) % 3, tx = tap % 3;
+#pragma unroll
+    for (int j = 0; j < NCH / 2; ++j) {
+      const uint32_t aoff = (uint32_t)((tz * NCH + 2 * j) * seg_rows + halo + (ty - 1) * xp + (tx - 1));
+      const uint32_t boff = (uint32_t)((tap * (NCH / 2) + j) * 64);
+      sm100::umma_f16(d, hi | (uint64_t)(a_lo + aoff), hi | (uint64_t)(b_lo + boff), idesc,
+                      (tap | j) != 0 ? 1u : 0u);
+    }
+  }
+}
+
 __device__ void tc_layer(Ctx& c, int layer) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
+  const long long t_layer = clock64();
   const int nch = layer == 0 ? 2 : 4;
   const __half* in = layer == 0 ? p.ws.act0_h : p.ws.act_h[(layer - 1) & 1];
   const int buf = layer & 1;
   unsigned char* act_smem = c.smem + 2 * 27 * 4 * 512;
-  const uint32_t idesc = sm100::umma_idesc_f16(kTileM, kFeat);
+  const int seg_rows = kGroupTiles * kTileM + 2 * g.halo;   // fixed k-chunk plane pitch (rows)
+  const bool issuer = c.warp == kIssueWarp && c.lane == 0;
+  const bool need_res = (layer & 1) && layer > 1;
 
   // Prefetch the next layer's weights (next step's layer 0 after the last layer) into the other
   // buffer: its previous user (layer - 1) has completed all MMAs.
-  if (c.tid == 0) {
-    const int nxt = (layer + 1 == g.nconv) ? 0 : layer + 1;
-    tc_issue_weight_load(c, nxt);
-  }
+  if (issuer) tc_issue_weight_load(c, (layer + 1 == g.nconv) ? 0 : layer + 1);
   c.w_pending[(layer + 1) & 1] = 1;
 
   int hit = 0;
   for (int g0 = c.t_begin; g0 < c.t_end; g0 += kGroupTiles) {
     const int ng = min(kGroupTiles, c.t_end - g0);
     const int r0 = g0 * kTileM;
-    const int seg_rows = ng * kTileM + 2 * g.halo;
-    if (c.tid == 0) {
-      sm100::fence_proxy_async();
-      sm100::mbar_expect_tx(c.mb_act, (uint32_t)(3 * nch * seg_rows * 16));
-      for (int dzi = 0; dzi < 3; ++dzi) {
-        for (int ch = 0; ch < nch; ++ch) {
-          const __half* src =
-              in + ((size_t)ch * g.rows_alloc + g.guard + r0 + (dzi - 1) * g.pp - g.halo) * 8;
-          sm100::bulk_g2s(act_smem + (size_t)(dzi * nch + ch) * seg_rows * 16, src, (uint32_t)seg_rows * 16,
-                          c.mb_act);
+    const bool first = g0 == c.t_begin;
+    if (c.warp == kIssueWarp) {
+      if (c.lane == 0) {
+        // ---- TMA producer: three z-plane segments x k-chunks of the input activations
+        const int load_rows = ng * kTileM + 2 * g.halo;
+        long long t0 = clock64();
+        sm100::fence_proxy_async();
+        sm100::mbar_expect_tx(c.mb_act, (uint32_t)(3 * nch * load_rows * 16));
+        for (int dzi = 0; dzi < 3; ++dzi)
+          for (int ch = 0; ch < nch; ++ch)
+            sm100::bulk_g2s(act_smem + (size_t)(dzi * nch + ch) * seg_rows * 16,
+                            in + ((size_t)ch * g.rows_alloc + g.guard + r0 + (dzi - 1) * g.pp - g.halo) * 8,
+                            (uint32_t)load_rows * 16, c.mb_act);
+        mbar_wait(c, c.mb_act, c.par_act);
+        prof_add(c, 1, clock64() - t0);
+        if (first) {
+          t0 = clock64();
+          mbar_wait(c, &c.mb_w[buf], c.par_w[buf]);
+          prof_add(c, 2, clock64() - t0);
         }
+        sm100::tc_fence_after();
+        // ---- UMMA issue: only the 14-bit start-address field changes between instructions
+        t0 = clock64();
+        const uint32_t a_lo = ((sm100::smem_u32(act_smem) >> 4) & 0x3FFFu) | ((uint32_t)seg_rows << 16);
+        const uint32_t b_lo = ((sm100::smem_u32(c.smem + buf * (27 * 4 * 512)) >> 4) & 0x3FFFu) | ((512u >> 4) << 16);
+        for (int i = 0; i < ng; ++i) {
+          const uint32_t d = c.tmem_base + (uint32_t)(i * kFeat);
+          if (layer == 0) {
+            tc_issue_tile<2>(d, a_lo + (uint32_t)(i * kTileM), b_lo, seg_rows, g.halo, g.xp);
+          } else {
+            tc_issue_tile<4>(d, a_lo + (uint32_t)(i * kTileM), b_lo, seg_rows, g.halo, g.xp);
+          }
+          sm100::umma_commit(&c.mb_mma[i]);
+        }
+        prof_add(c, 3, clock64() - t0);
+      }
+      __syncwarp();
+    } else {
+      // ---- Epilogue: warps 0-3 take tiles 0 and 2, warps 4-7 tile 1; warp w reads TMEM lanes 32*(w%4)...
+      for (int i = c.warp >> 2; i < ng; i += 2) {
+        const int r = r0 + i * kTileM + (c.warp & 3) * 32 + c.lane;
+        int z, y, x;
+        const bool valid = row_to_zyx(g, r, z, y, x);
+        float4 pre[8];
+        if (need_res && valid) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) pre[q] = __ldcg(p.ws.res + (size_t)q * g.rows_alloc + g.guard + r);
+        }
+        long long t0 = clock64();
+        mbar_wait(c, &c.mb_mma[i], c.par_mma[i]);
+        if (c.tid == 0) prof_add(c, 4, clock64() - t0);
+        t0 = clock64();
+        sm100::tc_fence_after();
+        uint32_t raw[32];
+        sm100::tmem_ld32(c.tmem_base + ((uint32_t)((c.warp & 3) * 32) << 16) + (uint32_t)(i * kFeat), raw);
+        sm100::tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+          epilogue_row(c, layer, r, v, hit, need_res ? pre : nullptr);
+        }
+        if (c.tid == 0) prof_add(c, 5, clock64() - t0);
       }
     }
-    mbar_wait(c, c.mb_act, c.par_act);
     c.par_act ^= 1;
-    if (g0 == c.t_begin) {
-      mbar_wait(c, &c.mb_w[buf], c.par_w[buf]);
+    if (first) {
       c.par_w[buf] ^= 1;
       c.w_pending[buf] = 0;
-    }
-    sm100::tc_fence_after();
-
-    if (c.tid == 0) {
-      const uint32_t a_base = sm100::smem_u32(act_smem);
-      const uint32_t b_base = sm100::smem_u32(c.smem + buf * (27 * 4 * 512));
-      const uint32_t a_lbo = (uint32_t)seg_rows * 16;
-      for (int i = 0; i < ng; ++i) {
-        const uint32_t d = c.tmem_base + (uint32_t)(i * kFeat);
-        uint32_t acc = 0;
-        for (int tap = 0; tap < 27; ++tap) {
-          const int tz = tap / 9, ty = (tap / 3) % 3, tx = tap % 3;
-          const int a_row = i * kTileM + g.halo + (ty - 1) * g.xp + (tx - 1);
-          for (int j = 0; j < nch / 2; ++j) {
-            const uint32_t a_addr = a_base + (uint32_t)(((tz * nch + 2 * j) * seg_rows + a_row) * 16);
-            const uint32_t b_addr = b_base + (uint32_t)((tap * nch + 2 * j) * 512);
-            sm100::umma_f16(d, sm100::umma_desc(a_addr, a_lbo, 128), sm100::umma_desc(b_addr, 512, 128), idesc,
-                            acc);
-            acc = 1;
-          }
-        }
-        sm100::umma_commit(&c.mb_mma[i]);
-      }
-    }
-    __syncwarp();
-
-    // Epilogue: warps 0-3 take tiles 0 and 2, warps 4-7 tile 1; warp w reads TMEM lanes 32*(w%4)...
-    for (int i = c.warp >> 2; i < ng; i += 2) {
-      mbar_wait(c, &c.mb_mma[i], c.par_mma[i]);
-      sm100::tc_fence_after();
-      uint32_t raw[32];
-      sm100::tmem_ld32(c.tmem_base + ((uint32_t)((c.warp & 3) * 32) << 16) + (uint32_t)(i * kFeat), raw);
-      sm100::tmem_ld_wait();
-      const int r = r0 + i * kTileM + (c.warp & 3) * 32 + c.lane;
-      int z, y, x;
-      if (row_to_zyx(g, r, z, y, x)) {
-        float v[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
-        epilogue_row(c, layer, r, v, hit);
-      }
     }
     for (int i = 0; i < ng; ++i) c.par_mma[i] ^= 1;
     sm100::tc_fence_before();
@@ -317,6 +354,7 @@ __device__ void tc_layer(Ctx& c, int layer) {
     hit = __reduce_add_sync(0xffffffffu, hit);
     if (c.lane == 0 && hit) atomicAdd(&c.s_misc[0], hit);
   }
+  if (c.tid == 0) prof_add(c, 11, clock64() - t_layer);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -978,6 +1016,10 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   c.mb_mma = c.mb_w + 3;
   c.s_tmem = reinterpret_cast<uint32_t*>(c.mb_w + 3 + kGroupTiles);
   c.s_misc = reinterpret_cast<int*>(c.s_tmem + 2);
+  c.s_aoff = c.s_misc + 64;
+  c.prof = nullptr;
+  if (p.ws.prof && (c.cta == 0 || c.cta == c.G - 1)) c.prof = p.ws.prof + (c.cta == 0 ? 0 : 16);
+  const long long t_kernel = clock64();
   c.par_w[0] = c.par_w[1] = c.par_act = 0;
   for (int i = 0; i < kGroupTiles; ++i) c.par_mma[i] = 0;
   c.w_pending[0] = c.w_pending[1] = 0;
@@ -988,6 +1030,17 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   if (c.tid < 32) c.s_bias[p.g.nconv * 32 + c.tid] = p.w.w_lom[c.tid];
   if (c.tid == 0) c.s_bias[p.g.nconv * 32 + 32] = p.w.b_lom;
   if (tc) {
+    {
+      // A-descriptor start-address offsets (16-byte rows) per (tap, k-pair), see tc_layer
+      const int seg_rows = kGroupTiles * kTileM + 2 * p.g.halo;
+      for (int k = c.tid; k < 27 + 54; k += kThreads) {
+        const int nch = k < 27 ? 2 : 4;
+        const int kk = k < 27 ? k : k - 27;
+        const int tap = kk / (nch / 2), j = kk % (nch / 2);
+        const int tz = tap / 9, ty = (tap / 3) % 3, tx = tap % 3;
+        c.s_aoff[k] = (tz * nch + 2 * j) * seg_rows + p.g.halo + (ty - 1) * p.g.xp + (tx - 1);
+      }
+    }
     if (c.tid == 0) {
       sm100::mbar_init(&c.mb_w[0], 1);
       sm100::mbar_init(&c.mb_w[1], 1);
@@ -1001,7 +1054,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
     __syncthreads();
     sm100::tc_fence_after();
     c.tmem_base = *c.s_tmem;
-    if (c.tid == 0) tc_issue_weight_load(c, 0);
+    if (c.warp == kIssueWarp && c.lane == 0) tc_issue_weight_load(c, 0);
     c.w_pending[0] = 1;
   }
   __syncthreads();
@@ -1016,7 +1069,11 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
     }
   } else {
     for (;;) {
-      if (c.cta == 0) leader_decide(c);
+      if (c.cta == 0) {
+        const long long t0 = clock64();
+        leader_decide(c);
+        if (c.tid == 0) prof_add(c, 8, clock64() - t0);
+      }
       grid_barrier(c);
       if (aborted(c)) break;
       const int action = sm100::ld_volatile_s32(p.job.action);
@@ -1025,9 +1082,16 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
         const int pz = sm100::ld_volatile_s32(&p.st->cur[0]);
         const int py = sm100::ld_volatile_s32(&p.st->cur[1]);
         const int px = sm100::ld_volatile_s32(&p.st->cur[2]);
+        long long t0 = clock64();
         stage_fov(c, pz, py, px, 0);
+        if (c.tid == 0) prof_add(c, 6, clock64() - t0);
         run_network(c);
+        t0 = clock64();
         tail_paste(c, pz, py, px, 0);
+        if (c.tid == 0) {
+          prof_add(c, 7, clock64() - t0);
+          prof_add(c, 9, 1);
+        }
       } else {
         // The leader's next decision reads what these collectives produce (counts, labels,
         // the cleared seed), so every CTA must be done before CTA 0 runs leader_decide again.
@@ -1039,6 +1103,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
     }
   }
 
+  if (c.tid == 0) prof_add(c, 10, clock64() - t_kernel);
   // Teardown: no bulk copy may be in flight into this CTA's shared memory at exit.
   if (tc) {
     for (int b = 0; b < 2; ++b)

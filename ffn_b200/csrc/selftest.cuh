@@ -74,9 +74,11 @@ __global__ void umma_kat_kernel(const __half* a_g, int a_rows_total, const __hal
   if (warp == 0) sm100::tmem_dealloc<32>(tmem);
 }
 
-// ---- variant 1: UMMA issue rate for N in {32, 64, 96, 128, 256}, A and B from shared memory ---
-template <int N>
-__global__ void umma_rate_kernel(int iters, int nacc, long long* cycles_out) {
+// ---- variant 1: UMMA issue rate, A and B from shared memory ----------------------------------
+// M x N x 16 UMMAs issued back to back by one thread; NACC independent accumulators (rotating);
+// the A start address moves like a convolution tap.  Reports cycles per UMMA.
+template <int M, int N, int NACC>
+__global__ void umma_rate_kernel(int iters, long long* cycles_out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 98304);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 98304 + 16);
@@ -87,29 +89,35 @@ __global__ void umma_rate_kernel(int iters, int nacc, long long* cycles_out) {
     sm100::fence_mbar_init();
   }
   __syncwarp();
-  if (warp == 0) sm100::tmem_alloc<256>(tmem_slot);
+  if (warp == 0) sm100::tmem_alloc<512>(tmem_slot);
   sm100::fence_proxy_async();
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (tid == 0) {
-    const uint32_t idesc = sm100::umma_idesc_f16(128, N);
-    const uint32_t a0 = sm100::smem_u32(smem);            // A: 64 KB window, shifted per MMA like conv taps
-    const uint32_t b0 = sm100::smem_u32(smem + 65536);    // B: N x 16 halfs
+    const uint32_t idesc = sm100::umma_idesc_f16(M, N);
+    const uint32_t hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo = ((sm100::smem_u32(smem) >> 4) & 0x3FFFu) | ((16384u >> 4) << 16);
+    const uint32_t b_lo = ((sm100::smem_u32(smem + 65536) >> 4) & 0x3FFFu) | (((uint32_t)N * 16u >> 4) << 16);
+    const uint64_t bd = ((uint64_t)hi << 32) | b_lo;
     const long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      const uint32_t a_addr = a0 + (uint32_t)((i * 37) & 1023) * 16;
-      sm100::umma_f16(tmem + (uint32_t)((i % nacc) * N), sm100::umma_desc(a_addr, 16384, 128),
-                      sm100::umma_desc(b0, (uint32_t)N * 16, 128), idesc, i >= nacc ? 1u : 0u);
+    for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(a_lo + (uint32_t)(((i + u) * 37) & 511));
+        sm100::umma_f16(tmem + (uint32_t)((u % NACC) * N), ad, bd, idesc, i > 0 ? 1u : 0u);
+      }
     }
     sm100::umma_commit(bar);
+    const long long t1 = clock64();
     bounded_wait(bar, 0);
-    cycles_out[blockIdx.x] = clock64() - t0;
+    cycles_out[2 * blockIdx.x] = clock64() - t0;
+    cycles_out[2 * blockIdx.x + 1] = t1 - t0;   // issue-only time
   }
   sm100::tc_fence_before();
   __syncthreads();
-  if (warp == 0) sm100::tmem_dealloc<256>(tmem);
+  if (warp == 0) sm100::tmem_dealloc<512>(tmem);
 }
 
 // ---- variant 2: grid-barrier latency --------------------------------------------------------
@@ -223,22 +231,26 @@ inline int run_kat(double* out, std::string* err) {
   return 0;
 }
 
-template <int N>
-inline int run_rate_one(int grid, int nacc, double* cyc_per_mma, std::string* err) {
-  const int iters = 2048;
+template <int M, int N, int NACC>
+inline int run_rate_one(int grid, double* cyc_per_mma, double* issue_per_mma, std::string* err) {
+  const int iters = 4096;
   long long* d_c = nullptr;
-  ST_CUDA(cudaMalloc(&d_c, sizeof(long long) * grid));
-  ST_CUDA(cudaFuncSetAttribute(umma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304 + 64));
-  umma_rate_kernel<N><<<grid, 128, 98304 + 64>>>(iters, nacc, d_c);   // warm-up
-  umma_rate_kernel<N><<<grid, 128, 98304 + 64>>>(iters, nacc, d_c);
+  ST_CUDA(cudaMalloc(&d_c, sizeof(long long) * grid * 2));
+  ST_CUDA(cudaFuncSetAttribute(umma_rate_kernel<M, N, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304 + 64));
+  umma_rate_kernel<M, N, NACC><<<grid, 128, 98304 + 64>>>(iters, d_c);   // warm-up
+  umma_rate_kernel<M, N, NACC><<<grid, 128, 98304 + 64>>>(iters, d_c);
   ST_CUDA(cudaGetLastError());
   ST_CUDA(cudaDeviceSynchronize());
-  std::vector<long long> c(grid);
-  ST_CUDA(cudaMemcpy(c.data(), d_c, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+  std::vector<long long> c(grid * 2);
+  ST_CUDA(cudaMemcpy(c.data(), d_c, sizeof(long long) * grid * 2, cudaMemcpyDeviceToHost));
   cudaFree(d_c);
-  long long worst = 0;
-  for (long long v : c) worst = std::max(worst, v);
+  long long worst = 0, worst_issue = 0;
+  for (int i = 0; i < grid; ++i) {
+    worst = std::max(worst, c[2 * i]);
+    worst_issue = std::max(worst_issue, c[2 * i + 1]);
+  }
   *cyc_per_mma = (double)worst / iters;
+  if (issue_per_mma) *issue_per_mma = (double)worst_issue / iters;
   return 0;
 }
 
@@ -249,15 +261,19 @@ inline int run(int device, int variant, double* out, int n_out, std::string* err
   for (int i = 0; i < n_out; ++i) out[i] = -1.0;
   if (variant == 0) return run_kat(out, err);
   if (variant == 1 || variant == 4) {
+    if (n_out < 16) {
+      *err = "need 16 output slots";
+      return 1;
+    }
     const int grid = variant == 1 ? 1 : prop.multiProcessorCount;   // 4: all SMs at once (power/clock effects)
-    if (run_rate_one<32>(grid, 1, &out[0], err)) return 1;
-    if (run_rate_one<64>(grid, 1, &out[1], err)) return 1;
-    if (run_rate_one<96>(grid, 1, &out[2], err)) return 1;
-    if (run_rate_one<128>(grid, 1, &out[3], err)) return 1;
-    if (run_rate_one<256>(grid, 1, &out[4], err)) return 1;
-    if (run_rate_one<32>(grid, 4, &out[6], err)) return 1;    // four independent accumulators
-    if (run_rate_one<96>(grid, 2, &out[7], err)) return 1;
-    out[5] = prop.clockRate * 1e-3;   // MHz (max)
+    if (run_rate_one<128, 32, 1>(grid, &out[0], &out[8], err)) return 1;
+    if (run_rate_one<128, 32, 4>(grid, &out[1], &out[9], err)) return 1;
+    if (run_rate_one<64, 32, 4>(grid, &out[2], &out[10], err)) return 1;
+    if (run_rate_one<128, 64, 4>(grid, &out[3], &out[11], err)) return 1;
+    if (run_rate_one<128, 96, 4>(grid, &out[4], &out[12], err)) return 1;
+    if (run_rate_one<128, 128, 2>(grid, &out[5], &out[13], err)) return 1;
+    if (run_rate_one<128, 256, 2>(grid, &out[6], &out[14], err)) return 1;
+    out[7] = prop.clockRate * 1e-3;   // MHz (max)
     return 0;
   }
   if (variant == 2) {

@@ -117,8 +117,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));   // volatile: ordered w.r.t. the waits/fences
 }
 
 // Arrive on an mbarrier when all previously issued UMMAs of this thread have completed

@@ -93,6 +93,16 @@ class Engine:
     keys = ('sm_count', 'grid', 'smem_bytes', 'tiles', 'rows', 'fov_voxels', 'launches', 'last_kernel_ns')
     return dict(zip(keys, [int(v) for v in buf]))
 
+  PROFILE_SLOTS = ('barrier_wait', 'act_tma_wait', 'weight_wait', 'umma_issue', 'epi_wait_mma', 'epi_body',
+                   'stage', 'paste', 'leader', 'steps', 'kernel', 'conv_layers')
+
+  def profile(self, reset: bool = True) -> dict:
+    """Device cycle counters of CTA 0 and of the last CTA (see ffn_engine_profile)."""
+    buf = (C.c_int64 * 32)()
+    _lib.check(self._lib.ffn_engine_profile(self._h, buf, 1 if reset else 0))
+    return {'cta0': dict(zip(self.PROFILE_SLOTS, [int(v) for v in buf[:12]])),
+            'cta_last': dict(zip(self.PROFILE_SLOTS, [int(v) for v in buf[16:28]]))}
+
   def predict(self, seed: np.ndarray, image: np.ndarray) -> np.ndarray:
     """(Z,Y,X) or (B,Z,Y,X) float32 patches -> logits of the same shape (executor.py:134-139)."""
     seed = np.ascontiguousarray(seed, dtype=np.float32)
@@ -206,6 +216,9 @@ class DeviceCanvas:
     c = _lib.Counters()
     _lib.check(self._lib.ffn_canvas_get_counters(self._h, C.byref(c)))
     return c
+
+  def set_resume(self, iters: int, min_pos, max_pos):
+    _lib.check(self._lib.ffn_canvas_set_resume(self._h, int(iters), _lib.i3(min_pos), _lib.i3(max_pos)))
 
   def set_max_id(self, max_id: int):
     _lib.check(self._lib.ffn_canvas_set_max_id(self._h, int(max_id)))

@@ -119,6 +119,11 @@ int ffn_engine_set_compute_mode(FfnEngine* engine, int compute_mode);
 /* sm count, cooperative grid size, shared memory per CTA, tiles per FoV: info[0..3]. */
 int ffn_engine_info(FfnEngine* engine, int64_t info[8]);
 
+/* Device-side cycle counters of CTA 0 (out[0..15]) and the last CTA (out[16..31]): slot 0 grid-barrier
+ * wait, 1 activation TMA wait, 2 weight wait, 3 UMMA issue, 4 epilogue wait-for-MMA, 5 epilogue body,
+ * 6 stage, 7 paste, 8 leader, 9 steps, 10 kernel, 11 conv layers.  Debug / profiles only. */
+int ffn_engine_profile(FfnEngine* engine, int64_t out[32], int reset);
+
 /* ---- L0 drop-in: ExecutorClient.predict (ffn/inference/executor.py:134-139, 266-340) -------
  * seed, image: host float32 [batch, Z, Y, X]; logits_out: host float32 [batch, Z, Y, X]
  * (the 'logits' fetch without the trailing channel axis).  Copies in, runs, copies out. */
@@ -170,6 +175,12 @@ int ffn_canvas_policy_state_get(FfnCanvas* canvas, double* queue_szyx, int32_t* 
 int ffn_canvas_policy_state_set(FfnCanvas* canvas, const double* queue_szyx, int64_t queue_len,
                                 const int32_t* done_zyx, int64_t done_len,
                                 const int32_t start_zyx[3]);
+/* Resume of an in-flight object restored from a .cpoint (Canvas.restore_checkpoint returning
+ * partial_segment_iters > 0, inference.py:728-778): after ffn_canvas_policy_state_set and the
+ * seed/segmentation writes, the next ffn_canvas_segment_all first finishes this object (with
+ * the given iteration count and extents) and commits it, then continues with its seed list. */
+int ffn_canvas_set_resume(FfnCanvas* canvas, int64_t iters, const int32_t min_pos[3],
+                          const int32_t max_pos[3]);
 /* Canvas._max_id / counters carried across calls (checkpoint restore, init segmentation). */
 int ffn_canvas_set_max_id(FfnCanvas* canvas, int64_t max_id);
 int ffn_canvas_get_counters(FfnCanvas* canvas, FfnCounters* out);

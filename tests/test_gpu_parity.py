@@ -1,0 +1,366 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+fixtures recorded from the reference's own Python modules.
+
+Tolerances (also stated in DESIGN.md):
+  * FFN_COMPUTE_FP32     logits max-abs <= 1e-4 vs the fp32 oracle; trajectories / labels identical to the
+                         reference golden run; qprob within +-1 LSB.
+  * FFN_COMPUTE_FP16_TC  logits max-abs <= 6e-2 (fp16 operand rounding, fp32 accumulate) vs the fp32
+                         oracle; flood-fill state BIT-EXACT vs the oracle loop driven by the same
+                         GPU network ("hybrid oracle"): every integer / index / decision is exact.
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import flood_fill as ff
+
+pytestmark = pytest.mark.gpu
+
+FOV, DELTAS = (33, 33, 33), (8, 8, 8)
+
+
+@pytest.fixture(scope='module')
+def weights(golden_dir):
+  from ffn_b200 import tf_checkpoint
+  return tf_checkpoint.load_convstack_npz(os.path.join(golden_dir, 'fib25_convstack.npz'))
+
+
+@pytest.fixture(scope='module')
+def engines(weights):
+  from ffn_b200 import _lib, engine as eng
+  w, b = weights
+  out = {'fp32': eng.Engine(w, b, FOV, DELTAS, compute_mode=_lib.COMPUTE_FP32),
+         'tc': eng.Engine(w, b, FOV, DELTAS, compute_mode=_lib.COMPUTE_FP16_TC)}
+  yield out
+  for e in out.values():
+    e.close()
+
+
+@pytest.fixture(scope='module')
+def g64(golden_dir):
+  return np.load(os.path.join(golden_dir, 'flood_fill_64.npz'))
+
+
+def _image(vol):
+  return (vol.astype(np.float32) - np.float32(128.0)) / np.float32(33.0)
+
+
+def test_umma_descriptor_known_answer():
+  """tcgen05.mma with the K-major / no-swizzle descriptors the conv kernel uses, incl. tap shifts."""
+  from ffn_b200 import engine as eng
+  out = eng.selftest(0, n_out=16)
+  assert out[0] == 0.0 and out[1] == 0.0 and out[2] == 0.0, out   # exact: small-integer operands
+  assert out[3] > 1.0, 'swapped LBO/SBO must NOT reproduce the product'
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('tc', 6e-2)])
+def test_predict_matches_oracle(engines, golden_dir, mode, tol):
+  pat = np.load(os.path.join(golden_dir, 'net_patches.npz'))
+  e = engines[mode]
+  got = e.predict(pat['seed'], pat['image'])
+  assert np.isfinite(got).all()
+  assert np.abs(got - pat['logits_fp32']).max() <= tol
+  assert np.abs(got - pat['logits_fp64']).max() <= tol
+  one = e.predict(pat['seed'][3], pat['image'][3])
+  np.testing.assert_array_equal(one, got[3])                          # batch == single, deterministic
+  np.testing.assert_array_equal(e.predict(pat['seed'][3], pat['image'][3]), one)
+
+
+def test_predict_is_linear_in_nothing_but_respects_seed_add(engines):
+  """Size-independent property: logits - seed (the update) does not depend on a constant added to
+  the seed only through the network input, i.e. predict(seed) - seed == update(seed)."""
+  rng = np.random.RandomState(0)
+  img = rng.randn(*FOV).astype(np.float32)
+  seed = np.full(FOV, -2.9444, np.float32)
+  e = engines['fp32']
+  a = e.predict(seed, img)
+  assert np.abs((a - seed) - (e.predict(seed, img) - seed)).max() == 0.0
+
+
+def test_fp32_segment_at_matches_reference_golden(engines, golden_dir, g64):
+  from ffn_b200 import _lib, engine as eng
+  gat = np.load(os.path.join(golden_dir, 'segment_at_64.npz'))
+  cv = eng.DeviceCanvas(engines['fp32'], g64['volume'], eng.make_options(), 128.0, 33.0)
+  st = cv.segment_at(tuple(int(v) for v in gat['start']))
+  assert st.iters == int(gat['iters']) and st.finished
+  seed = cv.read(_lib.ARRAY_SEED)
+  want = gat['seed_canvas']
+  np.testing.assert_array_equal(np.isnan(seed), np.isnan(want))
+  ok = ~np.isnan(want)
+  assert np.abs(seed[ok] - want[ok]).max() < 1e-3
+  queue, done, start = cv.policy_state()
+  assert queue.shape[0] == gat['queue'].shape[0] and start == tuple(int(v) for v in gat['start'])
+  trace_cells = {tuple(((p - gat['start'] + 4) // 8).tolist()) for p in gat['trace']}
+  assert {tuple(d) for d in done.tolist()} == trace_cells            # quantised done-set == visited lattice cells
+  cv.close()
+
+
+def _check_segment_all(cv, origins, overlaps, ctr, g, exact_qprob):
+  from ffn_b200 import _lib
+  seg = cv.read(_lib.ARRAY_SEGMENTATION)
+  np.testing.assert_array_equal(seg, g['segmentation'])
+  qp = cv.read(_lib.ARRAY_QPROB).astype(int)
+  diff = np.abs(qp - g['seg_prob'].astype(int))
+  assert diff.max() <= (0 if exact_qprob else 1)
+  assert (diff > 0).mean() < 1e-3
+  got = np.array([[o.id] + list(o.start_zyx) + [o.iters] for o in origins], dtype=np.int64).reshape(-1, 5)
+  np.testing.assert_array_equal(got, g['origins'])
+  ov = sorted((o.id, o.other_id, o.count) for o in overlaps)
+  want = sorted(zip(*g['overlaps'].tolist())) if g['overlaps'].size else []
+  assert ov == [tuple(int(v) for v in t) for t in want]
+  gc = json.loads(str(g['counters']))
+  assert ctr.inference_calls == gc['inference-calls']
+  assert ctr.segment_at_calls == gc['segment_at-loop-calls']
+  assert ctr.skip_threshold == gc.get('skip_threshold', 0)
+  assert ctr.skip_invalid_pos == gc.get('skip_invalid_pos', 0)
+  assert ctr.voxels_segmented == gc['voxels-segmented']
+  assert ctr.voxels_overlapping == gc['voxels-overlapping']
+  for sid, z, y, x, _ in g['origins']:
+    assert seg[z, y, x] == sid                                       # every origin carries its own id
+
+
+def test_fp32_segment_all_matches_reference_golden(engines, g64):
+  """Whole-canvas run == the reference's Canvas.segment_all on the same volume / seeds / weights."""
+  from ffn_b200 import engine as eng
+  cv = eng.DeviceCanvas(engines['fp32'], g64['volume'], eng.make_options(), 128.0, 33.0)
+  origins, overlaps, ctr = cv.segment_all(g64['seeds'])
+  _check_segment_all(cv, origins, overlaps, ctr, g64, exact_qprob=False)
+  # idempotence: a second pass over the same seeds finds nothing new to segment
+  seg_before = cv.read(1)
+  o2, _, c2 = cv.segment_all(g64['seeds'])
+  assert not o2 and c2.segments == ctr.segments
+  np.testing.assert_array_equal((cv.read(1) > 0), (seg_before > 0))
+  cv.close()
+
+
+@pytest.mark.parametrize('mode', ['tc', 'fp32'])
+def test_device_loop_bit_exact_vs_hybrid_oracle(engines, g64, mode):
+  """Same network (the GPU's) under both loops: the reference loop restated on the CPU and the
+  persistent kernel must agree bit for bit on seed, labels, qprob, origins, overlaps."""
+  from ffn_b200 import _lib, engine as eng
+  e = engines[mode]
+  vol = g64['volume']
+  cv = eng.DeviceCanvas(e, vol, eng.make_options(), 128.0, 33.0)
+  origins, overlaps, ctr = cv.segment_all(g64['seeds'])
+  hyb = ff.Canvas(lambda s, im: e.predict(s, im), _image(vol), FOV, DELTAS, ff.Options())
+  hyb.segment_all(g64['seeds'])
+  np.testing.assert_array_equal(cv.read(_lib.ARRAY_SEGMENTATION), hyb.segmentation)
+  np.testing.assert_array_equal(cv.read(_lib.ARRAY_SEED), hyb.seed)
+  qd = np.abs(cv.read(_lib.ARRAY_QPROB).astype(int) - hyb.seg_prob.astype(int))
+  assert qd.max() <= 1 and (qd > 0).mean() < 1e-3                    # expf vs scipy expit at bin edges
+  assert ctr.inference_calls == len(hyb.trace)
+  assert [(o.id, tuple(o.start_zyx), o.iters) for o in origins] == \
+      [(k, v[0], v[1]) for k, v in sorted(hyb.origins.items())]
+  for k, v in hyb.overlaps.items():
+    mine = sorted((o.other_id, o.count) for o in overlaps if o.id == k)
+    assert mine == sorted(zip(v[0].tolist(), v[1].tolist()))
+  assert ctr.skip_threshold == hyb.counters['skip_threshold']
+  assert ctr.skip_invalid_pos == hyb.counters['skip_invalid_pos']
+  cv.close()
+
+
+def test_masks_and_rejections_vs_hybrid_oracle(engines):
+  """Movement mask, seed mask, min_boundary_dist, small-object rejection (-1 markers)."""
+  from ffn_b200 import _lib, engine as eng
+  from ffn_b200.synthetic import voronoi_phantom
+  e = engines['tc']
+  vol = voronoi_phantom((56, 64, 72), seed=5, cell_volume=30000.0)
+  mask = np.zeros(vol.shape, bool)
+  mask[:, 30:34, :] = True
+  seed_mask = np.zeros(vol.shape, bool)
+  seed_mask[:, :, :24] = True
+  opts = ff.Options(min_segment_size=40000, min_boundary_dist=(2, 3, 1))
+  seeds = ff.grid_seeds(vol.shape, step=8, offsets=(0, 4))
+  cv = eng.DeviceCanvas(e, vol, eng.make_options(min_segment_size=40000, min_boundary_dist_zyx=(2, 3, 1)), 128.0, 33.0)
+  cv.set_mask(_lib.MASK_MOVEMENT, mask)
+  cv.set_mask(_lib.MASK_SEED, seed_mask)
+  origins, _, ctr = cv.segment_all(seeds)
+  hyb = ff.Canvas(lambda s, im: e.predict(s, im), _image(vol), FOV, DELTAS, opts, mask=mask, seed_mask=seed_mask)
+  hyb.segment_all(seeds)
+  seg = cv.read(_lib.ARRAY_SEGMENTATION)
+  np.testing.assert_array_equal(seg, hyb.segmentation)
+  assert (seg == -1).sum() == (hyb.segmentation == -1).sum() > 0     # rejected seeds are marked
+  assert ctr.skip_restricted_pos == hyb.counters['skip_restriced_pos']
+  assert ctr.invalid_small == hyb.counters['invalid-small']
+  assert len(origins) == len(hyb.origins)
+  cv.close()
+
+
+def test_update_at_and_init_seed(engines, g64):
+  from ffn_b200 import _lib, engine as eng
+  e = engines['fp32']
+  vol = g64['volume']
+  cv = eng.DeviceCanvas(e, vol, eng.make_options(), 128.0, 33.0)
+  pos = (24, 40, 36)
+  cv.init_seed(pos)
+  pred = cv.update_at(pos)
+  hyb = ff.Canvas(lambda s, im: e.predict(s, im), _image(vol), FOV, DELTAS, ff.Options())
+  hyb.init_seed(pos)
+  want = hyb.update_at(pos)
+  np.testing.assert_array_equal(pred, want)
+  np.testing.assert_array_equal(cv.read(_lib.ARRAY_SEED), hyb.seed)
+  # a second init_seed clears exactly what was touched
+  cv.init_seed((30, 30, 30))
+  s = cv.read(_lib.ARRAY_SEED)
+  assert np.isfinite(s).sum() == 1 and s[30, 30, 30] == np.float32(eng.f32_logit(0.95))
+  cv.close()
+
+
+def test_u8_and_f32_images_are_equivalent(engines, g64):
+  from ffn_b200 import _lib, engine as eng
+  e = engines['fp32']
+  vol = g64['volume']
+  a = eng.DeviceCanvas(e, vol, eng.make_options(), 128.0, 33.0)
+  b = eng.DeviceCanvas(e, _image(vol), eng.make_options())
+  np.testing.assert_array_equal(a.read(_lib.ARRAY_IMAGE), _image(vol))   # device normalisation == runner.py:383-385
+  sa, sb = a.segment_at((16, 48, 32)), b.segment_at((16, 48, 32))
+  assert sa.iters == sb.iters
+  np.testing.assert_array_equal(a.read(_lib.ARRAY_SEED), b.read(_lib.ARRAY_SEED))
+  a.close()
+  b.close()
+
+
+def test_pause_resume_and_box_io(engines, g64):
+  """max_steps pauses inside an object; resuming reproduces the uninterrupted run."""
+  from ffn_b200 import _lib, engine as eng
+  e = engines['tc']
+  vol = g64['volume']
+  ref = eng.DeviceCanvas(e, vol, eng.make_options(), 128.0, 33.0)
+  full = ref.segment_at((16, 48, 32))
+  cv = eng.DeviceCanvas(e, vol, eng.make_options(), 128.0, 33.0)
+  part = cv.segment_at((16, 48, 32), max_steps=11)
+  assert part.iters == 11 and not part.finished
+  rest = cv.segment_at((16, 48, 32), reset=False)
+  assert rest.finished and rest.iters == full.iters
+  np.testing.assert_array_equal(cv.read(_lib.ARRAY_SEED), ref.read(_lib.ARRAY_SEED))
+  box = cv.read(_lib.ARRAY_SEED, (3, 5, 7), (10, 11, 12))
+  np.testing.assert_array_equal(box, ref.read(_lib.ARRAY_SEED)[3:13, 5:16, 7:19])
+  patch = np.arange(24, dtype=np.int32).reshape(2, 3, 4)
+  cv.write(_lib.ARRAY_SEGMENTATION, patch, (1, 2, 3))
+  np.testing.assert_array_equal(cv.read(_lib.ARRAY_SEGMENTATION)[1:3, 2:5, 3:7], patch)
+  ref.close()
+  cv.close()
+
+
+def test_anisotropic_model_vs_oracle(weights):
+  """configs[4] geometry: fov zyx (17,33,33), deltas (4,8,8), depth 9 (first 9 modules of FIB-25)."""
+  from ffn_b200 import _lib, engine as eng
+  from ffn_b200.synthetic import voronoi_phantom
+  from oracle.network import ConvStackOracle
+  w, b = weights
+  w9, b9 = w[:18] + [w[-1]], b[:18] + [b[-1]]
+  fov, deltas = (17, 33, 33), (4, 8, 8)
+  vol = voronoi_phantom((40, 72, 72), seed=4, sigma=(0.5, 1.0, 1.0), voxel_size_zyx=(2.0, 1.0, 1.0))
+  oracle_net = ConvStackOracle(w9, b9)
+  for mode, tol in ((_lib.COMPUTE_FP32, 1e-4), (_lib.COMPUTE_FP16_TC, 6e-2)):
+    e = eng.Engine(w9, b9, fov, deltas, compute_mode=mode)
+    rng = np.random.RandomState(1)
+    img = _image(vol)[4:21, 8:41, 10:43]
+    seed = np.where(rng.rand(*fov) < 0.3, rng.randn(*fov) * 2, -2.9444).astype(np.float32)
+    assert np.abs(e.predict(seed, img) - oracle_net(seed, img)).max() <= tol
+    cv = eng.DeviceCanvas(e, vol, eng.make_options(), 128.0, 33.0)
+    st = cv.segment_at((20, 36, 36))
+    hyb = ff.Canvas(lambda s, im: e.predict(s, im), _image(vol), fov, deltas, ff.Options())
+    n = hyb.segment_at((20, 36, 36))
+    assert st.iters == n and n > 1
+    np.testing.assert_array_equal(cv.read(_lib.ARRAY_SEED), hyb.seed)
+    cv.close()
+    e.close()
+
+
+def test_full_size_properties_256(engines):
+  """BASELINE configs[1] size: invariants that do not need the (slow) CPU oracle."""
+  from ffn_b200 import _lib, engine as eng
+  from ffn_b200.synthetic import interior_seed, voronoi_phantom
+  e = engines['tc']
+  vol = voronoi_phantom((256, 256, 256), seed=1)
+  cv = eng.DeviceCanvas(e, vol, eng.make_options(), 128.0, 33.0)
+  start = interior_seed(vol, (128, 128, 128))
+  st = cv.segment_at(start)
+  assert st.finished and st.iters > 5
+  seed = cv.read(_lib.ARRAY_SEED)
+  lo = np.array(st.min_pos) - 16
+  hi = np.array(st.max_pos) + 17
+  outside = np.ones(seed.shape, bool)
+  outside[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = False
+  assert np.isnan(seed[outside]).all()                                # untouched voxels stay NaN
+  assert seed[start] >= eng.f32_logit(0.9)                            # the seed survived
+  queue, done, s0 = cv.policy_state()
+  assert queue.shape[0] == 0 and done.shape[0] == st.iters            # one lattice cell per step
+  again = cv.segment_at(start)                                        # deterministic
+  assert again.iters == st.iters
+  np.testing.assert_array_equal(cv.read(_lib.ARRAY_SEED), seed)
+  cv.close()
+
+
+def test_runner_end_to_end(tmp_path, golden_dir, g64):
+  """Reference entry-point surface: InferenceRequest -> Runner.start/run -> seg-*.npz / .prob."""
+  from google.protobuf import text_format
+  from ffn.inference import inference_pb2, runner as runner_mod, storage
+  vol_path = str(tmp_path / 'vol.npy')
+  np.save(vol_path, g64['volume'])
+  req = inference_pb2.InferenceRequest()
+  text_format.Parse('''
+    image { hdf5: "%s:raw" }
+    image_mean: 128 image_stddev: 33 seed_policy: "PolicyGrid3d"
+    model_checkpoint_path: "%s"
+    model_name: "convstack_3d.ConvStack3DFFNModel"
+    model_args: "{\\"depth\\": 12, \\"fov_size\\": [33, 33, 33], \\"deltas\\": [8, 8, 8]}"
+    segmentation_output_dir: "%s"
+    inference_options { init_activation: 0.95 pad_value: 0.05 move_threshold: 0.9
+                        min_boundary_dist { x: 1 y: 1 z: 1} segment_threshold: 0.6 min_segment_size: 1000 }
+  ''' % (vol_path, os.path.join(golden_dir, 'fib25_convstack.npz'), str(tmp_path / 'out')), req)
+  from ffn_b200 import _lib
+  runner = runner_mod.Runner(compute_mode=_lib.COMPUTE_FP32)
+  runner.start(req)
+  canvas = runner.run((0, 0, 0), g64['volume'].shape)
+  assert canvas is not None
+  seg, origins = storage.load_segmentation(str(tmp_path / 'out'), (0, 0, 0))
+  want = g64['segmentation'].copy()
+  want[want < 0] = 0
+  np.testing.assert_array_equal(seg, want.astype(np.uint64))
+  assert sorted(origins) == g64['origins'][:, 0].tolist()
+  assert origins[4].start_zyx == tuple(g64['origins'][3, 1:4]) and origins[4].iters == g64['origins'][3, 4]
+  with np.load(storage.object_prob_path(str(tmp_path / 'out'), (0, 0, 0))) as z:
+    assert np.abs(z['qprob'].astype(int) - g64['seg_prob'].astype(int)).max() <= 1
+  assert canvas.counters['inference-calls'].value == g64['trace'].shape[0]
+  assert runner.counters['voxels-segmented'].value == int((want > 0).sum())
+  assert runner.run((0, 0, 0), g64['volume'].shape) is None          # idempotent restart (runner.py:509-510)
+  runner.stop_executor()
+
+
+def test_canvas_checkpoint_roundtrip(tmp_path, golden_dir, g64):
+  """save_checkpoint / restore_checkpoint with an object in flight resumes to the same result."""
+  from ffn.inference import executor, inference, inference_pb2, inference_utils, seed as seed_mod
+  from ffn.training.models import convstack_3d
+  from ffn_b200 import _lib
+  model = convstack_3d.ConvStack3DFFNModel(fov_size=[33, 33, 33], deltas=[8, 8, 8], depth=12)
+  exe = executor.B200Executor(executor.ExecutorInterface(), model, inference_utils.Counters(),
+                              checkpoint_path=os.path.join(golden_dir, 'fib25_convstack.npz'),
+                              compute_mode=_lib.COMPUTE_FP32)
+  opts = inference_pb2.InferenceOptions(init_activation=0.95, pad_value=0.05, move_threshold=0.9,
+                                        segment_threshold=0.6, min_segment_size=1000)
+  opts.min_boundary_dist.x = opts.min_boundary_dist.y = opts.min_boundary_dist.z = 1
+
+  def make():
+    return inference.Canvas(model.info, exe.get_client(inference_utils.Counters()), g64['volume'], opts,
+                            keep_probability_maps=True, image_mean=128, image_stddev=33)
+  a = make()
+  start = (16, 48, 32)
+  n = a.segment_at(start, max_steps=20)
+  assert n == 20
+  path = str(tmp_path / 'c.cpoint')
+  a.seed_policy = seed_mod.PolicyGrid3d(a)
+  a.save_checkpoint(path, partial_segment_iters=n)
+  b = make()
+  partial = b.restore_checkpoint(path)
+  assert partial == 20
+  np.testing.assert_array_equal(np.asarray(b.seed), np.asarray(a.seed))
+  total_b = b.segment_at(start, partial_segment_iters=partial)
+  total_a = a.segment_at(start, partial_segment_iters=n)
+  assert total_a == total_b == 80
+  np.testing.assert_array_equal(np.asarray(b.seed), np.asarray(a.seed))
+  exe.close()

@@ -1,0 +1,199 @@
+"""CPU-only checks of the host package: wire formats, file layout, counters, seed policies, the
+C-ABI surface, and the 'no CPU fallback' guarantees."""
+
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+from google.protobuf import text_format
+
+from ffn.inference import inference_pb2, inference_utils, movement, seed, storage
+from ffn.utils import bounding_box_pb2
+from ffn_b200 import _lib, distributed
+from oracle import flood_fill as ff
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SAMPLE_REQUEST = """
+image { hdf5: "third_party/neuroproof_examples/training_sample2/grayscale_maps.h5:raw" }
+image_mean: 128
+image_stddev: 33
+checkpoint_interval: 1800
+seed_policy: "PolicyPeaks"
+model_checkpoint_path: "models/fib25/model.ckpt-27465036"
+model_name: "convstack_3d.ConvStack3DFFNModel"
+model_args: "{\\"depth\\": 12, \\"fov_size\\": [33, 33, 33], \\"deltas\\": [8, 8, 8]}"
+segmentation_output_dir: "results/fib25/training2"
+inference_options {
+  init_activation: 0.95
+  pad_value: 0.05
+  move_threshold: 0.9
+  min_boundary_dist { x: 1 y: 1 z: 1}
+  segment_threshold: 0.6
+  min_segment_size: 1000
+}
+"""
+
+
+def test_request_text_format_and_wire_roundtrip():
+  req = inference_pb2.InferenceRequest()
+  text_format.Parse(SAMPLE_REQUEST, req)
+  assert req.model_name == 'convstack_3d.ConvStack3DFFNModel'
+  assert json.loads(req.model_args)['depth'] == 12
+  assert req.batch_size == 1 and req.concurrent_requests == 1          # proto2 defaults
+  assert req.inference_options.disco_seed_threshold == 0.0
+  assert req.image.WhichOneof('volume_path') == 'hdf5'
+  assert req.alignment_options.type == inference_pb2.AlignmentOptions.NO_ALIGNMENT
+  again = inference_pb2.InferenceRequest()
+  again.ParseFromString(req.SerializeToString())
+  assert again == req
+  box = bounding_box_pb2.BoundingBox()
+  text_format.Parse('start { x:0 y:0 z:0 } size { x:250 y:250 z:250 }', box)
+  assert (box.size.x, box.size.y, box.size.z) == (250, 250, 250)
+
+
+def test_field_numbers_match_reference_schema():
+  """Spot-check of tags that matter for reading files written by the reference."""
+  d = inference_pb2.InferenceRequest.DESCRIPTOR.fields_by_name
+  assert {n: d[n].number for n in ('image', 'image_mean', 'model_name', 'model_args', 'batch_size',
+                                   'inference_options', 'segmentation_output_dir', 'seed_policy',
+                                   'init_segmentation', 'seed_masks')} == {
+      'image': 24, 'image_mean': 2, 'model_name': 11, 'model_args': 12, 'batch_size': 27,
+      'inference_options': 14, 'segmentation_output_dir': 15, 'seed_policy': 17, 'init_segmentation': 25,
+      'seed_masks': 30}
+  o = inference_pb2.InferenceOptions.DESCRIPTOR.fields_by_name
+  assert [o[n].number for n in ('init_activation', 'pad_value', 'move_threshold', 'disco_seed_threshold',
+                                'min_boundary_dist', 'segment_threshold', 'min_segment_size')] == [1, 2, 3, 5, 6, 7, 8]
+
+
+def test_storage_paths_and_quantisation(tmp_path, golden_dir):
+  corner = (10, 20, 30)   # z, y, x
+  assert storage.segmentation_path('/o', corner) == '/o/30/20/seg-30_20_10.npz'
+  assert storage.object_prob_path('/o', corner) == '/o/30/20/seg-30_20_10.prob'
+  assert storage.checkpoint_path('/o', corner) == '/o/30/20/seg-30_20_10.cpoint'
+  assert storage.get_corner_from_path('/o/30/20/seg-30_20_10.npz') == corner
+  g = np.load(os.path.join(golden_dir, 'qprob.npz'))
+  np.testing.assert_array_equal(storage.quantize_probability(g['prob']), g['q'])
+  dq = storage.dequantize_probability(np.array([0, 1, 128, 255], np.uint8))
+  assert np.isnan(dq[0]) and abs(dq[2] - 127.5 / 255) < 1e-6
+  labels = np.zeros((4, 4, 4), np.int32)
+  labels[1:3] = 300
+  origins = {300: storage.OriginInfo((1, 2, 3), 7, 0.5)}
+  path = str(tmp_path / '3' / '2' / 'seg-3_2_1.npz')
+  storage.save_subvolume(labels, origins, path, counters='{}')
+  seg, org = storage.load_segmentation(str(tmp_path), (1, 2, 3))
+  assert seg.dtype == np.uint64 and seg.max() == 300 and org[300].iters == 7
+  with np.load(path, allow_pickle=True) as z:
+    assert z['segmentation'].dtype == np.uint16
+
+
+def test_counters_and_timer():
+  c = inference_utils.Counters()
+  sub = c.get_sub_counters()
+  with inference_utils.timer_counter(sub, 'inference'):
+    pass
+  sub['voxels-segmented'].IncrementBy(5)
+  assert sub['inference-calls'].value == 1 and c['voxels-segmented'].value == 5
+  state = sub.dumps()
+  other = inference_utils.Counters()
+  other.loads(state)
+  assert other['voxels-segmented'].value == 5
+
+
+class _FakeCanvas:
+  def __init__(self, shape, image=None):
+    self.shape = shape
+    self.margin = np.array([16, 16, 16])
+    self.image = image if image is not None else np.zeros(shape, np.float32)
+    self.segmentation = np.zeros(shape, np.int32)
+    self.restrictor = None
+    self.voxel_size_zyx = (1, 1, 1)
+
+
+def test_grid_seed_policy_matches_oracle_and_border_filter():
+  cv = _FakeCanvas((48, 56, 64))
+  pol = seed.PolicyGrid3d(cv)
+  got = np.array(list(pol))
+  want = ff.grid_seeds(cv.shape)
+  keep = np.all((want - 16 >= 0) & (want + 16 < np.array(cv.shape)), axis=1)
+  np.testing.assert_array_equal(got, want[keep])
+  pol2 = seed.PolicyGrid3d(cv)
+  first = next(pol2)
+  assert pol2.remaining().shape[0] == got.shape[0] - 1 and first == tuple(got[0])
+  coords, idx = pol2.get_state(previous=True)
+  assert idx == 0 and coords.shape == got.shape
+
+
+def test_policy_peaks_runs_and_is_sorted():
+  from ffn_b200.synthetic import voronoi_phantom
+  vol = voronoi_phantom((48, 64, 64), seed=2, cell_volume=20000.0)
+  cv = _FakeCanvas(vol.shape, (vol.astype(np.float32) - 128) / 33)
+  coords = seed.PolicyPeaks(cv).remaining()
+  assert coords.shape[0] > 3
+  assert [tuple(c) for c in coords] == sorted(tuple(c) for c in coords)
+
+
+def test_host_scored_moves_match_oracle(golden_dir):
+  g = np.load(os.path.join(golden_dir, 'moves.npz'))
+  for i in range(0, int(g['n']), 5):
+    got = sorted(movement.get_scored_move_offsets(g['deltas_%d' % i], g['logits_%d' % i], float(g['threshold'])),
+                 reverse=True)
+    arr = np.asarray([(float(s),) + r for s, r in got], dtype=np.float64).reshape(-1, 4)
+    np.testing.assert_array_equal(arr, g['moves_%d' % i])
+
+
+def test_c_abi_exports_every_declared_symbol():
+  header = open(os.path.join(REPO, 'include', 'ffn_b200.h')).read()
+  declared = set(re.findall(r'\b(ffn_[a-z0-9_]+)\s*\(', header))
+  assert declared, 'no declarations found'
+  lib = _lib.load()
+  missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+  assert not missing, missing
+  assert declared == set(_lib.EXPORTS)
+
+
+def test_no_cpu_fallback_without_gpu():
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip('GPU present')
+  from ffn_b200 import engine as eng, tf_checkpoint
+  w, b = tf_checkpoint.load_convstack_npz(os.path.join(REPO, 'tests', 'golden', 'fib25_convstack.npz'))
+  with pytest.raises(RuntimeError):
+    eng.Engine(w, b)
+
+
+def test_canvas_rejects_foreign_executor_clients():
+  from ffn.inference import executor, inference
+  from ffn.training import model as ffn_model
+  info = ffn_model.ModelInfo([8, 8, 8], [33, 33, 33], [33, 33, 33], [33, 33, 33])
+
+  class Other(executor.ExecutorClient):
+    pass
+  with pytest.raises(TypeError):
+    inference.Canvas(info, Other(inference_utils.Counters(), executor.ExecutorInterface()),
+                     np.zeros((40, 40, 40), np.float32), inference_pb2.InferenceOptions())
+
+
+def test_product_never_imports_oracle():
+  bad = []
+  for root in ('ffn_b200', 'ffn'):
+    for d, _, files in os.walk(os.path.join(REPO, root)):
+      for f in files:
+        if f.endswith('.py'):
+          src = open(os.path.join(d, f)).read()
+          if re.search(r'^\s*(from|import)\s+oracle\b', src, re.M):
+            bad.append(os.path.join(d, f))
+  assert not bad, bad
+
+
+def test_slab_partition_and_offsets():
+  boxes = distributed.slab_boxes((1024, 1024, 1024), 8)
+  assert len(boxes) == 8 and all(b[1] == (512, 512, 512) for b in boxes)
+  cover = np.zeros((4, 4, 4), int)
+  for (lo, sz) in distributed.slab_boxes((4, 4, 4), 8):
+    cover[lo[0]:lo[0] + sz[0], lo[1]:lo[1] + sz[1], lo[2]:lo[2] + sz[2]] += 1
+  assert (cover == 1).all()
+  assert distributed.exclusive_offsets([3, 0, 5]) == [0, 3, 3]
+  assert distributed.slabs_of_rank(8, 1, 2) == [4, 5, 6, 7]

@@ -29,7 +29,7 @@ for v, nm in ((0, 'kat'), (1, 'rate_1cta'), (4, 'rate_allsm'), (2, 'barrier'), (
   if 'selftest%d' % v in which:
     @stage('selftest_' + nm)
     def _():
-      return eng.selftest(v)
+      return eng.selftest(v, n_out=16)
 
 from oracle import flood_fill as ff
 pat = np.load(os.path.join(G, 'net_patches.npz'))
@@ -97,6 +97,12 @@ def run_mode(tag, mode):
     out['hybrid_min_margin'] = hyb.min_margin
     out['golden_trace_equal_hybrid'] = bool(np.array_equal(np.asarray(hyb.trace, np.int32).reshape(-1, 3), gat['trace']))
     cv.close()
+    e.profile(reset=True)
+    cv2 = eng.DeviceCanvas(e, g64['volume'], opts, 128.0, 33.0)
+    st2 = cv2.segment_at(start)
+    out['profile'] = e.profile()
+    out['profile_device_seconds'] = cv2.counters().device_seconds
+    cv2.close()
     return out
 
   @stage(tag + '_segment_all')

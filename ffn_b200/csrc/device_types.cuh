@@ -76,6 +76,8 @@ struct CanvasDev {
   int* q_pos;                 // [cap][3]
   int q_cap;
   unsigned* lattice;          // epoch stamps over the quantised lattice
+  int* trace;                 // optional event log [cap][4]: (type, z, y, x); null = off
+  int trace_cap;
   int lat_dim[3], lat_off[3];
 };
 
@@ -118,6 +120,7 @@ struct CanvasState {
   unsigned long long seg_t0;  // globaltimer at segment start
   long long n_origins, n_overlaps;
   int overflow;               // origins / overlaps / queue capacity exceeded
+  int n_trace;                // events written to the trace log
   FfnCounters ctr;
 };
 

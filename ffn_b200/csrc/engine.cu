@@ -448,6 +448,7 @@ void ffn_canvas_destroy(FfnCanvas* c) {
   cudaFree(c->cv.lattice);
   cudaFree(c->cv.q_score);
   cudaFree(c->cv.q_pos);
+  cudaFree(c->cv.trace);
   cudaFree(c->d_state);
   cudaFree(c->d_pred);
   cudaFree(c->d_mask);
@@ -806,6 +807,27 @@ int ffn_canvas_set_resume(FfnCanvas* c, int64_t iters, const int32_t min_pos[3],
   st.have_cur = 0;
   st.seg_t0 = 0;
   c->resume_pending = true;
+  return push_state(c);
+}
+
+int ffn_canvas_trace(FfnCanvas* c, int64_t capacity, int32_t* events_out, int64_t* n_events) {
+  if (!c) return fail("null canvas");
+  if (set_device(c->eng)) return 1;
+  if (pull_state(c)) return 1;
+  if (events_out && n_events) {   // fetch what was logged so far
+    const int64_t n = std::min<int64_t>(c->h_state.n_trace, c->cv.trace_cap);
+    *n_events = c->h_state.n_trace;
+    if (n > 0) CUDA_OK(cudaMemcpy(events_out, c->cv.trace, (size_t)n * 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  cudaFree(c->cv.trace);
+  c->cv.trace = nullptr;
+  c->cv.trace_cap = 0;
+  if (capacity > 0) {
+    if (dev_alloc(&c->cv.trace, (size_t)capacity * 4)) return 1;
+    c->cv.trace_cap = (int)capacity;
+  }
+  c->h_state.n_trace = 0;
   return push_state(c);
 }
 

@@ -503,12 +503,27 @@ __device__ __forceinline__ float seed_value(const KParams& p, const CanvasState*
   return __ldcg(p.cv.seed + cv_index(p.cv, z, y, x));
 }
 
+// Optional event log for debugging / history export (thread 0 of CTA 0 only).
+enum TraceEvent : int { EV_PUSH = 1, EV_POP_VALID = 2, EV_POP_INVALID = 3, EV_POP_THRESHOLD = 4, EV_POP_DONE = 5,
+                        EV_STEP = 6, EV_SEED_INVALID = 7, EV_SEED_START = 8 };
+__device__ __forceinline__ void trace_event(const KParams& p, CanvasState* st, int type, int z, int y, int x) {
+  if (!p.cv.trace) return;
+  const int i = st->n_trace++;
+  if (i < p.cv.trace_cap) {
+    p.cv.trace[4 * i] = type;
+    p.cv.trace[4 * i + 1] = z;
+    p.cv.trace[4 * i + 2] = y;
+    p.cv.trace[4 * i + 3] = x;
+  }
+}
+
 __device__ __forceinline__ void push_move(const KParams& p, CanvasState* st, float score, int z, int y, int x) {
   if (st->q_tail >= p.cv.q_cap) {
     st->overflow |= 1;
     return;
   }
   const int t = st->q_tail++;
+  trace_event(p, st, EV_PUSH, z, y, x);
   p.cv.q_score[t] = score;
   p.cv.q_pos[3 * t + 0] = z;
   p.cv.q_pos[3 * t + 1] = y;
@@ -579,8 +594,18 @@ __device__ void policy_update(Ctx& c, CanvasState* st, bool disco) {
   if (c.tid == 0) {
     p.cv.lattice[lattice_index(p, st, st->cur[0], st->cur[1], st->cur[2])] = st->epoch;
     int order[6], n = 0;
-    for (int f = 0; f < 6; ++f)
-      if (s_ok[f]) order[n++] = f;
+    for (int f = 0; f < 6; ++f) {
+      if (!s_ok[f]) continue;
+      // movement.py:95-99: identical (score, offset) tuples are yielded once — two faces share an
+      // edge, and the same edge voxel can be the arg-max of both.
+      bool dup = false;
+      for (int i = 0; i < n; ++i) {
+        const int h = order[i];
+        dup |= s_rel[3 * f] == s_rel[3 * h] && s_rel[3 * f + 1] == s_rel[3 * h + 1] &&
+               s_rel[3 * f + 2] == s_rel[3 * h + 2] && s_score[f] == s_score[h];
+      }
+      if (!dup) order[n++] = f;
+    }
     // sorted(..., reverse=True) on (score, (dz, dy, dx)) tuples (movement.py:218)
     for (int i = 1; i < n; ++i) {
       const int f = order[i];
@@ -621,18 +646,22 @@ __device__ bool is_valid_pos(const KParams& p, CanvasState* st, bool disco, int 
     const float v = seed_value(p, st, disco, z, y, x);
     if (v < p.cv.opt.move_threshold) {
       st->ctr.skip_threshold++;
+      trace_event(p, st, EV_POP_THRESHOLD, z, y, x);
       return false;
     }
   }
   if (z - g.mz < 0 || y - g.my < 0 || x - g.mx < 0 || z + g.mz >= p.cv.sz || y + g.my >= p.cv.sy ||
       x + g.mx >= p.cv.sx) {
     st->ctr.skip_invalid_pos++;
+    trace_event(p, st, ignore_move_threshold ? EV_SEED_INVALID : EV_POP_INVALID, z, y, x);
     return false;
   }
   if (__ldcg(p.cv.seg + cv_index(p.cv, z, y, x)) > 0) {
     st->ctr.skip_invalid_pos++;
+    trace_event(p, st, ignore_move_threshold ? EV_SEED_INVALID : EV_POP_INVALID, z, y, x);
     return false;
   }
+  if (!ignore_move_threshold) trace_event(p, st, EV_POP_VALID, z, y, x);
   return true;
 }
 
@@ -643,7 +672,10 @@ __device__ bool pop_next(const KParams& p, CanvasState* st, bool disco, int& z, 
     z = p.cv.q_pos[3 * h];
     y = p.cv.q_pos[3 * h + 1];
     x = p.cv.q_pos[3 * h + 2];
-    if (p.cv.lattice[lattice_index(p, st, z, y, x)] == st->epoch) continue;
+    if (p.cv.lattice[lattice_index(p, st, z, y, x)] == st->epoch) {
+      trace_event(p, st, EV_POP_DONE, z, y, x);
+      continue;
+    }
     if (is_valid_pos(p, st, disco, z, y, x, false)) return true;
   }
   return false;
@@ -770,6 +802,7 @@ __device__ void leader_decide(Ctx& c) {
         st->cur[1] = y;
         st->cur[2] = x;
         st->have_cur = 1;
+        trace_event(p, st, EV_STEP, z, y, x);
         for (int k = 0; k < 3; ++k) {
           st->dirty_lo[k] = min(st->dirty_lo[k], st->cur[k] - (k == 0 ? g.mz : k == 1 ? g.my : g.mx));
           st->dirty_hi[k] = max(st->dirty_hi[k], st->cur[k] + (k == 0 ? g.mz : k == 1 ? g.my : g.mx) + 1);

@@ -220,6 +220,17 @@ class DeviceCanvas:
   def set_resume(self, iters: int, min_pos, max_pos):
     _lib.check(self._lib.ffn_canvas_set_resume(self._h, int(iters), _lib.i3(min_pos), _lib.i3(max_pos)))
 
+  def start_trace(self, capacity: int = 1 << 20):
+    self._trace_cap = int(capacity)
+    _lib.check(self._lib.ffn_canvas_trace(self._h, int(capacity), None, None))
+
+  def get_trace(self) -> np.ndarray:
+    """[n, 4] int32 rows (type, z, y, x); see ffn_canvas_trace."""
+    buf = np.zeros((getattr(self, '_trace_cap', 0), 4), dtype=np.int32)
+    n = C.c_int64(0)
+    _lib.check(self._lib.ffn_canvas_trace(self._h, 0, _lib.ptr(buf), C.byref(n)))
+    return buf[:min(int(n.value), buf.shape[0])]
+
   def set_max_id(self, max_id: int):
     _lib.check(self._lib.ffn_canvas_set_max_id(self._h, int(max_id)))
 

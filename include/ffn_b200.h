@@ -181,6 +181,11 @@ int ffn_canvas_policy_state_set(FfnCanvas* canvas, const double* queue_szyx, int
  * the given iteration count and extents) and commits it, then continues with its seed list. */
 int ffn_canvas_set_resume(FfnCanvas* canvas, int64_t iters, const int32_t min_pos[3],
                           const int32_t max_pos[3]);
+/* Event log of the device loop (debugging, Canvas.history export).  Call with capacity > 0 and
+ * events_out == NULL to (re)start logging, capacity == 0 to stop; call with events_out != NULL to
+ * fetch: rows of (type, z, y, x), type 1 push, 2 pop valid, 3 pop invalid, 4 pop below threshold,
+ * 5 pop already done, 6 FoV step, 7 seed invalid.  *n_events = events produced (may exceed capacity). */
+int ffn_canvas_trace(FfnCanvas* canvas, int64_t capacity, int32_t* events_out, int64_t* n_events);
 /* Canvas._max_id / counters carried across calls (checkpoint restore, init segmentation). */
 int ffn_canvas_set_max_id(FfnCanvas* canvas, int64_t max_id);
 int ffn_canvas_get_counters(FfnCanvas* canvas, FfnCounters* out);

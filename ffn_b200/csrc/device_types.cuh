@@ -11,11 +11,14 @@ namespace ffn {
 
 constexpr int kThreads = 288;     // warps 0-7: two epilogue quads (TMEM lane quarters x 2 tiles); warp 8: TMA + UMMA issue
 constexpr int kIssueWarp = 8;
-constexpr int kTileM = 128;       // UMMA M: FoV rows per tensor-core tile
+constexpr int kTileM = 128;       // UMMA M: accumulator rows per tensor-core tile
+constexpr int kTileOut = 126;     // FoV rows a tile OUTPUTS: the dx = -1/+1 partial sums live one row up/down, so
+                                  // the first and last accumulator row of every tile only feed their neighbours
+constexpr int kStackN = 96;       // UMMA N: the three dx taps of a (dz, dy) tap-row stacked along N
 constexpr int kFeat = 32;         // feature maps of every hidden layer (UMMA N)
 constexpr int kGroupTiles = 3;    // tiles whose operands are staged in shared memory together
 constexpr int kMaxConv = 32;      // 2 * depth limit
-constexpr int kTmemCols = 128;    // >= kGroupTiles * kFeat, power of two
+constexpr int kTmemCols = 512;    // >= kGroupTiles * kStackN, power of two
 
 // Field-of-view geometry in the "row" space the kernels work in.
 //
@@ -30,7 +33,7 @@ struct Geom {
   int nconv;        // number of 3x3x3 convolutions (2 * depth)
   int xp, pp;       // row pitches
   int nr;           // rows spanned by the FoV: (fz-1)*pp + (fy-1)*xp + fx
-  int nt;           // tiles: ceil(nr / 128)
+  int nt;           // tiles: ceil(nr / kTileOut)
   int halo;         // xp + 1: in-plane reach of a tap, in rows
   int guard;        // zero rows before row 0 / after the last tile in global activation buffers
   int rows_alloc;   // guard + nt*128 + guard
@@ -38,7 +41,8 @@ struct Geom {
 };
 
 struct Weights {
-  const __half* w16;   // per layer [27][kchunk][4 n-groups][8 n][8 k] fp16 (UMMA K-major, no swizzle)
+  const __half* w16;   // per layer [9 tap-rows][kchunk][12 n-groups][8 n][8 k] fp16 (UMMA K-major, no swizzle),
+                       // n = dx * 32 + cout
   const float* w32;    // per layer [27][cin_padded][32] fp32
   const float* bias;   // [nconv][32]
   const float* w_lom;  // [32]
@@ -175,11 +179,11 @@ __host__ __device__ inline SmemLayout smem_layout(const Geom& g) {
   SmemLayout s;
   s.wbuf = 0;
   s.act = 2 * 27 * 4 * 512;   // 110592
-  const int seg_rows = kGroupTiles * kTileM + 2 * g.halo;
+  const int seg_rows = kGroupTiles * kTileOut + 2 * g.halo;
   const int act_bytes = 3 * 4 * seg_rows * 16;
   s.bias = s.act + act_bytes;
   s.bars = s.bias + (kMaxConv + 1) * 32 * 4 + 16;
-  s.total = s.bars + 1024;
+  s.total = s.bars + 1024 + 3072;   // + epilogue warp-boundary exchange + conv_lom partial dots
   return s;
 }
 

@@ -99,7 +99,7 @@ Geom make_geom(const FfnModelDesc& m) {
   g.xp = g.fx + 1;
   g.pp = (g.fy + 1) * g.xp;
   g.nr = (g.fz - 1) * g.pp + (g.fy - 1) * g.xp + g.fx;
-  g.nt = (g.nr + kTileM - 1) / kTileM;
+  g.nt = (g.nr + kTileOut - 1) / kTileOut;
   g.halo = g.xp + 1;
   g.guard = ((g.pp + g.halo + 7) / 8) * 8;
   g.rows_alloc = g.guard + g.nt * kTileM + g.guard;
@@ -162,7 +162,10 @@ void pack_weights(const Geom& g, const float* const* w, std::vector<__half>& w16
       for (int ci = 0; ci < cin; ++ci)
         for (int co = 0; co < 32; ++co) {
           const float v = w[l][((size_t)tap * cin + ci) * 32 + co];   // DHWIO: tap = kz*9 + ky*3 + kx
-          d16[(((size_t)tap * nch + ci / 8) * 4 + co / 8) * 64 + (co % 8) * 8 + (ci % 8)] = __float2half_rn(v);
+          {
+            const int row = tap / 3, n = (tap % 3) * 32 + co;   // tap-row (kz, ky); n stacks kx
+            d16[(((size_t)row * nch + ci / 8) * 12 + n / 8) * 64 + (n % 8) * 8 + (ci % 8)] = __float2half_rn(v);
+          }
           d32[((size_t)tap * cin_pad + ci) * 32 + co] = v;
         }
   }

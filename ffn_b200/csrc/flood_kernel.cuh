@@ -36,13 +36,14 @@ struct Ctx {
   unsigned char* smem;
   float* s_bias;               // [(nconv)*32] biases, then w_lom[32], b_lom
   uint64_t* mb_w;              // [2]
-  uint64_t* mb_act;            // [1]
+  uint64_t* mb_act;            // [3] one per z-plane segment (dz = -1, 0, +1)
   uint64_t* mb_mma;            // [kGroupTiles]
   uint32_t* s_tmem;            // TMEM base address
   int* s_misc;                 // [0] step count>=th accumulator, [1..] leader scratch
-  int* s_aoff;                 // UMMA A-descriptor row offsets per (tap, k-pair): [27] for layer 0, [54] others
+  float* s_xchg;               // [2 tile parities][2 halves][4 warps][2][16] partial sums crossing warp boundaries
+  float* s_dot;                // [2][128] conv_lom partial dot products of the upper channel half
   long long* prof;             // profiling slots of this CTA (null unless CTA 0 / G-1)
-  uint32_t par_w[2], par_act, par_mma[kGroupTiles];
+  uint32_t par_w[2], par_act[3], par_mma[kGroupTiles];
   int w_pending[2];
   uint32_t tmem_base;
 };
@@ -115,7 +116,7 @@ __device__ void stage_fov(Ctx& c, int pz, int py, int px, int batch_idx) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
   const bool predict = p.job.mode == MODE_PREDICT;
-  for (int r = c.t_begin * kTileM + c.tid; r < c.t_end * kTileM; r += kThreads) {
+  for (int r = c.t_begin * kTileOut + c.tid; r < c.t_end * kTileOut; r += kThreads) {
     int z, y, x;
     if (!row_to_zyx(g, r, z, y, x)) continue;
     float img, s, fed;
@@ -222,6 +223,59 @@ __device__ __forceinline__ void epilogue_row(const Ctx& c, int layer, int r, flo
   }
 }
 
+// Tensor-core epilogue for one FoV row and ONE HALF of the feature maps (16 channels): the two
+// epilogue quads split every tile by channel so a tile's latency is halved.  Same arithmetic as
+// epilogue_row; for the last layer returns this half's share of <relu(net), w_lom>.
+__device__ __forceinline__ float epilogue_half(const Ctx& c, int layer, int r, float (&v)[16], int half,
+                                               const float4* pre_res) {
+  const KParams& p = *c.p;
+  const Geom& g = p.g;
+  const float* b = c.s_bias + layer * 32 + half * 16;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] += b[k];
+  const bool is_b = (layer & 1) != 0;
+  const bool last = layer == g.nconv - 1;
+  const size_t ra = (size_t)g.guard + r;
+  if (is_b) {
+    if (layer > 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[4 * q + 0] += pre_res[q].x;
+        v[4 * q + 1] += pre_res[q].y;
+        v[4 * q + 2] += pre_res[q].z;
+        v[4 * q + 3] += pre_res[q].w;
+      }
+    }
+    if (!last) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        p.ws.res[(size_t)(half * 4 + q) * g.rows_alloc + ra] =
+            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
+  if (last) {
+    const float* wl = c.s_bias + g.nconv * 32 + half * 16;
+    float upd = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) upd = fmaf(v[k], wl[k], upd);
+    return upd;
+  }
+  __half* dst = p.ws.act_h[layer & 1];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint4 o;
+    __half2 h;
+    h = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+    *reinterpret_cast<uint4*>(dst + ((size_t)(half * 2 + q) * g.rows_alloc + ra) * 8) = o;
+  }
+  return 0.f;
+}
+
 // ------------------------------------------------------------------------------------------
 // Tensor-core layer: implicit GEMM, M = 128 FoV rows, N = 32 features, K = 27 taps x Cin.
 // A = activation rows (K-major, no swizzle: [k-chunk][row] 16-byte units, so a tap is a shifted
@@ -235,26 +289,34 @@ __device__ __forceinline__ void tc_issue_weight_load(Ctx& c, int layer) {
   sm100::bulk_g2s(c.smem + buf * (27 * 4 * 512), p.w.w16 + w16_layer_offset_halfs(layer), bytes, &c.mb_w[buf]);
 }
 
-// Issues the 27 * NCH/2 UMMAs (128 x 32 x 16) of one tile.  Fully unrolled: every A start-address
-// offset is (const * seg_rows + const * xp + const), so the loop body is two adds and the UMMA.
+// Issues the 3 * NCH/2 UMMAs (128 x 96 x 16) of one tile that read z-plane segment `tz`: one per dy
+// tap-row and k-pair; the three dx taps ride along N.  Fully unrolled: every A start-address offset
+// is (const * seg_rows + const * xp), so the loop body is two adds and the UMMA.
 template <int NCH>
-__device__ __forceinline__ void tc_issue_tile(uint32_t d, uint32_t a_lo, uint32_t b_lo, int seg_rows, int halo,
-                                              int xp) {
-  const uint32_t idesc = sm100::umma_idesc_f16(kTileM, kFeat);
+__device__ __forceinline__ void tc_issue_plane(uint32_t d, uint32_t a_lo, uint32_t b_lo, int seg_rows, int xp, int tz,
+                                               uint32_t accumulate) {
+  const uint32_t idesc = sm100::umma_idesc_f16(kTileM, kStackN);
   const uint64_t hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
 #pragma unroll
-  for (int tap = 0; tap < 27; ++tap) {
-    const int tz = tap / 9, ty = (tap / 3) % 3, tx = tap % 3;
+  for (int ty = 0; ty < 3; ++ty) {
 #pragma unroll
     for (int j = 0; j < NCH / 2; ++j) {
-      const uint32_t aoff = (uint32_t)((tz * NCH + 2 * j) * seg_rows + halo + (ty - 1) * xp + (tx - 1));
-      const uint32_t boff = (uint32_t)((tap * (NCH / 2) + j) * 64);
+      const uint32_t aoff = (uint32_t)((tz * NCH + 2 * j) * seg_rows + ty * xp);
+      const uint32_t boff = (uint32_t)(((tz * 3 + ty) * NCH + 2 * j) * (12 * 128 / 16));
       sm100::umma_f16(d, hi | (uint64_t)(a_lo + aoff), hi | (uint64_t)(b_lo + boff), idesc,
-                      (tap | j) != 0 ? 1u : 0u);
+                      (ty | j) != 0 ? 1u : accumulate);
     }
   }
 }
 
+__device__ __forceinline__ void quad_sync(int quad) {   // the four epilogue warps of one tile
+  asm volatile("bar.sync %0, 128;" ::"r"(quad + 1) : "memory");
+}
+
+// Tensor-core layer.  Accumulator row m of a tile holds, for the FoV row u = tile_row0 - 1 + m,
+//   D[u][dx*32 + co] = sum_{dz,dy,ci} act[u + dz*pp + dy*xp][ci] * W[dz,dy,dx][ci][co]
+// and the convolution output is out[v] = D[v-1][dx=-1] + D[v][dx=0] + D[v+1][dx=+1]: one lane up /
+// down, done with warp shuffles (+ a 2 KB shared-memory exchange at the three warp boundaries).
 __device__ void tc_layer(Ctx& c, int layer) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
@@ -263,7 +325,7 @@ __device__ void tc_layer(Ctx& c, int layer) {
   const __half* in = layer == 0 ? p.ws.act0_h : p.ws.act_h[(layer - 1) & 1];
   const int buf = layer & 1;
   unsigned char* act_smem = c.smem + 2 * 27 * 4 * 512;
-  const int seg_rows = kGroupTiles * kTileM + 2 * g.halo;   // fixed k-chunk plane pitch (rows)
+  const int seg_rows = kGroupTiles * kTileOut + 2 * g.halo;   // fixed k-chunk plane pitch (rows)
   const bool issuer = c.warp == kIssueWarp && c.lane == 0;
   const bool need_res = (layer & 1) && layer > 1;
 
@@ -275,73 +337,124 @@ __device__ void tc_layer(Ctx& c, int layer) {
   int hit = 0;
   for (int g0 = c.t_begin; g0 < c.t_end; g0 += kGroupTiles) {
     const int ng = min(kGroupTiles, c.t_end - g0);
-    const int r0 = g0 * kTileM;
+    const int r0 = g0 * kTileOut;
     const bool first = g0 == c.t_begin;
     if (c.warp == kIssueWarp) {
       if (c.lane == 0) {
-        // ---- TMA producer: three z-plane segments x k-chunks of the input activations
-        const int load_rows = ng * kTileM + 2 * g.halo;
+        // ---- TMA producer: three z-plane segments x k-chunks of the input activations, centre plane
+        // first; each segment has its own mbarrier so the UMMAs of a plane start as soon as it lands.
+        const int load_rows = ng * kTileOut + 2 * g.halo;
         long long t0 = clock64();
         sm100::fence_proxy_async();
-        sm100::mbar_expect_tx(c.mb_act, (uint32_t)(3 * nch * load_rows * 16));
-        for (int dzi = 0; dzi < 3; ++dzi)
+        const int order[3] = {1, 0, 2};
+        for (int oi = 0; oi < 3; ++oi) {
+          const int dzi = order[oi];
+          sm100::mbar_expect_tx(&c.mb_act[dzi], (uint32_t)(nch * load_rows * 16));
           for (int ch = 0; ch < nch; ++ch)
             sm100::bulk_g2s(act_smem + (size_t)(dzi * nch + ch) * seg_rows * 16,
                             in + ((size_t)ch * g.rows_alloc + g.guard + r0 + (dzi - 1) * g.pp - g.halo) * 8,
-                            (uint32_t)load_rows * 16, c.mb_act);
-        mbar_wait(c, c.mb_act, c.par_act);
-        prof_add(c, 1, clock64() - t0);
-        if (first) {
-          t0 = clock64();
-          mbar_wait(c, &c.mb_w[buf], c.par_w[buf]);
-          prof_add(c, 2, clock64() - t0);
+                            (uint32_t)load_rows * 16, &c.mb_act[dzi]);
         }
-        sm100::tc_fence_after();
+        if (first) {
+          const long long tw = clock64();
+          mbar_wait(c, &c.mb_w[buf], c.par_w[buf]);
+          prof_add(c, 2, clock64() - tw);
+        }
         // ---- UMMA issue: only the 14-bit start-address field changes between instructions
-        t0 = clock64();
         const uint32_t a_lo = ((sm100::smem_u32(act_smem) >> 4) & 0x3FFFu) | ((uint32_t)seg_rows << 16);
-        const uint32_t b_lo = ((sm100::smem_u32(c.smem + buf * (27 * 4 * 512)) >> 4) & 0x3FFFu) | ((512u >> 4) << 16);
+        const uint32_t b_lo = ((sm100::smem_u32(c.smem + buf * (27 * 4 * 512)) >> 4) & 0x3FFFu) | ((12u * 128u >> 4) << 16);
+        long long issue_cycles = 0;
         for (int i = 0; i < ng; ++i) {
-          const uint32_t d = c.tmem_base + (uint32_t)(i * kFeat);
-          if (layer == 0) {
-            tc_issue_tile<2>(d, a_lo + (uint32_t)(i * kTileM), b_lo, seg_rows, g.halo, g.xp);
-          } else {
-            tc_issue_tile<4>(d, a_lo + (uint32_t)(i * kTileM), b_lo, seg_rows, g.halo, g.xp);
+          const uint32_t d = c.tmem_base + (uint32_t)(i * kStackN);
+          for (int oi = 0; oi < 3; ++oi) {
+            const int tz = order[oi];
+            if (i == 0) {
+              mbar_wait(c, &c.mb_act[tz], c.par_act[tz]);
+              sm100::tc_fence_after();
+              if (oi == 0) prof_add(c, 1, clock64() - t0);
+            }
+            const long long ti = clock64();
+            if (layer == 0) {
+              tc_issue_plane<2>(d, a_lo + (uint32_t)(i * kTileOut), b_lo, seg_rows, g.xp, tz, oi ? 1u : 0u);
+            } else {
+              tc_issue_plane<4>(d, a_lo + (uint32_t)(i * kTileOut), b_lo, seg_rows, g.xp, tz, oi ? 1u : 0u);
+            }
+            issue_cycles += clock64() - ti;
           }
           sm100::umma_commit(&c.mb_mma[i]);
         }
+        t0 = clock64() - issue_cycles;
         prof_add(c, 3, clock64() - t0);
       }
       __syncwarp();
     } else {
-      // ---- Epilogue: warps 0-3 take tiles 0 and 2, warps 4-7 tile 1; warp w reads TMEM lanes 32*(w%4)...
-      for (int i = c.warp >> 2; i < ng; i += 2) {
-        const int r = r0 + i * kTileM + (c.warp & 3) * 32 + c.lane;
+      // ---- Epilogue: every tile is handled by all eight warps — warp w reads TMEM lanes 32*(w%4)..,
+      // quad 0 (warps 0-3) takes feature maps 0-15, quad 1 (warps 4-7) feature maps 16-31.
+      const int half = c.warp >> 2, wq = c.warp & 3;
+      const bool last = layer == g.nconv - 1;
+      for (int i = 0; i < ng; ++i) {
+        float* xch = c.s_xchg + ((i & 1) * 2 + half) * (4 * 2 * 16);   // double-buffered by tile parity
+        const int m = wq * 32 + c.lane;                       // accumulator row of this thread
+        const int r = r0 + i * kTileOut - 1 + m;              // FoV row it holds partial sums for
         int z, y, x;
-        const bool valid = row_to_zyx(g, r, z, y, x);
-        float4 pre[8];
+        const bool valid = m >= 1 && m <= kTileOut && r >= 0 && row_to_zyx(g, r, z, y, x);
+        float4 pre[4];
         if (need_res && valid) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) pre[q] = __ldcg(p.ws.res + (size_t)q * g.rows_alloc + g.guard + r);
+          for (int q = 0; q < 4; ++q)
+            pre[q] = __ldcg(p.ws.res + (size_t)(half * 4 + q) * g.rows_alloc + g.guard + r);
         }
         long long t0 = clock64();
         mbar_wait(c, &c.mb_mma[i], c.par_mma[i]);
         if (c.tid == 0) prof_add(c, 4, clock64() - t0);
         t0 = clock64();
         sm100::tc_fence_after();
-        uint32_t raw[32];
-        sm100::tmem_ld32(c.tmem_base + ((uint32_t)((c.warp & 3) * 32) << 16) + (uint32_t)(i * kFeat), raw);
+        const uint32_t tbase = c.tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(i * kStackN + half * 16);
+        uint32_t a[16], b[16], d2[16];
+        sm100::tmem_ld16(tbase, a);          // dx = -1 block: consumed by the lane above (m + 1)
+        sm100::tmem_ld16(tbase + 32, b);     // dx =  0 block
+        sm100::tmem_ld16(tbase + 64, d2);    // dx = +1 block: consumed by the lane below (m - 1)
         sm100::tmem_ld_wait();
-        if (valid) {
-          float v[32];
+        if (c.lane == 31) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
-          epilogue_row(c, layer, r, v, hit, need_res ? pre : nullptr);
+          for (int k = 0; k < 16; ++k) xch[(wq * 2 + 0) * 16 + k] = __uint_as_float(a[k]);
+        }
+        if (c.lane == 0) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) xch[(wq * 2 + 1) * 16 + k] = __uint_as_float(d2[k]);
+        }
+        quad_sync(half);
+        // out[v] = D[v-1][dx=-1] + D[v][dx=0] + D[v+1][dx=+1]
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          float up = __shfl_up_sync(0xffffffffu, __uint_as_float(a[k]), 1);      // from lane - 1
+          float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k]), 1);   // from lane + 1
+          if (c.lane == 0 && wq > 0) up = xch[((wq - 1) * 2 + 0) * 16 + k];
+          if (c.lane == 31 && wq < 3) dn = xch[((wq + 1) * 2 + 1) * 16 + k];
+          v[k] = up + __uint_as_float(b[k]) + dn;
+        }
+        float part = 0.f;
+        if (valid) part = epilogue_half(c, layer, r, v, half, pre);
+        if (last) {
+          // conv_lom: combine the two halves' dot products, then logits = seed + update
+          float* dot = c.s_dot + (i & 1) * kTileM;
+          if (half == 1) dot[m] = part;
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          if (half == 0 && valid) {
+            const float* wl = c.s_bias + g.nconv * 32;
+            const float upd = part + dot[m] + wl[32];
+            const float raw = p.ws.seed_raw[r];
+            const float fed = isnan(raw) ? p.cv.opt.pad_value : raw;
+            const float logit = fed + upd;
+            p.ws.logits[r] = logit;
+            hit += (logit >= p.cv.opt.move_threshold) ? 1 : 0;
+          }
         }
         if (c.tid == 0) prof_add(c, 5, clock64() - t0);
       }
     }
-    c.par_act ^= 1;
+    for (int i = 0; i < 3; ++i) c.par_act[i] ^= 1;
     if (first) {
       c.par_w[buf] ^= 1;
       c.w_pending[buf] = 0;
@@ -376,7 +489,7 @@ __device__ void f32_layer(Ctx& c, int layer) {
   }
   __syncthreads();
   int hit = 0;
-  for (int r = c.t_begin * kTileM + c.tid; r < c.t_end * kTileM; r += kThreads) {
+  for (int r = c.t_begin * kTileOut + c.tid; r < c.t_end * kTileOut; r += kThreads) {
     int z, y, x;
     if (!row_to_zyx(g, r, z, y, x)) continue;
     float v[32];
@@ -454,7 +567,7 @@ __device__ void tail_paste(Ctx& c, int pz, int py, int px, int batch_idx) {
   const Geom& g = p.g;
   const bool predict = p.job.mode == MODE_PREDICT;
   const bool disco = predict ? false : disco_active(p);
-  for (int r = c.t_begin * kTileM + c.tid; r < c.t_end * kTileM; r += kThreads) {
+  for (int r = c.t_begin * kTileOut + c.tid; r < c.t_end * kTileOut; r += kThreads) {
     int z, y, x;
     if (!row_to_zyx(g, r, z, y, x)) continue;
     const size_t fi = ((size_t)z * g.fy + y) * g.fx + x;
@@ -552,16 +665,36 @@ __device__ void policy_update(Ctx& c, CanvasState* st, bool disco) {
       const int n0 = 2 * del[a0] + 1, n1 = 2 * del[a1] + 1;
       float best = -CUDART_INF_F;
       int best_i = 0x7fffffff;
-      for (int e = c.lane; e < n0 * n1; e += 32) {
-        const int i0 = e / n1, i1 = e - i0 * n1;
-        int zyx[3];
-        zyx[axis] = cen[axis] + off;
-        zyx[a0] = cen[a0] - del[a0] + i0;
-        zyx[a1] = cen[a1] - del[a1] + i1;
-        const float v = merged_row(p, zyx[0] * g.pp + zyx[1] * g.xp + zyx[2], disco);
-        if (v > best || best_i == 0x7fffffff) {
-          best = v;
-          best_i = e;
+      // eight independent L2 loads in flight per lane, then the (ordered) comparisons
+      for (int base = c.lane; base < n0 * n1; base += 256) {
+        float lg[8], od[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = base + 32 * u;
+          lg[u] = 0.f;
+          od[u] = 0.f;
+          if (e < n0 * n1) {
+            const int i0 = e / n1, i1 = e - i0 * n1;
+            int zyx[3];
+            zyx[axis] = cen[axis] + off;
+            zyx[a0] = cen[a0] - del[a0] + i0;
+            zyx[a1] = cen[a1] - del[a1] + i1;
+            const int row = zyx[0] * g.pp + zyx[1] * g.xp + zyx[2];
+            lg[u] = __ldcg(p.ws.logits + row);
+            if (disco) od[u] = __ldcg(p.ws.seed_raw + row);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = base + 32 * u;
+          if (e < n0 * n1) {
+            float v = lg[u];
+            if (disco && od[u] < 0.f && v > od[u]) v = od[u];
+            if (v > best || best_i == 0x7fffffff) {
+              best = v;
+              best_i = e;
+            }
+          }
         }
       }
 #pragma unroll
@@ -665,18 +798,55 @@ __device__ bool is_valid_pos(const KParams& p, CanvasState* st, bool disco, int 
   return true;
 }
 
-// FaceMaxMovementPolicy.__next__ (movement.py:186-198); thread 0 only.
+// FaceMaxMovementPolicy.__next__ (movement.py:186-198) + Canvas.is_valid_pos (inference.py:312-346)
+// for queue entries; thread 0 only.  The lattice stamp, the seed value and the label of a
+// candidate are independent, so their loads are issued together and only the decisions are ordered.
 __device__ bool pop_next(const KParams& p, CanvasState* st, bool disco, int& z, int& y, int& x) {
+  const Geom& g = p.g;
   while (st->q_head < st->q_tail) {
     const int h = st->q_head++;
     z = p.cv.q_pos[3 * h];
     y = p.cv.q_pos[3 * h + 1];
     x = p.cv.q_pos[3 * h + 2];
-    if (p.cv.lattice[lattice_index(p, st, z, y, x)] == st->epoch) {
+    const unsigned stamp = p.cv.lattice[lattice_index(p, st, z, y, x)];
+    const bool inside = z >= 0 && y >= 0 && x >= 0 && z < p.cv.sz && y < p.cv.sy && x < p.cv.sx;
+    float v = 0.f, old = 0.f;
+    int sg = 0;
+    bool in_fov = false;
+    if (inside) {
+      const size_t i = cv_index(p.cv, z, y, x);
+      sg = __ldcg(p.cv.seg + i);
+      if (st->have_cur) {
+        const int fz = z - (st->cur[0] - g.mz), fy = y - (st->cur[1] - g.my), fx = x - (st->cur[2] - g.mx);
+        in_fov = fz >= 0 && fz < g.fz && fy >= 0 && fy < g.fy && fx >= 0 && fx < g.fx;
+        if (in_fov) {
+          const int row = fz * g.pp + fy * g.xp + fx;
+          v = __ldcg(p.ws.logits + row);
+          old = __ldcg(p.ws.seed_raw + row);
+        }
+      }
+      if (!in_fov) v = __ldcg(p.cv.seed + i);
+    }
+    if (stamp == st->epoch) {
       trace_event(p, st, EV_POP_DONE, z, y, x);
       continue;
     }
-    if (is_valid_pos(p, st, disco, z, y, x, false)) return true;
+    if (inside) {
+      if (in_fov && disco && old < 0.f && v > old) v = old;
+      if (v < p.cv.opt.move_threshold) {
+        st->ctr.skip_threshold++;
+        trace_event(p, st, EV_POP_THRESHOLD, z, y, x);
+        continue;
+      }
+    }
+    if (z - g.mz < 0 || y - g.my < 0 || x - g.mx < 0 || z + g.mz >= p.cv.sz || y + g.my >= p.cv.sy ||
+        x + g.mx >= p.cv.sx || sg > 0) {
+      st->ctr.skip_invalid_pos++;
+      trace_event(p, st, EV_POP_INVALID, z, y, x);
+      continue;
+    }
+    trace_event(p, st, EV_POP_VALID, z, y, x);
+    return true;
   }
   return false;
 }
@@ -1046,14 +1216,16 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   c.s_bias = reinterpret_cast<float*>(smem_raw + L.bias);
   c.mb_w = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
   c.mb_act = c.mb_w + 2;
-  c.mb_mma = c.mb_w + 3;
-  c.s_tmem = reinterpret_cast<uint32_t*>(c.mb_w + 3 + kGroupTiles);
+  c.mb_mma = c.mb_w + 5;
+  c.s_tmem = reinterpret_cast<uint32_t*>(c.mb_w + 5 + kGroupTiles);
   c.s_misc = reinterpret_cast<int*>(c.s_tmem + 2);
-  c.s_aoff = c.s_misc + 64;
+  c.s_xchg = reinterpret_cast<float*>(smem_raw + L.bars + 1024);
+  c.s_dot = c.s_xchg + 2 * 2 * 4 * 2 * 16;
   c.prof = nullptr;
   if (p.ws.prof && (c.cta == 0 || c.cta == c.G - 1)) c.prof = p.ws.prof + (c.cta == 0 ? 0 : 16);
   const long long t_kernel = clock64();
-  c.par_w[0] = c.par_w[1] = c.par_act = 0;
+  c.par_w[0] = c.par_w[1] = 0;
+  c.par_act[0] = c.par_act[1] = c.par_act[2] = 0;
   for (int i = 0; i < kGroupTiles; ++i) c.par_mma[i] = 0;
   c.w_pending[0] = c.w_pending[1] = 0;
   c.tmem_base = 0;
@@ -1063,21 +1235,10 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   if (c.tid < 32) c.s_bias[p.g.nconv * 32 + c.tid] = p.w.w_lom[c.tid];
   if (c.tid == 0) c.s_bias[p.g.nconv * 32 + 32] = p.w.b_lom;
   if (tc) {
-    {
-      // A-descriptor start-address offsets (16-byte rows) per (tap, k-pair), see tc_layer
-      const int seg_rows = kGroupTiles * kTileM + 2 * p.g.halo;
-      for (int k = c.tid; k < 27 + 54; k += kThreads) {
-        const int nch = k < 27 ? 2 : 4;
-        const int kk = k < 27 ? k : k - 27;
-        const int tap = kk / (nch / 2), j = kk % (nch / 2);
-        const int tz = tap / 9, ty = (tap / 3) % 3, tx = tap % 3;
-        c.s_aoff[k] = (tz * nch + 2 * j) * seg_rows + p.g.halo + (ty - 1) * p.g.xp + (tx - 1);
-      }
-    }
     if (c.tid == 0) {
       sm100::mbar_init(&c.mb_w[0], 1);
       sm100::mbar_init(&c.mb_w[1], 1);
-      sm100::mbar_init(c.mb_act, 1);
+      for (int i = 0; i < 3; ++i) sm100::mbar_init(&c.mb_act[i], 1);
       for (int i = 0; i < kGroupTiles; ++i) sm100::mbar_init(&c.mb_mma[i], 1);
       sm100::fence_mbar_init();
     }

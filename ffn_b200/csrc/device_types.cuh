@@ -183,7 +183,7 @@ __host__ __device__ inline SmemLayout smem_layout(const Geom& g) {
   const int act_bytes = 3 * 4 * seg_rows * 16;
   s.bias = s.act + act_bytes;
   s.bars = s.bias + (kMaxConv + 1) * 32 * 4 + 16;
-  s.total = s.bars + 1024 + 3072;   // + epilogue warp-boundary exchange + conv_lom partial dots
+  s.total = s.bars + 4096 + 512;    // barriers/misc | prof | epilogue exchange + conv_lom dots | leader's state copy
   return s;
 }
 

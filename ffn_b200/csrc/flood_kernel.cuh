@@ -42,11 +42,18 @@ struct Ctx {
   int* s_misc;                 // [0] step count>=th accumulator, [1..] leader scratch
   float* s_xchg;               // [2 tile parities][2 halves][4 warps][2][16] partial sums crossing warp boundaries
   float* s_dot;                // [2][128] conv_lom partial dot products of the upper channel half
-  long long* prof;             // profiling slots of this CTA (null unless CTA 0 / G-1)
-  uint32_t par_w[2], par_act[3], par_mma[kGroupTiles];
-  int w_pending[2];
+  CanvasState* s_state;        // CTA 0: shared-memory working copy of the canvas state during leader_decide
+  long long* prof;             // profiling slots of this CTA in SHARED memory (null unless CTA 0 / G-1);
+                               // flushed to global once, at kernel end, so timing does not stall the timed code
+  // mbarrier phase parities and pending-prefetch flags as ONE bit field: dynamically indexed arrays
+  // would push this whole struct into local memory (behind the L1 every grid barrier invalidates).
+  uint32_t bits;   // bit b: weights[b] parity; 2+z: activation plane z; 5+i: tile i UMMA; 8+b: weights[b] in flight
   uint32_t tmem_base;
 };
+
+__device__ __forceinline__ uint32_t bit_get(const Ctx& c, int k) { return (c.bits >> k) & 1u; }
+__device__ __forceinline__ void bit_flip(Ctx& c, int k) { c.bits ^= 1u << k; }
+__device__ __forceinline__ void bit_set(Ctx& c, int k, bool v) { c.bits = (c.bits & ~(1u << k)) | ((v ? 1u : 0u) << k); }
 
 __device__ __forceinline__ bool aborted(const Ctx& c) {
   return sm100::ld_volatile_s32(c.p->ws.abort_flag) != 0;
@@ -112,7 +119,7 @@ __device__ __forceinline__ bool row_to_zyx(const Geom& g, int r, int& z, int& y,
 // ------------------------------------------------------------------------------------------
 // Stage: canvas (or host-provided patch) -> layer-0 operands + raw seed copy
 // ------------------------------------------------------------------------------------------
-__device__ void stage_fov(Ctx& c, int pz, int py, int px, int batch_idx) {
+__device__ __forceinline__ void stage_fov(Ctx& c, int pz, int py, int px, int batch_idx) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
   const bool predict = p.job.mode == MODE_PREDICT;
@@ -317,7 +324,7 @@ __device__ __forceinline__ void quad_sync(int quad) {   // the four epilogue war
 //   D[u][dx*32 + co] = sum_{dz,dy,ci} act[u + dz*pp + dy*xp][ci] * W[dz,dy,dx][ci][co]
 // and the convolution output is out[v] = D[v-1][dx=-1] + D[v][dx=0] + D[v+1][dx=+1]: one lane up /
 // down, done with warp shuffles (+ a 2 KB shared-memory exchange at the three warp boundaries).
-__device__ void tc_layer(Ctx& c, int layer) {
+__device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
   const long long t_layer = clock64();
@@ -329,10 +336,7 @@ __device__ void tc_layer(Ctx& c, int layer) {
   const bool issuer = c.warp == kIssueWarp && c.lane == 0;
   const bool need_res = (layer & 1) && layer > 1;
 
-  // Prefetch the next layer's weights (next step's layer 0 after the last layer) into the other
-  // buffer: its previous user (layer - 1) has completed all MMAs.
-  if (issuer) tc_issue_weight_load(c, (layer + 1 == g.nconv) ? 0 : layer + 1);
-  c.w_pending[(layer + 1) & 1] = 1;
+  bit_set(c, 8 + ((layer + 1) & 1), true);   // weight prefetch is issued once this layer's activations landed
 
   int hit = 0;
   for (int g0 = c.t_begin; g0 < c.t_end; g0 += kGroupTiles) {
@@ -346,9 +350,8 @@ __device__ void tc_layer(Ctx& c, int layer) {
         const int load_rows = ng * kTileOut + 2 * g.halo;
         long long t0 = clock64();
         sm100::fence_proxy_async();
-        const int order[3] = {1, 0, 2};
         for (int oi = 0; oi < 3; ++oi) {
-          const int dzi = order[oi];
+          const int dzi = oi == 0 ? 1 : (oi == 1 ? 0 : 2);   // centre plane first
           sm100::mbar_expect_tx(&c.mb_act[dzi], (uint32_t)(nch * load_rows * 16));
           for (int ch = 0; ch < nch; ++ch)
             sm100::bulk_g2s(act_smem + (size_t)(dzi * nch + ch) * seg_rows * 16,
@@ -357,7 +360,7 @@ __device__ void tc_layer(Ctx& c, int layer) {
         }
         if (first) {
           const long long tw = clock64();
-          mbar_wait(c, &c.mb_w[buf], c.par_w[buf]);
+          mbar_wait(c, &c.mb_w[buf], bit_get(c, buf));
           prof_add(c, 2, clock64() - tw);
         }
         // ---- UMMA issue: only the 14-bit start-address field changes between instructions
@@ -367,11 +370,15 @@ __device__ void tc_layer(Ctx& c, int layer) {
         for (int i = 0; i < ng; ++i) {
           const uint32_t d = c.tmem_base + (uint32_t)(i * kStackN);
           for (int oi = 0; oi < 3; ++oi) {
-            const int tz = order[oi];
+            const int tz = oi == 0 ? 1 : (oi == 1 ? 0 : 2);
             if (i == 0) {
-              mbar_wait(c, &c.mb_act[tz], c.par_act[tz]);
+              mbar_wait(c, &c.mb_act[tz], bit_get(c, 2 + tz));
               sm100::tc_fence_after();
               if (oi == 0) prof_add(c, 1, clock64() - t0);
+              // Prefetch the next layer's weights (next step's layer 0 after the last layer) into the
+              // other buffer — its previous user (layer - 1) has completed all MMAs — only once this
+              // layer's activations have landed, so the 55 KB do not compete with the critical loads.
+              if (oi == 2 && first) tc_issue_weight_load(c, (layer + 1 == g.nconv) ? 0 : layer + 1);
             }
             const long long ti = clock64();
             if (layer == 0) {
@@ -405,7 +412,7 @@ __device__ void tc_layer(Ctx& c, int layer) {
             pre[q] = __ldcg(p.ws.res + (size_t)(half * 4 + q) * g.rows_alloc + g.guard + r);
         }
         long long t0 = clock64();
-        mbar_wait(c, &c.mb_mma[i], c.par_mma[i]);
+        mbar_wait(c, &c.mb_mma[i], bit_get(c, 5 + i));
         if (c.tid == 0) prof_add(c, 4, clock64() - t0);
         t0 = clock64();
         sm100::tc_fence_after();
@@ -454,14 +461,16 @@ __device__ void tc_layer(Ctx& c, int layer) {
         if (c.tid == 0) prof_add(c, 5, clock64() - t0);
       }
     }
-    for (int i = 0; i < 3; ++i) c.par_act[i] ^= 1;
+    c.bits ^= 7u << 2;
     if (first) {
-      c.par_w[buf] ^= 1;
-      c.w_pending[buf] = 0;
+      bit_flip(c, buf);
+      bit_set(c, 8 + buf, false);
     }
-    for (int i = 0; i < ng; ++i) c.par_mma[i] ^= 1;
+    for (int i = 0; i < ng; ++i) bit_flip(c, 5 + i);
     sm100::tc_fence_before();
+    const long long t_sync = clock64();
     __syncthreads();   // act smem / TMEM are reused by the next group or layer
+    if (c.tid == 0) prof_add(c, 15, clock64() - t_sync);
   }
   if (layer == g.nconv - 1) {
     hit = __reduce_add_sync(0xffffffffu, hit);
@@ -474,7 +483,7 @@ __device__ void tc_layer(Ctx& c, int layer) {
 // fp32 layer ("precise" parity mode): one thread per FoV row, 32 accumulators, weights
 // broadcast from shared memory, activations through L1.
 // ------------------------------------------------------------------------------------------
-__device__ void f32_layer(Ctx& c, int layer) {
+__device__ __forceinline__ void f32_layer(Ctx& c, int layer) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
   const int ngrp = layer == 0 ? 1 : 8;           // input groups of 4 channels
@@ -527,7 +536,7 @@ __device__ void f32_layer(Ctx& c, int layer) {
 
 // Runs the conv stack on the staged FoV; on return (after a grid barrier) ws.logits and ws.count
 // are complete and visible to every CTA.
-__device__ void run_network(Ctx& c) {
+__device__ __forceinline__ void run_network(Ctx& c) {
   const KParams& p = *c.p;
   grid_barrier(c);   // staged operands visible
   for (int layer = 0; layer < p.g.nconv; ++layer) {
@@ -562,7 +571,7 @@ __device__ __forceinline__ float merged_row(const KParams& p, int r, bool disco)
 }
 
 // Paste this CTA's rows into the seed canvas (inference.py:439) / the prediction output.
-__device__ void tail_paste(Ctx& c, int pz, int py, int px, int batch_idx) {
+__device__ __forceinline__ void tail_paste(Ctx& c, int pz, int py, int px, int batch_idx) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
   const bool predict = p.job.mode == MODE_PREDICT;
@@ -644,25 +653,26 @@ __device__ __forceinline__ void push_move(const KParams& p, CanvasState* st, flo
 }
 
 // FaceMaxMovementPolicy.update (movement.py:210-222) for the step just executed at st->cur.
-// All threads of CTA 0 call this; warps 0-5 each reduce one face.
-__device__ void policy_update(Ctx& c, CanvasState* st, bool disco) {
+// All threads of CTA 0 call this; warps 0-5 each reduce one face.  (No dynamically indexed local
+// arrays here: local memory lives behind the L1 that every grid barrier invalidates.)
+__device__ __forceinline__ void policy_update(Ctx& c, CanvasState* st, bool disco) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
   float* s_score = reinterpret_cast<float*>(c.s_misc + 8);
-  int* s_rel = c.s_misc + 16;   // [6][3]
-  int* s_ok = c.s_misc + 40;    // [6]
+  int* s_rel = c.s_misc + 16;     // [6][3]
+  int* s_ok = c.s_misc + 40;      // [6]
+  int* s_order = c.s_misc + 48;   // [6]
   const int cz = g.fz / 2, cy = g.fy / 2, cx = g.fx / 2;
-  const int del[3] = {g.dz, g.dy, g.dx};
-  const int cen[3] = {cz, cy, cx};
   if (c.warp < 6) {
     const int axis = c.warp >> 1;
-    const int off = (c.warp & 1) ? del[axis] : -del[axis];
+    const int dax = axis == 0 ? g.dz : (axis == 1 ? g.dy : g.dx);
+    const int off = (c.warp & 1) ? dax : -dax;
+    // the two in-face axes in their original (C) order: (y,x) for z faces, (z,x) for y, (z,y) for x
+    const int d0 = axis == 0 ? g.dy : g.dz;
+    const int d1 = axis == 2 ? g.dy : g.dx;
+    const int n0 = 2 * d0 + 1, n1 = 2 * d1 + 1;
     int ok = 0;
-    if (del[axis] != 0) {
-      // the two in-face axes in their original (C) order
-      const int a0 = axis == 0 ? 1 : 0;
-      const int a1 = axis == 2 ? 1 : 2;
-      const int n0 = 2 * del[a0] + 1, n1 = 2 * del[a1] + 1;
+    if (dax != 0) {
       float best = -CUDART_INF_F;
       int best_i = 0x7fffffff;
       // eight independent L2 loads in flight per lane, then the (ordered) comparisons
@@ -675,11 +685,10 @@ __device__ void policy_update(Ctx& c, CanvasState* st, bool disco) {
           od[u] = 0.f;
           if (e < n0 * n1) {
             const int i0 = e / n1, i1 = e - i0 * n1;
-            int zyx[3];
-            zyx[axis] = cen[axis] + off;
-            zyx[a0] = cen[a0] - del[a0] + i0;
-            zyx[a1] = cen[a1] - del[a1] + i1;
-            const int row = zyx[0] * g.pp + zyx[1] * g.xp + zyx[2];
+            const int z = axis == 0 ? cz + off : cz - g.dz + i0;
+            const int y = axis == 0 ? cy - g.dy + i0 : (axis == 1 ? cy + off : cy - g.dy + i1);
+            const int x = axis == 2 ? cx + off : cx - g.dx + i1;
+            const int row = z * g.pp + y * g.xp + x;
             lg[u] = __ldcg(p.ws.logits + row);
             if (disco) od[u] = __ldcg(p.ws.seed_raw + row);
           }
@@ -711,14 +720,11 @@ __device__ void policy_update(Ctx& c, CanvasState* st, bool disco) {
         // the smallest float32 >= threshold)
         ok = (best >= p.cv.policy_th_f32) ? 1 : 0;
         const int i0 = best_i / n1, i1 = best_i - i0 * n1;
-        int rel[3];
-        rel[axis] = off;
-        rel[a0] = i0 - n0 / 2;
-        rel[a1] = i1 - n1 / 2;
+        const int r0 = i0 - n0 / 2, r1 = i1 - n1 / 2;
         s_score[c.warp] = best;
-        s_rel[3 * c.warp + 0] = rel[0];
-        s_rel[3 * c.warp + 1] = rel[1];
-        s_rel[3 * c.warp + 2] = rel[2];
+        s_rel[3 * c.warp + 0] = axis == 0 ? off : r0;
+        s_rel[3 * c.warp + 1] = axis == 0 ? r0 : (axis == 1 ? off : r1);
+        s_rel[3 * c.warp + 2] = axis == 2 ? off : r1;
       }
     }
     if (c.lane == 0) s_ok[c.warp] = ok;
@@ -726,25 +732,25 @@ __device__ void policy_update(Ctx& c, CanvasState* st, bool disco) {
   __syncthreads();
   if (c.tid == 0) {
     p.cv.lattice[lattice_index(p, st, st->cur[0], st->cur[1], st->cur[2])] = st->epoch;
-    int order[6], n = 0;
+    int n = 0;
     for (int f = 0; f < 6; ++f) {
       if (!s_ok[f]) continue;
       // movement.py:95-99: identical (score, offset) tuples are yielded once — two faces share an
       // edge, and the same edge voxel can be the arg-max of both.
       bool dup = false;
       for (int i = 0; i < n; ++i) {
-        const int h = order[i];
+        const int h = s_order[i];
         dup |= s_rel[3 * f] == s_rel[3 * h] && s_rel[3 * f + 1] == s_rel[3 * h + 1] &&
                s_rel[3 * f + 2] == s_rel[3 * h + 2] && s_score[f] == s_score[h];
       }
-      if (!dup) order[n++] = f;
+      if (!dup) s_order[n++] = f;
     }
     // sorted(..., reverse=True) on (score, (dz, dy, dx)) tuples (movement.py:218)
     for (int i = 1; i < n; ++i) {
-      const int f = order[i];
+      const int f = s_order[i];
       int j = i - 1;
       while (j >= 0) {
-        const int h = order[j];
+        const int h = s_order[j];
         bool greater = s_score[f] > s_score[h];
         if (s_score[f] == s_score[h]) {
           greater = false;
@@ -756,13 +762,13 @@ __device__ void policy_update(Ctx& c, CanvasState* st, bool disco) {
           }
         }
         if (!greater) break;
-        order[j + 1] = h;
+        s_order[j + 1] = h;
         --j;
       }
-      order[j + 1] = f;
+      s_order[j + 1] = f;
     }
     for (int i = 0; i < n; ++i) {
-      const int f = order[i];
+      const int f = s_order[i];
       push_move(p, st, s_score[f], st->cur[0] + s_rel[3 * f], st->cur[1] + s_rel[3 * f + 1],
                 st->cur[2] + s_rel[3 * f + 2]);
     }
@@ -771,7 +777,7 @@ __device__ void policy_update(Ctx& c, CanvasState* st, bool disco) {
 }
 
 // Canvas.is_valid_pos (inference.py:312-346); thread 0 only.
-__device__ bool is_valid_pos(const KParams& p, CanvasState* st, bool disco, int z, int y, int x,
+__device__ __forceinline__ bool is_valid_pos(const KParams& p, CanvasState* st, bool disco, int z, int y, int x,
                              bool ignore_move_threshold) {
   const Geom& g = p.g;
   const bool inside = z >= 0 && y >= 0 && x >= 0 && z < p.cv.sz && y < p.cv.sy && x < p.cv.sx;
@@ -801,7 +807,7 @@ __device__ bool is_valid_pos(const KParams& p, CanvasState* st, bool disco, int 
 // FaceMaxMovementPolicy.__next__ (movement.py:186-198) + Canvas.is_valid_pos (inference.py:312-346)
 // for queue entries; thread 0 only.  The lattice stamp, the seed value and the label of a
 // candidate are independent, so their loads are issued together and only the decisions are ordered.
-__device__ bool pop_next(const KParams& p, CanvasState* st, bool disco, int& z, int& y, int& x) {
+__device__ __forceinline__ bool pop_next(const KParams& p, CanvasState* st, bool disco, int& z, int& y, int& x) {
   const Geom& g = p.g;
   while (st->q_head < st->q_tail) {
     const int h = st->q_head++;
@@ -867,20 +873,28 @@ __device__ __forceinline__ uint8_t quantize_prob(float logit) {
 
 // Decides the next collective action; executed by all threads of CTA 0, serial parts on thread 0.
 // Writes *job.action (read by every CTA after the following grid barrier).
-__device__ void leader_decide(Ctx& c) {
+__device__ __forceinline__ void leader_decide(Ctx& c) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
-  CanvasState* st = p.st;
+  // Work on a shared-memory copy of the state: the serial code below is full of read-after-write
+  // on these fields, and in global memory every one of those is an L2 round trip.
+  CanvasState* st = c.s_state;
   int* s_phase = c.s_misc + 4;
   int* s_disco = c.s_misc + 5;
   if (c.tid == 0) {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.st);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(st);
+#pragma unroll 8
+    for (int i = 0; i < (int)(sizeof(CanvasState) / 8); ++i) dst[i] = __ldcg(src + i);
     *s_phase = st->phase;
     *s_disco = (st->phase == PH_AFTER_STEP) ? (disco_active(p) ? 1 : 0) : 0;
   }
   __syncthreads();
   const bool disco = *s_disco != 0;
+  const long long t_pol = clock64();
   if (*s_phase == PH_AFTER_STEP && p.job.mode != MODE_UPDATE_AT) policy_update(c, st, disco);   // movement.py:210-222
   if (c.tid != 0) return;
+  prof_add(c, 12, clock64() - t_pol);
 
   int action = ACT_EXIT;
   int phase = st->phase;
@@ -951,6 +965,7 @@ __device__ void leader_decide(Ctx& c) {
       }
       bool run = false;
       int z = 0, y = 0, x = 0;
+      const long long t_pop = clock64();
       for (;;) {
         if (!pop_next(p, st, disco, z, y, x)) break;
         // inference.py:503-505
@@ -967,6 +982,7 @@ __device__ void leader_decide(Ctx& c) {
         run = true;
         break;
       }
+      prof_add(c, 13, clock64() - t_pop);
       if (run) {
         st->cur[0] = z;
         st->cur[1] = y;
@@ -1116,14 +1132,22 @@ __device__ void leader_decide(Ctx& c) {
     break;
   }
   st->phase = phase;
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.st);
+#pragma unroll 8
+    for (int i = 0; i < (int)(sizeof(CanvasState) / 8); ++i) dst[i] = src[i];
+  }
   *p.job.action = action;
+  const long long t_f = clock64();
   __threadfence();
+  prof_add(c, 14, clock64() - t_f);
 }
 
 // ------------------------------------------------------------------------------------------
 // Collective helpers over a canvas box
 // ------------------------------------------------------------------------------------------
-__device__ void clear_dirty(Ctx& c) {   // NumpyArray.clear restricted to the touched box
+__device__ __forceinline__ void clear_dirty(Ctx& c) {   // NumpyArray.clear restricted to the touched box
   const KParams& p = *c.p;
   const CanvasState* st = p.st;
   const int lo[3] = {max(st->dirty_lo[0], 0), max(st->dirty_lo[1], 0), max(st->dirty_lo[2], 0)};
@@ -1139,7 +1163,7 @@ __device__ void clear_dirty(Ctx& c) {   // NumpyArray.clear restricted to the to
   }
 }
 
-__device__ void commit_count(Ctx& c) {   // inference.py:624-636
+__device__ __forceinline__ void commit_count(Ctx& c) {   // inference.py:624-636
   const KParams& p = *c.p;
   CanvasState* st = p.st;
   const int* lo = st->box_lo;
@@ -1175,7 +1199,7 @@ __device__ void commit_count(Ctx& c) {   // inference.py:624-636
   }
 }
 
-__device__ void commit_write(Ctx& c) {   // inference.py:653-658
+__device__ __forceinline__ void commit_write(Ctx& c) {   // inference.py:653-658
   const KParams& p = *c.p;
   const CanvasState* st = p.st;
   const int* lo = st->box_lo;
@@ -1221,13 +1245,15 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   c.s_misc = reinterpret_cast<int*>(c.s_tmem + 2);
   c.s_xchg = reinterpret_cast<float*>(smem_raw + L.bars + 1024);
   c.s_dot = c.s_xchg + 2 * 2 * 4 * 2 * 16;
+  c.s_state = reinterpret_cast<CanvasState*>(smem_raw + L.bars + 4096);
+  static_assert(sizeof(CanvasState) <= 512 && sizeof(CanvasState) % 8 == 0, "state copy area");
   c.prof = nullptr;
-  if (p.ws.prof && (c.cta == 0 || c.cta == c.G - 1)) c.prof = p.ws.prof + (c.cta == 0 ? 0 : 16);
+  if (p.ws.prof && (c.cta == 0 || c.cta == c.G - 1)) {
+    c.prof = reinterpret_cast<long long*>(smem_raw + L.bars + 512);
+    if (c.tid < 16) c.prof[c.tid] = 0;
+  }
   const long long t_kernel = clock64();
-  c.par_w[0] = c.par_w[1] = 0;
-  c.par_act[0] = c.par_act[1] = c.par_act[2] = 0;
-  for (int i = 0; i < kGroupTiles; ++i) c.par_mma[i] = 0;
-  c.w_pending[0] = c.w_pending[1] = 0;
+  c.bits = 0;
   c.tmem_base = 0;
   const bool tc = p.compute_mode == FFN_COMPUTE_FP16_TC;
 
@@ -1249,7 +1275,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
     sm100::tc_fence_after();
     c.tmem_base = *c.s_tmem;
     if (c.warp == kIssueWarp && c.lane == 0) tc_issue_weight_load(c, 0);
-    c.w_pending[0] = 1;
+    bit_set(c, 8, true);
   }
   __syncthreads();
 
@@ -1298,10 +1324,12 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   }
 
   if (c.tid == 0) prof_add(c, 10, clock64() - t_kernel);
+  __syncthreads();
+  if (c.prof && c.tid < 16) p.ws.prof[(c.cta == 0 ? 0 : 16) + c.tid] += c.prof[c.tid];
   // Teardown: no bulk copy may be in flight into this CTA's shared memory at exit.
   if (tc) {
     for (int b = 0; b < 2; ++b)
-      if (c.w_pending[b]) mbar_wait(c, &c.mb_w[b], c.par_w[b]);
+      if (bit_get(c, 8 + b)) mbar_wait(c, &c.mb_w[b], bit_get(c, b));
     sm100::tc_fence_before();
     __syncthreads();
     if (c.warp == 0) sm100::tmem_dealloc<kTmemCols>(c.tmem_base);

@@ -94,14 +94,15 @@ class Engine:
     return dict(zip(keys, [int(v) for v in buf]))
 
   PROFILE_SLOTS = ('barrier_wait', 'act_tma_wait', 'weight_wait', 'umma_issue', 'epi_wait_mma', 'epi_body',
-                   'stage', 'paste', 'leader', 'steps', 'kernel', 'conv_layers')
+                   'stage', 'paste', 'leader', 'steps', 'kernel', 'conv_layers', 'leader_policy', 'leader_pops',
+                   'leader_fence', 'layer_end_sync')
 
   def profile(self, reset: bool = True) -> dict:
     """Device cycle counters of CTA 0 and of the last CTA (see ffn_engine_profile)."""
     buf = (C.c_int64 * 32)()
     _lib.check(self._lib.ffn_engine_profile(self._h, buf, 1 if reset else 0))
-    return {'cta0': dict(zip(self.PROFILE_SLOTS, [int(v) for v in buf[:12]])),
-            'cta_last': dict(zip(self.PROFILE_SLOTS, [int(v) for v in buf[16:28]]))}
+    return {'cta0': dict(zip(self.PROFILE_SLOTS, [int(v) for v in buf[:16]])),
+            'cta_last': dict(zip(self.PROFILE_SLOTS, [int(v) for v in buf[16:32]]))}
 
   def predict(self, seed: np.ndarray, image: np.ndarray) -> np.ndarray:
     """(Z,Y,X) or (B,Z,Y,X) float32 patches -> logits of the same shape (executor.py:134-139)."""

@@ -86,8 +86,9 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
   if (c.tid == 0) {
     c.bar_target += c.G;
     const long long t0 = clock64();
-    __threadfence();
-    atomicAdd(c.p->ws.bar, 1u);
+    // release: everything this CTA wrote (ordered before by bar.sync) becomes visible gpu-wide
+    // before the arrival is counted
+    sm100::red_release_add(c.p->ws.bar, 1u);
     unsigned spins = 0;
     while (sm100::ld_acquire_u32(c.p->ws.bar) < c.bar_target) {
       if ((++spins & 0xFF) == 0) {
@@ -98,7 +99,8 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
         }
       }
     }
-    __threadfence();
+    // the acquire load that observed the full count orders every later read of this CTA (after
+    // the bar.sync below) behind the other CTAs' writes
     sm100::fence_proxy_async();   // later TMA reads must see what other CTAs wrote
     prof_add(c, 0, clock64() - t0);
   }

@@ -58,6 +58,7 @@ struct FfnEngine {
   int predict_cap = 0;
   std::vector<void*> owned;
   double last_kernel_seconds = 0.0;
+  bool profiling = false;
   long long launches = 0;
 };
 
@@ -113,6 +114,7 @@ int launch(FfnEngine* e, const CanvasDev& cv, CanvasState* d_state, const Job& j
   p.g = e->g;
   p.w = e->w;
   p.ws = e->ws;
+  if (!e->profiling) p.ws.prof = nullptr;
   p.cv = cv;
   p.st = d_state ? d_state : e->d_dummy_state;
   p.job = job;
@@ -250,6 +252,9 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffn_flood_kernel, kThreads, L.total));
   if (per_sm < 1) return fail("persistent kernel does not fit on an SM");
   e->grid = std::min(e->sm_count, g.nt);
+  if ((g.nt + e->grid - 1) / e->grid > kGroupTiles)
+    return fail("field of view needs more than " + std::to_string(kGroupTiles) +
+                " tiles per SM: the TMEM-resident residual stream does not fit (too few SMs for this FoV)");
 
   // weights
   std::vector<__half> w16;
@@ -335,7 +340,11 @@ int ffn_engine_info(FfnEngine* e, int64_t info[8]) {
 }
 
 int ffn_engine_profile(FfnEngine* e, int64_t out[32], int reset) {
-  if (!e || !out) return fail("null argument");
+  if (!e) return fail("null argument");
+  if (!out) {   // (out == NULL): switch the device-side counters on (reset != 0) or off (reset == 0)
+    e->profiling = reset != 0;
+    return 0;
+  }
   if (set_device(e)) return 1;
   long long h[32];
   CUDA_OK(cudaMemcpy(h, e->ws.prof, sizeof(h), cudaMemcpyDeviceToHost));

@@ -59,19 +59,23 @@ __device__ __forceinline__ bool aborted(const Ctx& c) {
   return sm100::ld_volatile_s32(c.p->ws.abort_flag) != 0;
 }
 
+// Profiling is opt-in (ffn_engine_profile_enable): reading the clock is not free, and CTA G-1 —
+// one of the two profiled CTAs — is on the critical path of every layer.
+__device__ __forceinline__ long long prof_now(const Ctx& c) { return c.prof ? clock64() : 0ll; }
 __device__ __forceinline__ void prof_add(const Ctx& c, int slot, long long dt) {
   if (c.prof) c.prof[slot] += dt;
 }
 
 // Bounded spin on an mbarrier phase; a timeout raises the abort flag instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(const Ctx& c, uint64_t* bar, uint32_t parity) {
-  if (sm100::mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
   unsigned spins = 0;
+  long long t0 = 0;
   while (!sm100::mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3FF) == 0) {
       if (aborted(c)) return;
-      if (clock64() - t0 > (1ll << 32)) {   // ~2 s
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > (1ll << 32)) {   // ~2 s
         atomicExch(c.p->ws.abort_flag, 2);
         return;
       }
@@ -85,7 +89,8 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
   __syncthreads();
   if (c.tid == 0) {
     c.bar_target += c.G;
-    const long long t0 = clock64();
+    const long long t0 = prof_now(c);
+    long long tw = 0;
     // release: everything this CTA wrote (ordered before by bar.sync) becomes visible gpu-wide
     // before the arrival is counted
     sm100::red_release_add(c.p->ws.bar, 1u);
@@ -93,7 +98,9 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
     while (sm100::ld_acquire_u32(c.p->ws.bar) < c.bar_target) {
       if ((++spins & 0xFF) == 0) {
         if (aborted(c)) break;
-        if (clock64() - t0 > (1ll << 32)) {
+        const long long now = clock64();
+        if (tw == 0) tw = now;
+        if (now - tw > (1ll << 32)) {
           atomicExch(c.p->ws.abort_flag, 1);
           break;
         }
@@ -102,7 +109,7 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
     // the acquire load that observed the full count orders every later read of this CTA (after
     // the bar.sync below) behind the other CTAs' writes
     sm100::fence_proxy_async();   // later TMA reads must see what other CTAs wrote
-    prof_add(c, 0, clock64() - t0);
+    prof_add(c, 0, prof_now(c) - t0);
   }
   __syncthreads();
   sm100::tc_fence_after();
@@ -236,7 +243,7 @@ __device__ __forceinline__ void epilogue_row(const Ctx& c, int layer, int r, flo
 // epilogue quads split every tile by channel so a tile's latency is halved.  Same arithmetic as
 // epilogue_row; for the last layer returns this half's share of <relu(net), w_lom>.
 __device__ __forceinline__ float epilogue_half(const Ctx& c, int layer, int r, float (&v)[16], int half,
-                                               const float4* pre_res) {
+                                               float (&res)[16]) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
   const float* b = c.s_bias + layer * 32 + half * 16;
@@ -246,21 +253,13 @@ __device__ __forceinline__ float epilogue_half(const Ctx& c, int layer, int r, f
   const bool last = layer == g.nconv - 1;
   const size_t ra = (size_t)g.guard + r;
   if (is_b) {
+    // fp32 residual stream: `res` comes from / goes back to this thread's TMEM lane (tc_layer)
     if (layer > 1) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        v[4 * q + 0] += pre_res[q].x;
-        v[4 * q + 1] += pre_res[q].y;
-        v[4 * q + 2] += pre_res[q].z;
-        v[4 * q + 3] += pre_res[q].w;
-      }
+      for (int k = 0; k < 16; ++k) v[k] += res[k];
     }
-    if (!last) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        p.ws.res[(size_t)(half * 4 + q) * g.rows_alloc + ra] =
-            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    }
+    for (int k = 0; k < 16; ++k) res[k] = v[k];
   }
 #pragma unroll
   for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
@@ -329,7 +328,7 @@ __device__ __forceinline__ void quad_sync(int quad) {   // the four epilogue war
 __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
-  const long long t_layer = clock64();
+  const long long t_layer = prof_now(c);
   const int nch = layer == 0 ? 2 : 4;
   const __half* in = layer == 0 ? p.ws.act0_h : p.ws.act_h[(layer - 1) & 1];
   const int buf = layer & 1;
@@ -350,7 +349,7 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
         // ---- TMA producer: three z-plane segments x k-chunks of the input activations, centre plane
         // first; each segment has its own mbarrier so the UMMAs of a plane start as soon as it lands.
         const int load_rows = ng * kTileOut + 2 * g.halo;
-        long long t0 = clock64();
+        long long t0 = prof_now(c);
         sm100::fence_proxy_async();
         for (int oi = 0; oi < 3; ++oi) {
           const int dzi = oi == 0 ? 1 : (oi == 1 ? 0 : 2);   // centre plane first
@@ -361,9 +360,9 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
                             (uint32_t)load_rows * 16, &c.mb_act[dzi]);
         }
         if (first) {
-          const long long tw = clock64();
+          const long long tw = prof_now(c);
           mbar_wait(c, &c.mb_w[buf], bit_get(c, buf));
-          prof_add(c, 2, clock64() - tw);
+          prof_add(c, 2, prof_now(c) - tw);
         }
         // ---- UMMA issue: only the 14-bit start-address field changes between instructions
         const uint32_t a_lo = ((sm100::smem_u32(act_smem) >> 4) & 0x3FFFu) | ((uint32_t)seg_rows << 16);
@@ -376,24 +375,24 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
             if (i == 0) {
               mbar_wait(c, &c.mb_act[tz], bit_get(c, 2 + tz));
               sm100::tc_fence_after();
-              if (oi == 0) prof_add(c, 1, clock64() - t0);
+              if (oi == 0) prof_add(c, 1, prof_now(c) - t0);
               // Prefetch the next layer's weights (next step's layer 0 after the last layer) into the
               // other buffer — its previous user (layer - 1) has completed all MMAs — only once this
               // layer's activations have landed, so the 55 KB do not compete with the critical loads.
               if (oi == 2 && first) tc_issue_weight_load(c, (layer + 1 == g.nconv) ? 0 : layer + 1);
             }
-            const long long ti = clock64();
+            const long long ti = prof_now(c);
             if (layer == 0) {
               tc_issue_plane<2>(d, a_lo + (uint32_t)(i * kTileOut), b_lo, seg_rows, g.xp, tz, oi ? 1u : 0u);
             } else {
               tc_issue_plane<4>(d, a_lo + (uint32_t)(i * kTileOut), b_lo, seg_rows, g.xp, tz, oi ? 1u : 0u);
             }
-            issue_cycles += clock64() - ti;
+            issue_cycles += prof_now(c) - ti;
           }
           sm100::umma_commit(&c.mb_mma[i]);
         }
-        t0 = clock64() - issue_cycles;
-        prof_add(c, 3, clock64() - t0);
+        t0 = prof_now(c) - issue_cycles;
+        prof_add(c, 3, prof_now(c) - t0);
       }
       __syncwarp();
     } else {
@@ -407,22 +406,20 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
         const int r = r0 + i * kTileOut - 1 + m;              // FoV row it holds partial sums for
         int z, y, x;
         const bool valid = m >= 1 && m <= kTileOut && r >= 0 && row_to_zyx(g, r, z, y, x);
-        float4 pre[4];
-        if (need_res && valid) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            pre[q] = __ldcg(p.ws.res + (size_t)(half * 4 + q) * g.rows_alloc + g.guard + r);
-        }
-        long long t0 = clock64();
+        long long t0 = prof_now(c);
         mbar_wait(c, &c.mb_mma[i], bit_get(c, 5 + i));
-        if (c.tid == 0) prof_add(c, 4, clock64() - t0);
-        t0 = clock64();
+        if (c.tid == 0) prof_add(c, 4, prof_now(c) - t0);
+        t0 = prof_now(c);
         sm100::tc_fence_after();
         const uint32_t tbase = c.tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(i * kStackN + half * 16);
-        uint32_t a[16], b[16], d2[16];
+        // residual stream of this row / channel half: TMEM columns behind the accumulators
+        const uint32_t tres = c.tmem_base + ((uint32_t)(wq * 32) << 16) +
+                              (uint32_t)(kGroupTiles * kStackN + i * kFeat + half * 16);
+        uint32_t a[16], b[16], d2[16], rr[16];
         sm100::tmem_ld16(tbase, a);          // dx = -1 block: consumed by the lane above (m + 1)
         sm100::tmem_ld16(tbase + 32, b);     // dx =  0 block
         sm100::tmem_ld16(tbase + 64, d2);    // dx = +1 block: consumed by the lane below (m - 1)
+        if (need_res) sm100::tmem_ld16(tres, rr);
         sm100::tmem_ld_wait();
         if (c.lane == 31) {
 #pragma unroll
@@ -444,7 +441,16 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
           v[k] = up + __uint_as_float(b[k]) + dn;
         }
         float part = 0.f;
-        if (valid) part = epilogue_half(c, layer, r, v, half, pre);
+        float res[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) res[k] = need_res ? __uint_as_float(rr[k]) : 0.f;
+        if (valid) part = epilogue_half(c, layer, r, v, half, res);
+        if ((layer & 1) && !last) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) rr[k] = __float_as_uint(res[k]);
+          sm100::tmem_st16(tres, rr);
+          sm100::tmem_st_wait();
+        }
         if (last) {
           // conv_lom: combine the two halves' dot products, then logits = seed + update
           float* dot = c.s_dot + (i & 1) * kTileM;
@@ -460,7 +466,7 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
             hit += (logit >= p.cv.opt.move_threshold) ? 1 : 0;
           }
         }
-        if (c.tid == 0) prof_add(c, 5, clock64() - t0);
+        if (c.tid == 0) prof_add(c, 5, prof_now(c) - t0);
       }
     }
     c.bits ^= 7u << 2;
@@ -470,15 +476,15 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
     }
     for (int i = 0; i < ng; ++i) bit_flip(c, 5 + i);
     sm100::tc_fence_before();
-    const long long t_sync = clock64();
+    const long long t_sync = prof_now(c);
     __syncthreads();   // act smem / TMEM are reused by the next group or layer
-    if (c.tid == 0) prof_add(c, 15, clock64() - t_sync);
+    if (c.tid == 0) prof_add(c, 15, prof_now(c) - t_sync);
   }
   if (layer == g.nconv - 1) {
     hit = __reduce_add_sync(0xffffffffu, hit);
     if (c.lane == 0 && hit) atomicAdd(&c.s_misc[0], hit);
   }
-  if (c.tid == 0) prof_add(c, 11, clock64() - t_layer);
+  if (c.tid == 0) prof_add(c, 11, prof_now(c) - t_layer);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -893,10 +899,10 @@ __device__ __forceinline__ void leader_decide(Ctx& c) {
   }
   __syncthreads();
   const bool disco = *s_disco != 0;
-  const long long t_pol = clock64();
+  const long long t_pol = prof_now(c);
   if (*s_phase == PH_AFTER_STEP && p.job.mode != MODE_UPDATE_AT) policy_update(c, st, disco);   // movement.py:210-222
   if (c.tid != 0) return;
-  prof_add(c, 12, clock64() - t_pol);
+  prof_add(c, 12, prof_now(c) - t_pol);
 
   int action = ACT_EXIT;
   int phase = st->phase;
@@ -967,7 +973,7 @@ __device__ __forceinline__ void leader_decide(Ctx& c) {
       }
       bool run = false;
       int z = 0, y = 0, x = 0;
-      const long long t_pop = clock64();
+      const long long t_pop = prof_now(c);
       for (;;) {
         if (!pop_next(p, st, disco, z, y, x)) break;
         // inference.py:503-505
@@ -984,7 +990,7 @@ __device__ __forceinline__ void leader_decide(Ctx& c) {
         run = true;
         break;
       }
-      prof_add(c, 13, clock64() - t_pop);
+      prof_add(c, 13, prof_now(c) - t_pop);
       if (run) {
         st->cur[0] = z;
         st->cur[1] = y;
@@ -1141,9 +1147,9 @@ __device__ __forceinline__ void leader_decide(Ctx& c) {
     for (int i = 0; i < (int)(sizeof(CanvasState) / 8); ++i) dst[i] = src[i];
   }
   *p.job.action = action;
-  const long long t_f = clock64();
+  const long long t_f = prof_now(c);
   __threadfence();
-  prof_add(c, 14, clock64() - t_f);
+  prof_add(c, 14, prof_now(c) - t_f);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1254,7 +1260,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
     c.prof = reinterpret_cast<long long*>(smem_raw + L.bars + 512);
     if (c.tid < 16) c.prof[c.tid] = 0;
   }
-  const long long t_kernel = clock64();
+  const long long t_kernel = prof_now(c);
   c.bits = 0;
   c.tmem_base = 0;
   const bool tc = p.compute_mode == FFN_COMPUTE_FP16_TC;
@@ -1292,9 +1298,9 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   } else {
     for (;;) {
       if (c.cta == 0) {
-        const long long t0 = clock64();
+        const long long t0 = prof_now(c);
         leader_decide(c);
-        if (c.tid == 0) prof_add(c, 8, clock64() - t0);
+        if (c.tid == 0) prof_add(c, 8, prof_now(c) - t0);
       }
       grid_barrier(c);
       if (aborted(c)) break;
@@ -1304,14 +1310,14 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
         const int pz = sm100::ld_volatile_s32(&p.st->cur[0]);
         const int py = sm100::ld_volatile_s32(&p.st->cur[1]);
         const int px = sm100::ld_volatile_s32(&p.st->cur[2]);
-        long long t0 = clock64();
+        long long t0 = prof_now(c);
         stage_fov(c, pz, py, px, 0);
-        if (c.tid == 0) prof_add(c, 6, clock64() - t0);
+        if (c.tid == 0) prof_add(c, 6, prof_now(c) - t0);
         run_network(c);
-        t0 = clock64();
+        t0 = prof_now(c);
         tail_paste(c, pz, py, px, 0);
         if (c.tid == 0) {
-          prof_add(c, 7, clock64() - t0);
+          prof_add(c, 7, prof_now(c) - t0);
           prof_add(c, 9, 1);
         }
       } else {
@@ -1325,7 +1331,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
     }
   }
 
-  if (c.tid == 0) prof_add(c, 10, clock64() - t_kernel);
+  if (c.tid == 0) prof_add(c, 10, prof_now(c) - t_kernel);
   __syncthreads();
   if (c.prof && c.tid < 16) p.ws.prof[(c.cta == 0 ? 0 : 16) + c.tid] += c.prof[c.tid];
   // Teardown: no bulk copy may be in flight into this CTA's shared memory at exit.

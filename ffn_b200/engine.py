@@ -97,6 +97,9 @@ class Engine:
                    'stage', 'paste', 'leader', 'steps', 'kernel', 'conv_layers', 'leader_policy', 'leader_pops',
                    'leader_fence', 'layer_end_sync')
 
+  def enable_profiling(self, on: bool = True):
+    _lib.check(self._lib.ffn_engine_profile(self._h, None, 1 if on else 0))
+
   def profile(self, reset: bool = True) -> dict:
     """Device cycle counters of CTA 0 and of the last CTA (see ffn_engine_profile)."""
     buf = (C.c_int64 * 32)()

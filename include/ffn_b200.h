@@ -121,7 +121,9 @@ int ffn_engine_info(FfnEngine* engine, int64_t info[8]);
 
 /* Device-side cycle counters of CTA 0 (out[0..15]) and the last CTA (out[16..31]): slot 0 grid-barrier
  * wait, 1 activation TMA wait, 2 weight wait, 3 UMMA issue, 4 epilogue wait-for-MMA, 5 epilogue body,
- * 6 stage, 7 paste, 8 leader, 9 steps, 10 kernel, 11 conv layers.  Debug / profiles only. */
+ * 6 stage, 7 paste, 8 leader, 9 steps, 10 kernel, 11 conv layers, 12-14 leader parts, 15 layer-end sync.
+ * Off by default (reading the clock perturbs the critical CTA): ffn_engine_profile(e, NULL, 1) switches
+ * the counters on, (e, NULL, 0) off; with out != NULL the counters are returned (and reset if reset). */
 int ffn_engine_profile(FfnEngine* engine, int64_t out[32], int reset);
 
 /* ---- L0 drop-in: ExecutorClient.predict (ffn/inference/executor.py:134-139, 266-340) -------

@@ -97,11 +97,13 @@ def run_mode(tag, mode):
     out['hybrid_min_margin'] = hyb.min_margin
     out['golden_trace_equal_hybrid'] = bool(np.array_equal(np.asarray(hyb.trace, np.int32).reshape(-1, 3), gat['trace']))
     cv.close()
+    e.enable_profiling(True)
     e.profile(reset=True)
     cv2 = eng.DeviceCanvas(e, g64['volume'], opts, 128.0, 33.0)
     st2 = cv2.segment_at(start)
     out['profile'] = e.profile()
     out['profile_device_seconds'] = cv2.counters().device_seconds
+    e.enable_profiling(False)
     cv2.close()
     return out
 

@@ -22,10 +22,12 @@ constexpr int kTmemCols = 512;    // >= kGroupTiles * kStackN, power of two
 
 // Field-of-view geometry in the "row" space the kernels work in.
 //
-// A FoV voxel (z, y, x) lives at row  r = z * pp + y * xp + x  with xp = fx + 1 and
-// pp = (fy + 1) * xp: every x-line is followed by ONE zero column and every z-plane by ONE zero
-// line, so the SAME-padding halo of a 3x3x3 tap is always a stored zero and a tap is a constant
-// row offset dz*pp + dy*xp + dx.  Rows are cut into tiles of 128 consecutive rows = one UMMA M.
+// A FoV voxel (z, y, x) lives at row  r = z * pp + y * xp + x  with xp = fx and pp = (fy + 1) * xp:
+// every z-plane is followed by ONE zero line, which supplies the SAME-padding halo of the dy taps
+// (dz halos are the zero guard rows before / after the FoV), so a (dz, dy) tap-row is the constant
+// row offset dz*pp + dy*xp.  The dx taps need no padding in memory: the tensor-core path stacks them
+// along N and adds the neighbouring rows' partial sums in the epilogue (skipping x = 0 / x = fx-1),
+// the fp32 path masks them.  Rows are cut into tiles of kTileOut output rows = one 128-row UMMA.
 struct Geom {
   int fz, fy, fx;   // FoV size (z, y, x)
   int mz, my, mx;   // margin = size // 2

@@ -97,8 +97,8 @@ Geom make_geom(const FfnModelDesc& m) {
   g.dy = m.deltas_zyx[1];
   g.dx = m.deltas_zyx[2];
   g.nconv = 2 * m.depth;
-  g.xp = g.fx + 1;
-  g.pp = (g.fy + 1) * g.xp;
+  g.xp = g.fx;                  // no pad column: the dx taps are resolved in the epilogue / by masking
+  g.pp = (g.fy + 1) * g.xp;     // one zero line after every z-plane supplies the dy halo
   g.nr = (g.fz - 1) * g.pp + (g.fy - 1) * g.xp + g.fx;
   g.nt = (g.nr + kTileOut - 1) / kTileOut;
   g.halo = g.xp + 1;

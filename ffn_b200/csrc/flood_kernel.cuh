@@ -404,7 +404,7 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
         float* xch = c.s_xchg + ((i & 1) * 2 + half) * (4 * 2 * 16);   // double-buffered by tile parity
         const int m = wq * 32 + c.lane;                       // accumulator row of this thread
         const int r = r0 + i * kTileOut - 1 + m;              // FoV row it holds partial sums for
-        int z, y, x;
+        int z = 0, y = 0, x = 1;
         const bool valid = m >= 1 && m <= kTileOut && r >= 0 && row_to_zyx(g, r, z, y, x);
         long long t0 = prof_now(c);
         mbar_wait(c, &c.mb_mma[i], bit_get(c, 5 + i));
@@ -438,6 +438,8 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
           float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k]), 1);   // from lane + 1
           if (c.lane == 0 && wq > 0) up = xch[((wq - 1) * 2 + 0) * 16 + k];
           if (c.lane == 31 && wq < 3) dn = xch[((wq + 1) * 2 + 1) * 16 + k];
+          if (x == 0) up = 0.f;           // SAME padding in x: row v-1 / v+1 belongs to the neighbouring line
+          if (x == g.fx - 1) dn = 0.f;
           v[k] = up + __uint_as_float(b[k]) + dn;
         }
         float part = 0.f;
@@ -513,7 +515,9 @@ __device__ __forceinline__ void f32_layer(Ctx& c, int layer) {
 #pragma unroll
     for (int k = 0; k < 32; ++k) v[k] = 0.f;
     for (int tap = 0; tap < 27; ++tap) {
-      const int off = (tap / 9 - 1) * g.pp + ((tap / 3) % 3 - 1) * g.xp + (tap % 3 - 1);
+      const int tx = tap % 3;
+      if ((tx == 0 && x == 0) || (tx == 2 && x == g.fx - 1)) continue;   // SAME padding in x
+      const int off = (tap / 9 - 1) * g.pp + ((tap / 3) % 3 - 1) * g.xp + (tx - 1);
       const float4* a = in + (size_t)g.guard + r + off;
       const float* wt = wsm + (size_t)tap * cin * 32;
       for (int q = 0; q < ngrp; ++q) {

@@ -40,6 +40,7 @@ struct Geom {
   int guard;        // zero rows before row 0 / after the last tile in global activation buffers
   int rows_alloc;   // guard + nt*128 + guard
   int V;            // fz*fy*fx voxels
+  float inv_pp, inv_xp;   // reciprocals for the exact float row decode (checked on the host at engine creation)
 };
 
 struct Weights {

@@ -105,6 +105,8 @@ Geom make_geom(const FfnModelDesc& m) {
   g.guard = ((g.pp + g.halo + 7) / 8) * 8;
   g.rows_alloc = g.guard + g.nt * kTileM + g.guard;
   g.V = g.fz * g.fy * g.fx;
+  g.inv_pp = 1.0f / (float)g.pp;
+  g.inv_xp = 1.0f / (float)g.xp;
   return g;
 }
 
@@ -243,6 +245,12 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   e->compute_mode = compute_mode;
   e->g = make_geom(*model);
   const Geom& g = e->g;
+  for (int r = 0; r < g.nt * kTileM; ++r) {   // the device decodes rows with two float multiplies: prove it exact
+    const int z = (int)(((float)r + 0.5f) * g.inv_pp);
+    const int rem = r - z * g.pp;
+    const int y = (int)(((float)rem + 0.5f) * g.inv_xp);
+    if (z != r / g.pp || y != rem / g.xp) return fail("float row decode is not exact for this field of view");
+  }
   const SmemLayout L = smem_layout(g);
   e->smem_bytes = L.total;
   if ((size_t)L.total > prop.sharedMemPerBlockOptin)

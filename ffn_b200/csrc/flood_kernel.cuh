@@ -96,6 +96,7 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
     sm100::red_release_add(c.p->ws.bar, 1u);
     unsigned spins = 0;
     while (sm100::ld_acquire_u32(c.p->ws.bar) < c.bar_target) {
+      __nanosleep(20);   // 147 CTAs poll one L2 line: back off so the leader's loads are not starved
       if ((++spins & 0xFF) == 0) {
         if (aborted(c)) break;
         const long long now = clock64();
@@ -118,9 +119,9 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
 // row -> (z, y, x); false for the zero pad column / pad line / rows past the FoV.
 __device__ __forceinline__ bool row_to_zyx(const Geom& g, int r, int& z, int& y, int& x) {
   if (r >= g.nr) return false;
-  z = r / g.pp;
+  z = (int)(((float)r + 0.5f) * g.inv_pp);          // exact for every row (verified in ffn_engine_create)
   const int rem = r - z * g.pp;
-  y = rem / g.xp;
+  y = (int)(((float)rem + 0.5f) * g.inv_xp);
   x = rem - y * g.xp;
   return y < g.fy && x < g.fx;
 }
@@ -243,15 +244,13 @@ __device__ __forceinline__ void epilogue_row(const Ctx& c, int layer, int r, flo
 // epilogue quads split every tile by channel so a tile's latency is halved.  Same arithmetic as
 // epilogue_row; for the last layer returns this half's share of <relu(net), w_lom>.
 __device__ __forceinline__ float epilogue_half(const Ctx& c, int layer, int r, float (&v)[16], int half,
-                                               float (&res)[16]) {
-  const KParams& p = *c.p;
-  const Geom& g = p.g;
-  const float* b = c.s_bias + layer * 32 + half * 16;
+                                               float (&res)[16], const float (&bias)[16], __half* out_base,
+                                               size_t chunk_stride) {
+  const Geom& g = c.p->g;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) v[k] += b[k];
+  for (int k = 0; k < 16; ++k) v[k] += bias[k];
   const bool is_b = (layer & 1) != 0;
   const bool last = layer == g.nconv - 1;
-  const size_t ra = (size_t)g.guard + r;
   if (is_b) {
     // fp32 residual stream: `res` comes from / goes back to this thread's TMEM lane (tc_layer)
     if (layer > 1) {
@@ -270,7 +269,7 @@ __device__ __forceinline__ float epilogue_half(const Ctx& c, int layer, int r, f
     for (int k = 0; k < 16; ++k) upd = fmaf(v[k], wl[k], upd);
     return upd;
   }
-  __half* dst = p.ws.act_h[layer & 1];
+  __half* dst = out_base + (size_t)r * 8;   // [k-chunk][row][8 halfs]; this half owns chunks 2*half, 2*half+1
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     uint4 o;
@@ -279,7 +278,7 @@ __device__ __forceinline__ float epilogue_half(const Ctx& c, int layer, int r, f
     h = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]); o.y = *reinterpret_cast<uint32_t*>(&h);
     h = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]); o.z = *reinterpret_cast<uint32_t*>(&h);
     h = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]); o.w = *reinterpret_cast<uint32_t*>(&h);
-    *reinterpret_cast<uint4*>(dst + ((size_t)(half * 2 + q) * g.rows_alloc + ra) * 8) = o;
+    *reinterpret_cast<uint4*>(dst + q * chunk_stride) = o;
   }
   return 0.f;
 }
@@ -400,6 +399,11 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
       // quad 0 (warps 0-3) takes feature maps 0-15, quad 1 (warps 4-7) feature maps 16-31.
       const int half = c.warp >> 2, wq = c.warp & 3;
       const bool last = layer == g.nconv - 1;
+      float bias[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) bias[k] = c.s_bias[layer * 32 + half * 16 + k];
+      const size_t chunk_stride = (size_t)g.rows_alloc * 8;
+      __half* out_base = p.ws.act_h[layer & 1] + (size_t)(half * 2) * chunk_stride + (size_t)g.guard * 8;
       for (int i = 0; i < ng; ++i) {
         float* xch = c.s_xchg + ((i & 1) * 2 + half) * (4 * 2 * 16);   // double-buffered by tile parity
         const int m = wq * 32 + c.lane;                       // accumulator row of this thread
@@ -432,21 +436,22 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
         quad_sync(half);
         // out[v] = D[v-1][dx=-1] + D[v][dx=0] + D[v+1][dx=+1]
         float v[16];
+        const float m_up = x == 0 ? 0.f : 1.f, m_dn = x == g.fx - 1 ? 0.f : 1.f;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           float up = __shfl_up_sync(0xffffffffu, __uint_as_float(a[k]), 1);      // from lane - 1
           float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k]), 1);   // from lane + 1
           if (c.lane == 0 && wq > 0) up = xch[((wq - 1) * 2 + 0) * 16 + k];
           if (c.lane == 31 && wq < 3) dn = xch[((wq + 1) * 2 + 1) * 16 + k];
-          if (x == 0) up = 0.f;           // SAME padding in x: row v-1 / v+1 belongs to the neighbouring line
-          if (x == g.fx - 1) dn = 0.f;
-          v[k] = up + __uint_as_float(b[k]) + dn;
+          // SAME padding in x: at x = 0 / x = fx-1 row v-1 / v+1 belongs to the neighbouring line (mask 0);
+          // all partial sums are finite (pad rows multiply zero activations), so 0 * value is exact
+          v[k] = fmaf(up, m_up, fmaf(dn, m_dn, __uint_as_float(b[k])));
         }
         float part = 0.f;
         float res[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) res[k] = need_res ? __uint_as_float(rr[k]) : 0.f;
-        if (valid) part = epilogue_half(c, layer, r, v, half, res);
+        if (valid) part = epilogue_half(c, layer, r, v, half, res, bias, out_base, chunk_stride);
         if ((layer & 1) && !last) {
 #pragma unroll
           for (int k = 0; k < 16; ++k) rr[k] = __float_as_uint(res[k]);

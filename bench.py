@@ -148,9 +148,11 @@ def best_cpu_threads():
   for n in sorted({min(ncpu, c) for c in (4, 8, 16, 32, 64, ncpu)}):
     torch.set_num_threads(n)
     net(seed, img)
-    t0 = time.time()
-    net(seed, img)
-    dt = time.time() - t0
+    dt = 1e30
+    for _ in range(3):                      # best of three: a single sample is too noisy on a shared host
+      t0 = time.time()
+      net(seed, img)
+      dt = min(dt, time.time() - t0)
     if dt < best_t:
       best, best_t = n, dt
   torch.set_num_threads(best)
@@ -289,6 +291,8 @@ def main():
 
   # ---- end-to-end leg: the user's call path with host buffers — canvas creation (H2D of the pinned
   # uint8 volume), the same flood fills, D2H of the touched seed / segmentation box
+  warm = eng.DeviceCanvas(engine, vol_pinned, opts, 128.0, 33.0, keep_probability_maps=True)   # allocator warm-up
+  warm.close()
   barrier()
   t0 = time.perf_counter()
   cv2 = eng.DeviceCanvas(engine, vol_pinned, opts, 128.0, 33.0, keep_probability_maps=True)

@@ -26,7 +26,7 @@ MASK_MOVEMENT = 0
 MASK_SEED = 1
 
 EXPORTS = [
-    'ffn_last_error', 'ffn_engine_create', 'ffn_engine_destroy', 'ffn_engine_set_compute_mode',
+    'ffn_last_error', 'ffn_engine_create', 'ffn_engine_destroy', 'ffn_engine_set_compute_mode', 'ffn_engine_set_grid',
     'ffn_engine_info', 'ffn_engine_profile', 'ffn_predict', 'ffn_canvas_create', 'ffn_canvas_destroy',
     'ffn_canvas_set_mask', 'ffn_canvas_segment_at', 'ffn_canvas_segment_all',
     'ffn_canvas_update_at', 'ffn_canvas_init_seed', 'ffn_canvas_read', 'ffn_canvas_write',
@@ -101,6 +101,7 @@ def load() -> C.CDLL:
   lib.ffn_engine_destroy.argtypes = [p]
   lib.ffn_engine_destroy.restype = None
   lib.ffn_engine_set_compute_mode.argtypes = [p, C.c_int]
+  lib.ffn_engine_set_grid.argtypes = [p, C.c_int]
   lib.ffn_engine_info.argtypes = [p, C.POINTER(C.c_int64)]
   lib.ffn_engine_profile.argtypes = [p, C.POINTER(C.c_int64), C.c_int]
   lib.ffn_predict.argtypes = [p, p, p, C.c_int, p]

@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
   if not force and up_to_date():
     return OUT
   cmd = [
-      nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+      nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--default-stream', 'per-thread',
       '-Xcompiler', '-fPIC', '-shared', '-o', OUT, SRC, '-lcudart',
   ]
   if verbose:

@@ -18,7 +18,8 @@ constexpr int kStackN = 96;       // UMMA N: the three dx taps of a (dz, dy) tap
 constexpr int kFeat = 32;         // feature maps of every hidden layer (UMMA N)
 constexpr int kGroupTiles = 3;    // tiles whose operands are staged in shared memory together
 constexpr int kMaxConv = 32;      // 2 * depth limit
-constexpr int kTmemCols = 512;    // >= kGroupTiles * kStackN, power of two
+constexpr int kTmemCols = 512;    // accumulators (kGroupTiles * kStackN columns) + fp32 residual stream (32 per tile)
+constexpr int kMaxTilesPerCta = (kTmemCols - kGroupTiles * kStackN) / kFeat;   // 7: bound by the TMEM-resident residual
 
 // Field-of-view geometry in the "row" space the kernels work in.
 //

@@ -122,15 +122,15 @@ int launch(FfnEngine* e, const CanvasDev& cv, CanvasState* d_state, const Job& j
   p.job = job;
   p.job.action = e->d_action;
   p.compute_mode = e->compute_mode;
-  CUDA_OK(cudaMemsetAsync(e->ws.bar, 0, sizeof(unsigned), e->stream));
-  CUDA_OK(cudaMemsetAsync(e->ws.abort_flag, 0, sizeof(int), e->stream));
-  CUDA_OK(cudaMemsetAsync(e->d_action, 0, sizeof(int), e->stream));
+  CUDA_OK(cudaMemsetAsync(e->ws.bar, 0, sizeof(unsigned), cudaStreamPerThread));
+  CUDA_OK(cudaMemsetAsync(e->ws.abort_flag, 0, sizeof(int), cudaStreamPerThread));
+  CUDA_OK(cudaMemsetAsync(e->d_action, 0, sizeof(int), cudaStreamPerThread));
   void* args[] = {&p};
-  CUDA_OK(cudaEventRecord(e->ev0, e->stream));
+  CUDA_OK(cudaEventRecord(e->ev0, cudaStreamPerThread));
   CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(ffn_flood_kernel), dim3(e->grid),
-                                      dim3(kThreads), args, (size_t)e->smem_bytes, e->stream));
-  CUDA_OK(cudaEventRecord(e->ev1, e->stream));
-  CUDA_OK(cudaStreamSynchronize(e->stream));
+                                      dim3(kThreads), args, (size_t)e->smem_bytes, cudaStreamPerThread));
+  CUDA_OK(cudaEventRecord(e->ev1, cudaStreamPerThread));
+  CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
   float ms = 0.f;
   CUDA_OK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->last_kernel_seconds = ms * 1e-3;
@@ -238,7 +238,10 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   std::unique_ptr<FfnEngine> e(new FfnEngine());
   e->device = device;
   CUDA_OK(cudaSetDevice(device));
-  CUDA_OK(cudaStreamCreate(&e->stream));   // blocking: ordered after legacy-stream memcpys
+  // Built with --default-stream per-thread: every copy / memset / launch of a host thread goes to that
+  // thread's own stream, so engines driven from different host threads run concurrently (SM-partitioned
+  // cooperative grids, see ffn_engine_set_grid) while each thread's operations stay ordered.
+
   CUDA_OK(cudaEventCreate(&e->ev0));
   CUDA_OK(cudaEventCreate(&e->ev1));
   e->sm_count = prop.multiProcessorCount;
@@ -260,8 +263,8 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffn_flood_kernel, kThreads, L.total));
   if (per_sm < 1) return fail("persistent kernel does not fit on an SM");
   e->grid = std::min(e->sm_count, g.nt);
-  if ((g.nt + e->grid - 1) / e->grid > kGroupTiles)
-    return fail("field of view needs more than " + std::to_string(kGroupTiles) +
+  if ((g.nt + e->grid - 1) / e->grid > kMaxTilesPerCta)
+    return fail("field of view needs more than " + std::to_string(kMaxTilesPerCta) +
                 " tiles per SM: the TMEM-resident residual stream does not fit (too few SMs for this FoV)");
 
   // weights
@@ -316,15 +319,24 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
 void ffn_engine_destroy(FfnEngine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  cudaStreamSynchronize(e->stream);
+  cudaDeviceSynchronize();
   for (void* p : e->owned) cudaFree(p);
   cudaFree(e->d_in_seed);
   cudaFree(e->d_in_image);
   cudaFree(e->d_out);
   cudaEventDestroy(e->ev0);
   cudaEventDestroy(e->ev1);
-  cudaStreamDestroy(e->stream);
   delete e;
+}
+
+int ffn_engine_set_grid(FfnEngine* e, int num_ctas) {
+  if (!e) return fail("null engine");
+  if (num_ctas <= 0) num_ctas = std::min(e->sm_count, e->g.nt);
+  if (num_ctas > e->sm_count || num_ctas > e->g.nt) return fail("grid larger than the SM / tile count");
+  if ((e->g.nt + num_ctas - 1) / num_ctas > kMaxTilesPerCta)
+    return fail("grid too small: at most " + std::to_string(kMaxTilesPerCta) + " tiles per CTA (TMEM residual)");
+  e->grid = num_ctas;
+  return 0;
 }
 
 int ffn_engine_set_compute_mode(FfnEngine* e, int mode) {
@@ -375,8 +387,8 @@ int ffn_predict(FfnEngine* e, const float* seed, const float* image, int batch, 
     if (dev_alloc(&e->d_out, n, false)) return 1;
     e->predict_cap = batch;
   }
-  CUDA_OK(cudaMemcpyAsync(e->d_in_seed, seed, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  CUDA_OK(cudaMemcpyAsync(e->d_in_image, image, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  CUDA_OK(cudaMemcpyAsync(e->d_in_seed, seed, n * sizeof(float), cudaMemcpyHostToDevice, cudaStreamPerThread));
+  CUDA_OK(cudaMemcpyAsync(e->d_in_image, image, n * sizeof(float), cudaMemcpyHostToDevice, cudaStreamPerThread));
   Job job{};
   job.mode = MODE_PREDICT;
   job.in_seed = e->d_in_seed;
@@ -426,7 +438,7 @@ int ffn_canvas_create(FfnEngine* e, const void* image, int image_dtype, const in
   if (keep_probability_maps) {
     if (dev_alloc(&cv.qprob, c->nvox)) return 1;
   }
-  fill_f32_kernel<<<e->sm_count * 8, 256, 0, e->stream>>>(cv.seed, c->nvox, NAN);
+  fill_f32_kernel<<<e->sm_count * 8, 256, 0, cudaStreamPerThread>>>(cv.seed, c->nvox, NAN);
   CUDA_OK(cudaGetLastError());
   // movement policy storage
   const int del[3] = {std::max(g.dz, 1), std::max(g.dy, 1), std::max(g.dx, 1)};
@@ -453,7 +465,7 @@ int ffn_canvas_create(FfnEngine* e, const void* image, int image_dtype, const in
     c->h_state.dirty_hi[k] = 0;
   }
   if (push_state(c.get())) return 1;
-  CUDA_OK(cudaStreamSynchronize(e->stream));
+  CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
   *out = c.release();
   return 0;
 }
@@ -505,14 +517,14 @@ int ffn_canvas_init_seed(FfnCanvas* c, const int32_t pos[3]) {
     for (int y = std::max(st.dirty_lo[1], 0); y < std::min(st.dirty_hi[1], c->cv.sy); ++y) {
       const int x0 = std::max(st.dirty_lo[2], 0), x1 = std::min(st.dirty_hi[2], c->cv.sx);
       if (x1 > x0) {
-        fill_f32_kernel<<<1, 128, 0, c->eng->stream>>>(c->cv.seed + ((size_t)z * c->cv.sy + y) * c->cv.sx + x0,
+        fill_f32_kernel<<<1, 128, 0, cudaStreamPerThread>>>(c->cv.seed + ((size_t)z * c->cv.sy + y) * c->cv.sx + x0,
                                                        (size_t)(x1 - x0), NAN);
       }
     }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(c->cv.seed + ((size_t)pos[0] * c->cv.sy + pos[1]) * c->cv.sx + pos[2],
-                          &c->cv.opt.init_activation, sizeof(float), cudaMemcpyHostToDevice, c->eng->stream));
-  CUDA_OK(cudaStreamSynchronize(c->eng->stream));
+                          &c->cv.opt.init_activation, sizeof(float), cudaMemcpyHostToDevice, cudaStreamPerThread));
+  CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
   for (int k = 0; k < 3; ++k) {
     st.dirty_lo[k] = pos[k];
     st.dirty_hi[k] = pos[k] + 1;
@@ -703,7 +715,7 @@ int ffn_canvas_read(FfnCanvas* c, int which, const int32_t lo[3], const int32_t 
     }
     float* tmp = nullptr;
     if (dev_alloc(&tmp, c->nvox, false)) return 1;
-    normalize_u8_kernel<<<c->eng->sm_count * 8, 256, 0, c->eng->stream>>>(
+    normalize_u8_kernel<<<c->eng->sm_count * 8, 256, 0, cudaStreamPerThread>>>(
         reinterpret_cast<const uint8_t*>(cv.image), tmp, c->nvox, cv.mean, cv.stddev);
     cudaError_t err = cudaMemcpy(dst, tmp, c->nvox * 4, cudaMemcpyDeviceToHost);
     cudaFree(tmp);
@@ -885,9 +897,9 @@ int ffn_canvas_device_ptr(FfnCanvas* c, int which, void** ptr, int64_t* bytes) {
 int ffn_canvas_add_id_offset(FfnCanvas* c, int32_t offset) {
   if (!c) return fail("null canvas");
   if (set_device(c->eng)) return 1;
-  relabel_offset_kernel<<<c->eng->sm_count * 8, 256, 0, c->eng->stream>>>(c->cv.seg, c->nvox, offset);
+  relabel_offset_kernel<<<c->eng->sm_count * 8, 256, 0, cudaStreamPerThread>>>(c->cv.seg, c->nvox, offset);
   CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaStreamSynchronize(c->eng->stream));
+  CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
   return 0;
 }
 

@@ -418,7 +418,7 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
         const uint32_t tbase = c.tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(i * kStackN + half * 16);
         // residual stream of this row / channel half: TMEM columns behind the accumulators
         const uint32_t tres = c.tmem_base + ((uint32_t)(wq * 32) << 16) +
-                              (uint32_t)(kGroupTiles * kStackN + i * kFeat + half * 16);
+                              (uint32_t)(kGroupTiles * kStackN + (g0 - c.t_begin + i) * kFeat + half * 16);
         uint32_t a[16], b[16], d2[16], rr[16];
         sm100::tmem_ld16(tbase, a);          // dx = -1 block: consumed by the lane above (m + 1)
         sm100::tmem_ld16(tbase + 32, b);     // dx =  0 block

@@ -42,7 +42,7 @@ class Engine:
 
   def __init__(self, weights_dhwio: Sequence[np.ndarray], biases: Sequence[np.ndarray],
                fov_zyx=(33, 33, 33), deltas_zyx=(8, 8, 8), device: int = 0,
-               compute_mode: int = _lib.COMPUTE_FP16_TC):
+               compute_mode: int = _lib.COMPUTE_FP16_TC, num_ctas: int = 0):
     self._lib = _lib.load()
     depth = (len(weights_dhwio) - 1) // 2
     if len(weights_dhwio) != 2 * depth + 1 or len(biases) != len(weights_dhwio):
@@ -71,6 +71,8 @@ class Engine:
                                             C.byref(h)))
     self._h = h
     self.compute_mode = int(compute_mode)
+    if num_ctas:
+      self.set_grid(num_ctas)
 
   def close(self):
     if getattr(self, '_h', None):
@@ -82,6 +84,10 @@ class Engine:
       self.close()
     except Exception:  # pylint: disable=broad-except
       pass
+
+  def set_grid(self, num_ctas: int):
+    """SM budget of this engine's persistent kernel (0 = whole GPU); see ffn_engine_set_grid."""
+    _lib.check(self._lib.ffn_engine_set_grid(self._h, int(num_ctas)))
 
   def set_compute_mode(self, mode: int):
     _lib.check(self._lib.ffn_engine_set_compute_mode(self._h, int(mode)))

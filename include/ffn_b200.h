@@ -116,6 +116,11 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
                       const float* const* biases, int compute_mode, FfnEngine** out);
 void ffn_engine_destroy(FfnEngine* engine);
 int ffn_engine_set_compute_mode(FfnEngine* engine, int compute_mode);
+/* Number of SMs (CTAs of the cooperative grid) this engine's kernel occupies; 0 = all.  Several engines
+ * with disjoint SM budgets (e.g. 3 x 49) driven from different host threads run their persistent kernels
+ * CONCURRENTLY on one GPU: the B200 form of the reference's batching across canvases
+ * (InferenceRequest.batch_size / concurrent_requests, doc/manual.md:89-97). */
+int ffn_engine_set_grid(FfnEngine* engine, int num_ctas);
 /* sm count, cooperative grid size, shared memory per CTA, tiles per FoV: info[0..3]. */
 int ffn_engine_info(FfnEngine* engine, int64_t info[8]);
 

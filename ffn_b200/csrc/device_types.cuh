@@ -9,14 +9,17 @@
 
 namespace ffn {
 
-constexpr int kThreads = 288;     // warps 0-7: two epilogue quads (TMEM lane quarters x 2 tiles); warp 8: TMA + UMMA issue
-constexpr int kIssueWarp = 8;
+constexpr int kThreads = 320;     // warps 0-7: epilogue (2 channel halves x 4 TMEM lane quarters); warp 8: TMA producer; warp 9: UMMA issuer
+constexpr int kLoadWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kActStages = 2;     // shared-memory ring of per-tile activation operands
+constexpr int kAccSlots = 3;      // TMEM ring of per-tile accumulators
 constexpr int kTileM = 128;       // UMMA M: accumulator rows per tensor-core tile
 constexpr int kTileOut = 126;     // FoV rows a tile OUTPUTS: the dx = -1/+1 partial sums live one row up/down, so
                                   // the first and last accumulator row of every tile only feed their neighbours
 constexpr int kStackN = 96;       // UMMA N: the three dx taps of a (dz, dy) tap-row stacked along N
 constexpr int kFeat = 32;         // feature maps of every hidden layer (UMMA N)
-constexpr int kGroupTiles = 3;    // tiles whose operands are staged in shared memory together
+constexpr int kGroupTiles = 3;    // accumulator slots in TMEM (the residual stream starts behind them)
 constexpr int kMaxConv = 32;      // 2 * depth limit
 constexpr int kTmemCols = 512;    // accumulators (kGroupTiles * kStackN columns) + fp32 residual stream (32 per tile)
 constexpr int kMaxTilesPerCta = (kTmemCols - kGroupTiles * kStackN) / kFeat;   // 7: bound by the TMEM-resident residual
@@ -183,8 +186,8 @@ __host__ __device__ inline SmemLayout smem_layout(const Geom& g) {
   SmemLayout s;
   s.wbuf = 0;
   s.act = 2 * 27 * 4 * 512;   // 110592
-  const int seg_rows = kGroupTiles * kTileOut + 2 * g.halo;
-  const int act_bytes = 3 * 4 * seg_rows * 16;
+  const int seg_rows = kTileOut + 2 * g.halo;               // one tile + halos per stage
+  const int act_bytes = kActStages * 3 * 4 * seg_rows * 16;
   s.bias = s.act + act_bytes;
   s.bars = s.bias + (kMaxConv + 1) * 32 * 4 + 16;
   s.total = s.bars + 4096 + 512;    // barriers/misc | prof | epilogue exchange + conv_lom dots | leader's state copy

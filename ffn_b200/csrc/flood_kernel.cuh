@@ -36,8 +36,11 @@ struct Ctx {
   unsigned char* smem;
   float* s_bias;               // [(nconv)*32] biases, then w_lom[32], b_lom
   uint64_t* mb_w;              // [2]
-  uint64_t* mb_act;            // [3] one per z-plane segment (dz = -1, 0, +1)
-  uint64_t* mb_mma;            // [kGroupTiles]
+  uint64_t* mb_full;           // [kActStages] TMA -> UMMA: a tile's operands have landed
+  uint64_t* mb_empty;          // [kActStages] UMMA -> TMA: the stage may be overwritten
+  uint64_t* mb_tfull;          // [kAccSlots]  UMMA -> epilogue: accumulators complete
+  uint64_t* mb_tempty;         // [kAccSlots]  epilogue -> UMMA: accumulators drained (8 arrivals)
+  unsigned load_cnt, mma_cnt, epi_cnt;   // per-role running tile counters (ring index + phase parity)
   uint32_t* s_tmem;            // TMEM base address
   int* s_misc;                 // [0] step count>=th accumulator, [1..] leader scratch
   float* s_xchg;               // [2 tile parities][2 halves][4 warps][2][16] partial sums crossing warp boundaries
@@ -296,31 +299,37 @@ __device__ __forceinline__ void tc_issue_weight_load(Ctx& c, int layer) {
   sm100::bulk_g2s(c.smem + buf * (27 * 4 * 512), p.w.w16 + w16_layer_offset_halfs(layer), bytes, &c.mb_w[buf]);
 }
 
-// Issues the 3 * NCH/2 UMMAs (128 x 96 x 16) of one tile that read z-plane segment `tz`: one per dy
-// tap-row and k-pair; the three dx taps ride along N.  Fully unrolled: every A start-address offset
-// is (const * seg_rows + const * xp), so the loop body is two adds and the UMMA.
+// Issues the 9 * NCH/2 UMMAs (128 x 96 x 16) of one tile: one per (dz, dy) tap-row and k-pair; the
+// three dx taps ride along N.  Fully unrolled: every A start-address offset is
+// (const * seg_rows + const * xp), so the loop body is two adds and the UMMA.
 template <int NCH>
-__device__ __forceinline__ void tc_issue_plane(uint32_t d, uint32_t a_lo, uint32_t b_lo, int seg_rows, int xp, int tz,
-                                               uint32_t accumulate) {
+__device__ __forceinline__ void tc_issue_tile(uint32_t d, uint32_t a_lo, uint32_t b_lo, int seg_rows, int xp) {
   const uint32_t idesc = sm100::umma_idesc_f16(kTileM, kStackN);
   const uint64_t hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
 #pragma unroll
-  for (int ty = 0; ty < 3; ++ty) {
+  for (int row = 0; row < 9; ++row) {
+    const int tz = row / 3, ty = row % 3;
 #pragma unroll
     for (int j = 0; j < NCH / 2; ++j) {
       const uint32_t aoff = (uint32_t)((tz * NCH + 2 * j) * seg_rows + ty * xp);
-      const uint32_t boff = (uint32_t)(((tz * 3 + ty) * NCH + 2 * j) * (12 * 128 / 16));
+      const uint32_t boff = (uint32_t)((row * NCH + 2 * j) * (12 * 128 / 16));
       sm100::umma_f16(d, hi | (uint64_t)(a_lo + aoff), hi | (uint64_t)(b_lo + boff), idesc,
-                      (ty | j) != 0 ? 1u : accumulate);
+                      (row | j) != 0 ? 1u : 0u);
     }
   }
 }
 
-__device__ __forceinline__ void quad_sync(int quad) {   // the four epilogue warps of one tile
+__device__ __forceinline__ void quad_sync(int quad) {   // the four epilogue warps of one channel half
   asm volatile("bar.sync %0, 128;" ::"r"(quad + 1) : "memory");
 }
 
-// Tensor-core layer.  Accumulator row m of a tile holds, for the FoV row u = tile_row0 - 1 + m,
+// Tensor-core layer as a warp-specialised ring pipeline over this CTA's tiles:
+//   warp 8  TMA producer : per tile, 12 bulk copies (3 z-planes x k-chunks, 126 + 2*halo rows) into a
+//                          2-stage shared-memory ring              full[stage]  <-  empty[stage]
+//   warp 9  UMMA issuer  : 18 UMMAs 128x96x16 per tile into a 3-slot TMEM ring; one commit frees the
+//                          smem stage, one publishes the slot      tfull[slot]  <-  tempty[slot]
+//   warps 0-7 epilogue   : every tile by all eight warps (2 channel halves x 4 TMEM lane quarters)
+// Accumulator row m of a tile holds, for the FoV row u = tile_row0 - 1 + m,
 //   D[u][dx*32 + co] = sum_{dz,dy,ci} act[u + dz*pp + dy*xp][ci] * W[dz,dy,dx][ci][co]
 // and the convolution output is out[v] = D[v-1][dx=-1] + D[v][dx=0] + D[v+1][dx=+1]: one lane up /
 // down, done with warp shuffles (+ a 2 KB shared-memory exchange at the three warp boundaries).
@@ -332,162 +341,161 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
   const __half* in = layer == 0 ? p.ws.act0_h : p.ws.act_h[(layer - 1) & 1];
   const int buf = layer & 1;
   unsigned char* act_smem = c.smem + 2 * 27 * 4 * 512;
-  const int seg_rows = kGroupTiles * kTileOut + 2 * g.halo;   // fixed k-chunk plane pitch (rows)
-  const bool issuer = c.warp == kIssueWarp && c.lane == 0;
+  const int seg_rows = kTileOut + 2 * g.halo;                 // k-chunk plane pitch of a stage (rows)
+  const int stage_bytes = 3 * 4 * seg_rows * 16;
+  const int ntiles = c.t_end - c.t_begin;
   const bool need_res = (layer & 1) && layer > 1;
-
-  bit_set(c, 8 + ((layer + 1) & 1), true);   // weight prefetch is issued once this layer's activations landed
-
+  const bool last = layer == g.nconv - 1;
   int hit = 0;
-  for (int g0 = c.t_begin; g0 < c.t_end; g0 += kGroupTiles) {
-    const int ng = min(kGroupTiles, c.t_end - g0);
-    const int r0 = g0 * kTileOut;
-    const bool first = g0 == c.t_begin;
-    if (c.warp == kIssueWarp) {
-      if (c.lane == 0) {
-        // ---- TMA producer: three z-plane segments x k-chunks of the input activations, centre plane
-        // first; each segment has its own mbarrier so the UMMAs of a plane start as soon as it lands.
-        const int load_rows = ng * kTileOut + 2 * g.halo;
-        long long t0 = prof_now(c);
-        sm100::fence_proxy_async();
+
+  bit_set(c, 8 + ((layer + 1) & 1), true);   // the next layer's weights are prefetched below
+
+  if (c.warp == kLoadWarp) {
+    if (c.lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      sm100::fence_proxy_async();   // other CTAs' generic-proxy stores (ordered by the barrier) -> async proxy
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = c.load_cnt % kActStages;
+        mbar_wait(c, &c.mb_empty[s], ((c.load_cnt / kActStages) & 1u) ^ 1u);
+        const int r0 = (c.t_begin + j) * kTileOut;
+        unsigned char* dst = act_smem + (size_t)s * stage_bytes;
+        sm100::mbar_expect_tx(&c.mb_full[s], (uint32_t)(3 * nch * seg_rows * 16));
         for (int oi = 0; oi < 3; ++oi) {
           const int dzi = oi == 0 ? 1 : (oi == 1 ? 0 : 2);   // centre plane first
-          sm100::mbar_expect_tx(&c.mb_act[dzi], (uint32_t)(nch * load_rows * 16));
           for (int ch = 0; ch < nch; ++ch)
-            sm100::bulk_g2s(act_smem + (size_t)(dzi * nch + ch) * seg_rows * 16,
+            sm100::bulk_g2s(dst + (size_t)(dzi * nch + ch) * seg_rows * 16,
                             in + ((size_t)ch * g.rows_alloc + g.guard + r0 + (dzi - 1) * g.pp - g.halo) * 8,
-                            (uint32_t)load_rows * 16, &c.mb_act[dzi]);
+                            (uint32_t)seg_rows * 16, &c.mb_full[s]);
         }
-        if (first) {
-          const long long tw = prof_now(c);
-          mbar_wait(c, &c.mb_w[buf], bit_get(c, buf));
-          prof_add(c, 2, prof_now(c) - tw);
-        }
-        // ---- UMMA issue: only the 14-bit start-address field changes between instructions
-        const uint32_t a_lo = ((sm100::smem_u32(act_smem) >> 4) & 0x3FFFu) | ((uint32_t)seg_rows << 16);
-        const uint32_t b_lo = ((sm100::smem_u32(c.smem + buf * (27 * 4 * 512)) >> 4) & 0x3FFFu) | ((12u * 128u >> 4) << 16);
-        long long issue_cycles = 0;
-        for (int i = 0; i < ng; ++i) {
-          const uint32_t d = c.tmem_base + (uint32_t)(i * kStackN);
-          for (int oi = 0; oi < 3; ++oi) {
-            const int tz = oi == 0 ? 1 : (oi == 1 ? 0 : 2);
-            if (i == 0) {
-              mbar_wait(c, &c.mb_act[tz], bit_get(c, 2 + tz));
-              sm100::tc_fence_after();
-              if (oi == 0) prof_add(c, 1, prof_now(c) - t0);
-              // Prefetch the next layer's weights (next step's layer 0 after the last layer) into the
-              // other buffer — its previous user (layer - 1) has completed all MMAs — only once this
-              // layer's activations have landed, so the 55 KB do not compete with the critical loads.
-              if (oi == 2 && first) tc_issue_weight_load(c, (layer + 1 == g.nconv) ? 0 : layer + 1);
-            }
-            const long long ti = prof_now(c);
-            if (layer == 0) {
-              tc_issue_plane<2>(d, a_lo + (uint32_t)(i * kTileOut), b_lo, seg_rows, g.xp, tz, oi ? 1u : 0u);
-            } else {
-              tc_issue_plane<4>(d, a_lo + (uint32_t)(i * kTileOut), b_lo, seg_rows, g.xp, tz, oi ? 1u : 0u);
-            }
-            issue_cycles += prof_now(c) - ti;
-          }
-          sm100::umma_commit(&c.mb_mma[i]);
-        }
-        t0 = prof_now(c) - issue_cycles;
-        prof_add(c, 3, prof_now(c) - t0);
+        ++c.load_cnt;
       }
-      __syncwarp();
-    } else {
-      // ---- Epilogue: every tile is handled by all eight warps — warp w reads TMEM lanes 32*(w%4)..,
-      // quad 0 (warps 0-3) takes feature maps 0-15, quad 1 (warps 4-7) feature maps 16-31.
-      const int half = c.warp >> 2, wq = c.warp & 3;
-      const bool last = layer == g.nconv - 1;
-      float bias[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) bias[k] = c.s_bias[layer * 32 + half * 16 + k];
-      const size_t chunk_stride = (size_t)g.rows_alloc * 8;
-      __half* out_base = p.ws.act_h[layer & 1] + (size_t)(half * 2) * chunk_stride + (size_t)g.guard * 8;
-      for (int i = 0; i < ng; ++i) {
-        float* xch = c.s_xchg + ((i & 1) * 2 + half) * (4 * 2 * 16);   // double-buffered by tile parity
-        const int m = wq * 32 + c.lane;                       // accumulator row of this thread
-        const int r = r0 + i * kTileOut - 1 + m;              // FoV row it holds partial sums for
-        int z = 0, y = 0, x = 1;
-        const bool valid = m >= 1 && m <= kTileOut && r >= 0 && row_to_zyx(g, r, z, y, x);
-        long long t0 = prof_now(c);
-        mbar_wait(c, &c.mb_mma[i], bit_get(c, 5 + i));
-        if (c.tid == 0) prof_add(c, 4, prof_now(c) - t0);
+      // Prefetch the next layer's weights (next step's layer 0 after the last layer) into the other
+      // buffer — its previous user (layer - 1) has completed all MMAs — behind this layer's operands.
+      tc_issue_weight_load(c, (layer + 1 == g.nconv) ? 0 : layer + 1);
+    }
+    __syncwarp();
+  } else if (c.warp == kMmaWarp) {
+    if (c.lane == 0) {
+      // ---------------------------------------------------------------- UMMA issuer
+      long long t0 = prof_now(c);
+      mbar_wait(c, &c.mb_w[buf], bit_get(c, buf));
+      prof_add(c, 2, prof_now(c) - t0);
+      const uint32_t b_lo = ((sm100::smem_u32(c.smem + buf * (27 * 4 * 512)) >> 4) & 0x3FFFu) | ((12u * 128u >> 4) << 16);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = c.mma_cnt % kActStages, slot = c.mma_cnt % kAccSlots;
         t0 = prof_now(c);
+        mbar_wait(c, &c.mb_full[s], (c.mma_cnt / kActStages) & 1u);
+        prof_add(c, 1, prof_now(c) - t0);
+        mbar_wait(c, &c.mb_tempty[slot], ((c.mma_cnt / kAccSlots) & 1u) ^ 1u);
         sm100::tc_fence_after();
-        const uint32_t tbase = c.tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(i * kStackN + half * 16);
-        // residual stream of this row / channel half: TMEM columns behind the accumulators
-        const uint32_t tres = c.tmem_base + ((uint32_t)(wq * 32) << 16) +
-                              (uint32_t)(kGroupTiles * kStackN + (g0 - c.t_begin + i) * kFeat + half * 16);
-        uint32_t a[16], b[16], d2[16], rr[16];
-        sm100::tmem_ld16(tbase, a);          // dx = -1 block: consumed by the lane above (m + 1)
-        sm100::tmem_ld16(tbase + 32, b);     // dx =  0 block
-        sm100::tmem_ld16(tbase + 64, d2);    // dx = +1 block: consumed by the lane below (m - 1)
-        if (need_res) sm100::tmem_ld16(tres, rr);
-        sm100::tmem_ld_wait();
-        if (c.lane == 31) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) xch[(wq * 2 + 0) * 16 + k] = __uint_as_float(a[k]);
+        t0 = prof_now(c);
+        const uint32_t a_lo = ((sm100::smem_u32(act_smem + (size_t)s * stage_bytes) >> 4) & 0x3FFFu) | ((uint32_t)seg_rows << 16);
+        const uint32_t d = c.tmem_base + (uint32_t)(slot * kStackN);
+        if (layer == 0) {
+          tc_issue_tile<2>(d, a_lo, b_lo, seg_rows, g.xp);
+        } else {
+          tc_issue_tile<4>(d, a_lo, b_lo, seg_rows, g.xp);
         }
-        if (c.lane == 0) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) xch[(wq * 2 + 1) * 16 + k] = __uint_as_float(d2[k]);
-        }
-        quad_sync(half);
-        // out[v] = D[v-1][dx=-1] + D[v][dx=0] + D[v+1][dx=+1]
-        float v[16];
-        const float m_up = x == 0 ? 0.f : 1.f, m_dn = x == g.fx - 1 ? 0.f : 1.f;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          float up = __shfl_up_sync(0xffffffffu, __uint_as_float(a[k]), 1);      // from lane - 1
-          float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k]), 1);   // from lane + 1
-          if (c.lane == 0 && wq > 0) up = xch[((wq - 1) * 2 + 0) * 16 + k];
-          if (c.lane == 31 && wq < 3) dn = xch[((wq + 1) * 2 + 1) * 16 + k];
-          // SAME padding in x: at x = 0 / x = fx-1 row v-1 / v+1 belongs to the neighbouring line (mask 0);
-          // all partial sums are finite (pad rows multiply zero activations), so 0 * value is exact
-          v[k] = fmaf(up, m_up, fmaf(dn, m_dn, __uint_as_float(b[k])));
-        }
-        float part = 0.f;
-        float res[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) res[k] = need_res ? __uint_as_float(rr[k]) : 0.f;
-        if (valid) part = epilogue_half(c, layer, r, v, half, res, bias, out_base, chunk_stride);
-        if ((layer & 1) && !last) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) rr[k] = __float_as_uint(res[k]);
-          sm100::tmem_st16(tres, rr);
-          sm100::tmem_st_wait();
-        }
-        if (last) {
-          // conv_lom: combine the two halves' dot products, then logits = seed + update
-          float* dot = c.s_dot + (i & 1) * kTileM;
-          if (half == 1) dot[m] = part;
-          asm volatile("bar.sync 3, 256;" ::: "memory");
-          if (half == 0 && valid) {
-            const float* wl = c.s_bias + g.nconv * 32;
-            const float upd = part + dot[m] + wl[32];
-            const float raw = p.ws.seed_raw[r];
-            const float fed = isnan(raw) ? p.cv.opt.pad_value : raw;
-            const float logit = fed + upd;
-            p.ws.logits[r] = logit;
-            hit += (logit >= p.cv.opt.move_threshold) ? 1 : 0;
-          }
-        }
-        if (c.tid == 0) prof_add(c, 5, prof_now(c) - t0);
+        sm100::umma_commit(&c.mb_tfull[slot]);   // accumulators of this tile complete
+        sm100::umma_commit(&c.mb_empty[s]);      // ... and its shared-memory stage is free again
+        prof_add(c, 3, prof_now(c) - t0);
+        ++c.mma_cnt;
       }
     }
-    c.bits ^= 7u << 2;
-    if (first) {
-      bit_flip(c, buf);
-      bit_set(c, 8 + buf, false);
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-7)
+    const int half = c.warp >> 2, wq = c.warp & 3;
+    float bias[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) bias[k] = c.s_bias[layer * 32 + half * 16 + k];
+    const size_t chunk_stride = (size_t)g.rows_alloc * 8;
+    __half* out_base = p.ws.act_h[layer & 1] + (size_t)(half * 2) * chunk_stride + (size_t)g.guard * 8;
+    for (int j = 0; j < ntiles; ++j) {
+      const int slot = c.epi_cnt % kAccSlots;
+      float* xch = c.s_xchg + ((j & 1) * 2 + half) * (4 * 2 * 16);   // double-buffered by tile parity
+      const int m = wq * 32 + c.lane;                                 // accumulator row of this thread
+      const int r = (c.t_begin + j) * kTileOut - 1 + m;               // FoV row it holds partial sums for
+      int z = 0, y = 0, x = 1;
+      const bool valid = m >= 1 && m <= kTileOut && r >= 0 && row_to_zyx(g, r, z, y, x);
+      long long t0 = prof_now(c);
+      mbar_wait(c, &c.mb_tfull[slot], (c.epi_cnt / kAccSlots) & 1u);
+      if (c.tid == 0) prof_add(c, 4, prof_now(c) - t0);
+      t0 = prof_now(c);
+      sm100::tc_fence_after();
+      const uint32_t tbase = c.tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(slot * kStackN + half * 16);
+      // residual stream of this row / channel half: TMEM columns behind the accumulator ring
+      const uint32_t tres = c.tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(kAccSlots * kStackN + j * kFeat + half * 16);
+      uint32_t a[16], b[16], d2[16], rr[16];
+      sm100::tmem_ld16(tbase, a);          // dx = -1 block: consumed by the lane above (m + 1)
+      sm100::tmem_ld16(tbase + 32, b);     // dx =  0 block
+      sm100::tmem_ld16(tbase + 64, d2);    // dx = +1 block: consumed by the lane below (m - 1)
+      if (need_res) sm100::tmem_ld16(tres, rr);
+      sm100::tmem_ld_wait();
+      // the accumulators are in registers: hand the TMEM slot back to the UMMA issuer
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (c.lane == 0) sm100::mbar_arrive(&c.mb_tempty[slot]);
+      if (c.lane == 31) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) xch[(wq * 2 + 0) * 16 + k] = __uint_as_float(a[k]);
+      }
+      if (c.lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) xch[(wq * 2 + 1) * 16 + k] = __uint_as_float(d2[k]);
+      }
+      quad_sync(half);
+      // out[v] = D[v-1][dx=-1] + D[v][dx=0] + D[v+1][dx=+1]
+      float v[16];
+      const float m_up = x == 0 ? 0.f : 1.f, m_dn = x == g.fx - 1 ? 0.f : 1.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float up = __shfl_up_sync(0xffffffffu, __uint_as_float(a[k]), 1);      // from lane - 1
+        float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k]), 1);   // from lane + 1
+        if (c.lane == 0 && wq > 0) up = xch[((wq - 1) * 2 + 0) * 16 + k];
+        if (c.lane == 31 && wq < 3) dn = xch[((wq + 1) * 2 + 1) * 16 + k];
+        // SAME padding in x: at x = 0 / x = fx-1 row v-1 / v+1 belongs to the neighbouring line (mask 0);
+        // all partial sums are finite (pad rows multiply zero activations), so 0 * value is exact
+        v[k] = fmaf(up, m_up, fmaf(dn, m_dn, __uint_as_float(b[k])));
+      }
+      float part = 0.f;
+      float res[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) res[k] = need_res ? __uint_as_float(rr[k]) : 0.f;
+      if (valid) part = epilogue_half(c, layer, r, v, half, res, bias, out_base, chunk_stride);
+      if ((layer & 1) && !last) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) rr[k] = __float_as_uint(res[k]);
+        sm100::tmem_st16(tres, rr);
+        sm100::tmem_st_wait();
+      }
+      if (last) {
+        // conv_lom: combine the two halves' dot products, then logits = seed + update
+        float* dot = c.s_dot + (j & 1) * kTileM;
+        if (half == 1) dot[m] = part;
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (half == 0 && valid) {
+          const float* wl = c.s_bias + g.nconv * 32;
+          const float upd = part + dot[m] + wl[32];
+          const float raw = p.ws.seed_raw[r];
+          const float fed = isnan(raw) ? p.cv.opt.pad_value : raw;
+          const float logit = fed + upd;
+          p.ws.logits[r] = logit;
+          hit += (logit >= p.cv.opt.move_threshold) ? 1 : 0;
+        }
+      }
+      if (c.tid == 0) prof_add(c, 5, prof_now(c) - t0);
+      ++c.epi_cnt;
     }
-    for (int i = 0; i < ng; ++i) bit_flip(c, 5 + i);
-    sm100::tc_fence_before();
-    const long long t_sync = prof_now(c);
-    __syncthreads();   // act smem / TMEM are reused by the next group or layer
-    if (c.tid == 0) prof_add(c, 15, prof_now(c) - t_sync);
   }
-  if (layer == g.nconv - 1) {
+  // weights: this layer's buffer has been consumed, the other one is in flight
+  bit_flip(c, buf);
+  bit_set(c, 8 + buf, false);
+  sm100::tc_fence_before();
+  const long long t_sync = prof_now(c);
+  __syncthreads();   // every role has finished the layer (stores issued, UMMAs committed and drained)
+  if (c.tid == 0) prof_add(c, 15, prof_now(c) - t_sync);
+  if (last) {
     hit = __reduce_add_sync(0xffffffffu, hit);
     if (c.lane == 0 && hit) atomicAdd(&c.s_misc[0], hit);
   }
@@ -1256,9 +1264,12 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   const SmemLayout L = smem_layout(p.g);
   c.s_bias = reinterpret_cast<float*>(smem_raw + L.bias);
   c.mb_w = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
-  c.mb_act = c.mb_w + 2;
-  c.mb_mma = c.mb_w + 5;
-  c.s_tmem = reinterpret_cast<uint32_t*>(c.mb_w + 5 + kGroupTiles);
+  c.mb_full = c.mb_w + 2;
+  c.mb_empty = c.mb_full + kActStages;
+  c.mb_tfull = c.mb_empty + kActStages;
+  c.mb_tempty = c.mb_tfull + kAccSlots;
+  c.s_tmem = reinterpret_cast<uint32_t*>(c.mb_tempty + kAccSlots);
+  c.load_cnt = c.mma_cnt = c.epi_cnt = 0;
   c.s_misc = reinterpret_cast<int*>(c.s_tmem + 2);
   c.s_xchg = reinterpret_cast<float*>(smem_raw + L.bars + 1024);
   c.s_dot = c.s_xchg + 2 * 2 * 4 * 2 * 16;
@@ -1281,8 +1292,14 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
     if (c.tid == 0) {
       sm100::mbar_init(&c.mb_w[0], 1);
       sm100::mbar_init(&c.mb_w[1], 1);
-      for (int i = 0; i < 3; ++i) sm100::mbar_init(&c.mb_act[i], 1);
-      for (int i = 0; i < kGroupTiles; ++i) sm100::mbar_init(&c.mb_mma[i], 1);
+      for (int i = 0; i < kActStages; ++i) {
+        sm100::mbar_init(&c.mb_full[i], 1);
+        sm100::mbar_init(&c.mb_empty[i], 1);
+      }
+      for (int i = 0; i < kAccSlots; ++i) {
+        sm100::mbar_init(&c.mb_tfull[i], 1);
+        sm100::mbar_init(&c.mb_tempty[i], 8);   // one arrival per epilogue warp
+      }
       sm100::fence_mbar_init();
     }
     __syncwarp();
@@ -1291,7 +1308,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
     __syncthreads();
     sm100::tc_fence_after();
     c.tmem_base = *c.s_tmem;
-    if (c.warp == kIssueWarp && c.lane == 0) tc_issue_weight_load(c, 0);
+    if (c.warp == kLoadWarp && c.lane == 0) tc_issue_weight_load(c, 0);
     bit_set(c, 8, true);
   }
   __syncthreads();

@@ -50,19 +50,20 @@ class ExecutorClient:
 
 
 class B200ExecutorClient(ExecutorClient):
-  """Client bound to a `B200Executor`; `predict` runs the conv stack on the GPU."""
+  """Client bound to one engine of a `B200Executor`; `predict` runs the conv stack on the GPU."""
 
-  def __init__(self, counters, interface, executor):
+  def __init__(self, counters, interface, executor, slot):
     super().__init__(counters, interface)
     self._executor = executor
+    self._slot = slot
 
   @property
   def engine(self) -> engine_lib.Engine:
-    return self._executor.engine
+    return self._executor.engines[self._slot]
 
   @property
   def engine_lock(self):
-    return self._executor.lock
+    return self._executor.locks[self._slot]
 
   def start(self) -> int:
     with self._interface.lock:
@@ -87,7 +88,7 @@ class B200ExecutorClient(ExecutorClient):
     if unknown:
       raise KeyError('unsupported fetches: %r' % unknown)
     with timer_counter(self.counters, 'client-wait'):
-      with self._executor.lock:
+      with self.engine_lock:
         logits = self.engine.predict(seed, image)
     return {'logits': logits[..., np.newaxis]}
 
@@ -150,11 +151,34 @@ class B200Executor(BatchExecutor):
           weights, biases = tf_checkpoint.load_convstack_npz(checkpoint_path)
         else:
           weights, biases = tf_checkpoint.load_convstack_weights(checkpoint_path, model.depth)
-    self.lock = threading.RLock()
-    self.engine = engine_lib.Engine(weights, biases, fov_zyx=tuple(int(v) for v in info.input_image_size[::-1]),
-                                    deltas_zyx=tuple(int(v) for v in info.deltas[::-1]), device=device,
-                                    compute_mode=compute_mode)
+    # batch_size = number of canvases served concurrently (InferenceRequest.batch_size,
+    # doc/manual.md:89-97).  The reference batches their FoVs into one session.run; here every
+    # concurrent canvas gets its own engine with an equal share of the SMs, and the engines'
+    # persistent kernels run side by side on the GPU (one host thread per canvas).
+    n = max(1, int(batch_size))
+    fov = tuple(int(v) for v in info.input_image_size[::-1])
+    deltas = tuple(int(v) for v in info.deltas[::-1])
+    self.engines, self.locks = [], []
+    first = engine_lib.Engine(weights, biases, fov_zyx=fov, deltas_zyx=deltas, device=device, compute_mode=compute_mode)
+    sms = first.info()['grid']
+    self.engines.append(first)
+    for _ in range(1, n):
+      self.engines.append(engine_lib.Engine(weights, biases, fov_zyx=fov, deltas_zyx=deltas, device=device,
+                                            compute_mode=compute_mode))
+    if n > 1:
+      for e in self.engines:
+        e.set_grid(sms // n)
+    self.locks = [threading.RLock() for _ in self.engines]
+    self._next_slot = 0
     self._running = False
+
+  @property
+  def engine(self):
+    return self.engines[0]
+
+  @property
+  def lock(self):
+    return self.locks[0]
 
   def start_server(self):
     self._interface.exit_request.clear()
@@ -166,13 +190,20 @@ class B200Executor(BatchExecutor):
       self._running = False
 
   def get_client(self, subvol_counters):
-    return B200ExecutorClient(subvol_counters, self._interface, self)
+    with self._interface.lock:
+      slot = self._next_slot % len(self.engines)
+      self._next_slot += 1
+    return B200ExecutorClient(subvol_counters, self._interface, self, slot)
+
+  @property
+  def num_devices(self):
+    return 1
 
   def close(self):
     self.stop_server()
-    if self.engine is not None:
-      self.engine.close()
-      self.engine = None
+    for e in self.engines:
+      e.close()
+    self.engines = []
 
 
 # Name kept so code written against the reference's class keeps importing.

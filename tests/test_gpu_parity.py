@@ -365,3 +365,47 @@ def test_canvas_checkpoint_roundtrip(tmp_path, golden_dir, g64):
   assert total_a == total_b == 80
   np.testing.assert_array_equal(np.asarray(b.seed), np.asarray(a.seed))
   exe.close()
+
+
+def test_concurrent_canvases_batch_size_two(golden_dir, g64):
+  """InferenceRequest.batch_size semantics: two canvases served concurrently (two engines, half the
+  SMs each, one host thread per canvas) produce exactly what the whole-GPU engine produces."""
+  import threading
+  from ffn.inference import executor, inference, inference_pb2, inference_utils, seed as seed_mod
+  from ffn.training.models import convstack_3d
+  from ffn_b200 import _lib
+  model = convstack_3d.ConvStack3DFFNModel(fov_size=[33, 33, 33], deltas=[8, 8, 8], depth=12)
+  opts = inference_pb2.InferenceOptions(init_activation=0.95, pad_value=0.05, move_threshold=0.9,
+                                        segment_threshold=0.6, min_segment_size=1000)
+  opts.min_boundary_dist.x = opts.min_boundary_dist.y = opts.min_boundary_dist.z = 1
+  ckpt = os.path.join(golden_dir, 'fib25_convstack.npz')
+  vols = [g64['volume'], np.ascontiguousarray(g64['volume'][::-1])]
+
+  def run(exe, vol, out, i):
+    cv = inference.Canvas(model.info, exe.get_client(inference_utils.Counters()), vol, opts,
+                          keep_probability_maps=True, image_mean=128, image_stddev=33)
+    cv.segment_all(seed_policy=seed_mod.PolicyGrid3d)
+    out[i] = (np.asarray(cv.segmentation), np.asarray(cv.seg_prob), dict(cv.origins))
+
+  ref_exe = executor.B200Executor(executor.ExecutorInterface(), model, inference_utils.Counters(), batch_size=1,
+                                  checkpoint_path=ckpt)
+  want = [None, None]
+  for i in range(2):
+    run(ref_exe, vols[i], want, i)
+  ref_exe.close()
+
+  exe = executor.B200Executor(executor.ExecutorInterface(), model, inference_utils.Counters(), batch_size=2,
+                              checkpoint_path=ckpt)
+  assert len(exe.engines) == 2 and exe.engines[0].info()['grid'] * 2 <= exe.engines[0].info()['sm_count']
+  got = [None, None]
+  threads = [threading.Thread(target=run, args=(exe, vols[i], got, i)) for i in range(2)]
+  for t in threads:
+    t.start()
+  for t in threads:
+    t.join()
+  exe.close()
+  for i in range(2):
+    np.testing.assert_array_equal(got[i][0], want[i][0])
+    np.testing.assert_array_equal(got[i][1], want[i][1])
+    assert {k: (v.start_zyx, v.iters) for k, v in got[i][2].items()} == \
+        {k: (v.start_zyx, v.iters) for k, v in want[i][2].items()}

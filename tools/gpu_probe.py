@@ -40,7 +40,7 @@ def run_mode(tag, mode):
   E = {}
   @stage(tag + '_engine')
   def _():
-    E['e'] = eng.Engine(w, b, compute_mode=mode)
+    E['e'] = eng.Engine(w, b, compute_mode=mode, num_ctas=int(os.environ.get('FFN_CTAS', '0')))
     return E['e'].info()
   if 'e' not in E:
     return

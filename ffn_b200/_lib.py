@@ -31,7 +31,7 @@ EXPORTS = [
     'ffn_canvas_set_mask', 'ffn_canvas_segment_at', 'ffn_canvas_segment_all',
     'ffn_canvas_update_at', 'ffn_canvas_init_seed', 'ffn_canvas_read', 'ffn_canvas_write',
     'ffn_canvas_policy_state_size', 'ffn_canvas_policy_state_get', 'ffn_canvas_policy_state_set',
-    'ffn_canvas_set_resume', 'ffn_canvas_trace', 'ffn_canvas_set_max_id', 'ffn_canvas_get_counters', 'ffn_canvas_device_ptr',
+    'ffn_canvas_set_resume', 'ffn_canvas_trace', 'ffn_canvas_seed_peaks', 'ffn_canvas_set_max_id', 'ffn_canvas_get_counters', 'ffn_canvas_device_ptr',
     'ffn_canvas_add_id_offset', 'ffn_selftest_umma',
 ]
 
@@ -122,6 +122,7 @@ def load() -> C.CDLL:
   lib.ffn_canvas_policy_state_set.argtypes = [p, p, C.c_int64, p, C.c_int64, i32p]
   lib.ffn_canvas_set_resume.argtypes = [p, C.c_int64, i32p, i32p]
   lib.ffn_canvas_trace.argtypes = [p, C.c_int64, p, C.POINTER(C.c_int64)]
+  lib.ffn_canvas_seed_peaks.argtypes = [p, C.POINTER(C.c_float), p, p, C.c_int64, C.POINTER(C.c_int64)]
   lib.ffn_canvas_set_max_id.argtypes = [p, C.c_int64]
   lib.ffn_canvas_get_counters.argtypes = [p, C.POINTER(Counters)]
   lib.ffn_canvas_device_ptr.argtypes = [p, C.c_int, C.POINTER(p), C.POINTER(C.c_int64)]

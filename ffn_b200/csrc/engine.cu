@@ -10,6 +10,7 @@
 
 #include "device_types.cuh"
 #include "flood_kernel.cuh"
+#include "seed_kernels.cuh"
 #include "selftest.cuh"
 
 namespace {
@@ -861,6 +862,69 @@ int ffn_canvas_trace(FfnCanvas* c, int64_t capacity, int32_t* events_out, int64_
   }
   c->h_state.n_trace = 0;
   return push_state(c);
+}
+
+int ffn_canvas_seed_peaks(FfnCanvas* c, const float voxel_size_zyx[3], const double* noise, int32_t* coords_out,
+                          int64_t cap, int64_t* n_out) {
+  if (!c || !voxel_size_zyx || !coords_out || !n_out || cap < 1) return fail("bad argument");
+  FfnEngine* e = c->eng;
+  if (set_device(e)) return 1;
+  const CanvasDev& cv = c->cv;
+  const size_t n = c->nvox;
+  const int blocks = e->sm_count * 16;
+  float *a = nullptr, *b = nullptr, *d = nullptr;
+  double *d_noise = nullptr, *zbuf = nullptr, *d_w = nullptr;
+  int *vbuf = nullptr, *d_coords = nullptr;
+  unsigned long long* d_cnt = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(a); cudaFree(b); cudaFree(d); cudaFree(d_w); cudaFree(d_noise); cudaFree(zbuf); cudaFree(vbuf);
+    cudaFree(d_coords); cudaFree(d_cnt);
+  };
+  const int maxdim = std::max(cv.sz, cv.sy);
+  const size_t maxlines = std::max((size_t)cv.sy * cv.sx, (size_t)cv.sz * cv.sx);
+  // adaptive threshold: gaussian sigma = 49/6, truncate 4 (seed.py:160-163)
+  const double sigma = 49.0 / 6.0;
+  const int radius = (int)(4.0 * sigma + 0.5);
+  std::vector<double> w(radius + 1);                 // w[0] = centre tap
+  {
+    double sum = 0;
+    for (int k = -radius; k <= radius; ++k) sum += std::exp(-0.5 / (sigma * sigma) * k * k);
+    for (int k = 0; k <= radius; ++k) w[k] = std::exp(-0.5 / (sigma * sigma) * k * k) / sum;
+  }
+  int rc = 0;
+  if (dev_alloc(&a, n, false) || dev_alloc(&b, n, false) || dev_alloc(&d, n, false) || dev_alloc(&d_w, w.size(), false) ||
+      dev_alloc(&vbuf, (size_t)maxdim * maxlines, false) || dev_alloc(&zbuf, 2 * (size_t)maxdim * maxlines, false) ||
+      dev_alloc(&d_coords, (size_t)cap * 3, false) || dev_alloc(&d_cnt, 2) || (noise && dev_alloc(&d_noise, n, false))) {
+    cleanup();
+    return 1;
+  }
+  cudaStream_t st = cudaStreamPerThread;
+  bool ok = cudaMemcpyAsync(d_w, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, st) == cudaSuccess;
+  if (noise) ok = ok && cudaMemcpyAsync(d_noise, noise, n * sizeof(double), cudaMemcpyHostToDevice, st) == cudaSuccess;
+  seedk::sobel_mag<<<blocks, 256, 0, st>>>(cv.image, cv.image_is_u8, cv.mean, cv.stddev, a, cv.sz, cv.sy, cv.sx);
+  seedk::gauss_pass<<<blocks, 256, 0, st>>>(a, b, d_w, radius, 0, cv.sz, cv.sy, cv.sx);
+  seedk::gauss_pass<<<blocks, 256, 0, st>>>(b, d, d_w, radius, 1, cv.sz, cv.sy, cv.sx);
+  seedk::gauss_pass<<<blocks, 256, 0, st>>>(d, b, d_w, radius, 2, cv.sz, cv.sy, cv.sx);
+  seedk::edges_kernel<<<blocks, 256, 0, st>>>(a, b, cv.mask, cv.seed_mask, d, n, d_cnt);
+  seedk::edt_x<<<blocks, 128, 0, st>>>(d, cv.sz, cv.sy, cv.sx, voxel_size_zyx[2]);
+  seedk::edt_line<<<blocks, 128, 0, st>>>(d, 1, cv.sz, cv.sy, cv.sx, voxel_size_zyx[1], vbuf, zbuf);
+  seedk::edt_line<<<blocks, 128, 0, st>>>(d, 0, cv.sz, cv.sy, cv.sx, voxel_size_zyx[0], vbuf, zbuf);
+  seedk::finish_dt<<<blocks, 256, 0, st>>>(d, cv.seg, cv.mask, cv.seed_mask, n);
+  seedk::peaks_kernel<<<blocks, 256, 0, st>>>(d, d_noise, cv.sz, cv.sy, cv.sx, 3, d_coords, (unsigned long long)cap, d_cnt + 1);
+  unsigned long long counts[2] = {0, 0};
+  ok = ok && cudaGetLastError() == cudaSuccess;
+  ok = ok && cudaMemcpyAsync(counts, d_cnt, sizeof(counts), cudaMemcpyDeviceToHost, st) == cudaSuccess;
+  ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+  if (!ok) {
+    rc = fail(std::string("seed policy kernels failed: ") + cudaGetErrorString(cudaGetLastError()));
+  } else {
+    *n_out = counts[0] == 0 ? 0 : (int64_t)counts[1];   // everything is an edge: no seeds (seed.py:176-177)
+    const int64_t m = std::min<int64_t>(*n_out, cap);
+    if (m > 0 && cudaMemcpy(coords_out, d_coords, (size_t)m * 3 * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = fail("seed coordinate copy failed");
+  }
+  cleanup();
+  return rc;
 }
 
 int ffn_canvas_set_max_id(FfnCanvas* c, int64_t max_id) {

@@ -241,6 +241,27 @@ class DeviceCanvas:
     _lib.check(self._lib.ffn_canvas_trace(self._h, 0, _lib.ptr(buf), C.byref(n)))
     return buf[:min(int(n.value), buf.shape[0])]
 
+  def seed_peaks(self, voxel_size_zyx=(1, 1, 1), noise: Optional[np.ndarray] = None, cap: Optional[int] = None):
+    """Device PolicyPeaks: returns the peak coordinates [N, 3] (z, y, x), lexicographically sorted."""
+    cap = int(cap or max(self.shape[0] * self.shape[1] * self.shape[2] // 64, 4096))
+    vs = (C.c_float * 3)(*[float(v) for v in voxel_size_zyx])
+    while True:
+      out = np.empty((cap, 3), dtype=np.int32)
+      n = C.c_int64(0)
+      nz = None
+      if noise is not None:
+        nz = np.ascontiguousarray(noise, dtype=np.float64)
+        if nz.shape != self.shape:
+          raise ValueError('noise shape mismatch')
+      _lib.check(self._lib.ffn_canvas_seed_peaks(self._h, vs, _lib.ptr(nz) if nz is not None else None, _lib.ptr(out),
+                                                  cap, C.byref(n)))
+      if n.value <= cap:
+        break
+      cap = int(n.value)
+    coords = out[:n.value]
+    order = np.lexsort((coords[:, 2], coords[:, 1], coords[:, 0]))
+    return coords[order]
+
   def set_max_id(self, max_id: int):
     _lib.check(self._lib.ffn_canvas_set_max_id(self._h, int(max_id)))
 

@@ -106,6 +106,14 @@ class PolicyPeaks(BaseSeedPolicy):
   """Sobel edges -> adaptive threshold -> distance transform -> local maxima (seed.py:142-199)."""
 
   def init_coords(self):
+    dev = getattr(self.canvas, '_dev', None)
+    if dev is not None:
+      # device path: the canvas' image / segmentation / masks are already resident in HBM
+      rng = np.random.RandomState(seed=42)               # seed.py:133-139 tie-break noise
+      noise = rng.rand(*self.canvas.shape)
+      with self.canvas._exec_client.engine_lock:         # pylint: disable=protected-access
+        self.coords = dev.seed_peaks(self.canvas.voxel_size_zyx, noise).astype(np.int64).reshape(-1, 3)
+      return
     image = np.asarray(self.canvas.image).astype(np.float32)
     edges = ndimage.generic_gradient_magnitude(image, ndimage.sobel)
     sigma = 49.0 / 6.0

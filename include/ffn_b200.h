@@ -193,6 +193,13 @@ int ffn_canvas_set_resume(FfnCanvas* canvas, int64_t iters, const int32_t min_po
  * fetch: rows of (type, z, y, x), type 1 push, 2 pop valid, 3 pop invalid, 4 pop below threshold,
  * 5 pop already done, 6 FoV step, 7 seed invalid.  *n_events = events produced (may exceed capacity). */
 int ffn_canvas_trace(FfnCanvas* canvas, int64_t capacity, int32_t* events_out, int64_t* n_events);
+/* PolicyPeaks on the device (ffn/inference/seed.py:142-199): Sobel magnitude -> gaussian(sigma 49/6)
+ * adaptive threshold -> exact Euclidean distance transform (anisotropy = voxel size) -> local maxima
+ * (min_distance 3) with the tie-break noise `noise` (host float64 [Z,Y,X] = RandomState(42).rand, or
+ * NULL).  Uses the canvas' resident image, segmentation and masks.  coords_out receives up to `cap`
+ * (z, y, x) triples in arbitrary order (sort them for the policy); *n_out = number of peaks found. */
+int ffn_canvas_seed_peaks(FfnCanvas* canvas, const float voxel_size_zyx[3], const double* noise,
+                          int32_t* coords_out, int64_t cap, int64_t* n_out);
 /* Canvas._max_id / counters carried across calls (checkpoint restore, init segmentation). */
 int ffn_canvas_set_max_id(FfnCanvas* canvas, int64_t max_id);
 int ffn_canvas_get_counters(FfnCanvas* canvas, FfnCounters* out);

@@ -409,3 +409,53 @@ def test_concurrent_canvases_batch_size_two(golden_dir, g64):
     np.testing.assert_array_equal(got[i][1], want[i][1])
     assert {k: (v.start_zyx, v.iters) for k, v in got[i][2].items()} == \
         {k: (v.start_zyx, v.iters) for k, v in want[i][2].items()}
+
+
+class _HostCanvas:
+  """Just enough canvas for the host (scipy) PolicyPeaks path: no `_dev`."""
+
+  def __init__(self, image, segmentation, restrictor, voxel_size_zyx, margin):
+    self.image, self.segmentation, self.restrictor = image, segmentation, restrictor
+    self.voxel_size_zyx, self.margin, self.shape = voxel_size_zyx, margin, image.shape
+
+
+@pytest.mark.parametrize('voxel', [(1, 1, 1), (33, 8, 8)])
+def test_device_policy_peaks_matches_host_policy(golden_dir, voxel):
+  """PolicyPeaks on the device (Sobel, adaptive threshold, exact EDT, peak picking) produces the seed
+  list of the host scipy restatement: same coordinates in the same order, with masks and an
+  already-segmented region excluded (ffn/inference/seed.py:142-199)."""
+  from ffn.inference import executor, inference, inference_pb2, inference_utils, movement, seed as seed_mod
+  from ffn.training.models import convstack_3d
+  from ffn_b200 import synthetic
+  model = convstack_3d.ConvStack3DFFNModel(fov_size=[33, 33, 33], deltas=[8, 8, 8], depth=12)
+  exe = executor.B200Executor(executor.ExecutorInterface(), model, inference_utils.Counters(),
+                              checkpoint_path=os.path.join(golden_dir, 'fib25_convstack.npz'))
+  opts = inference_pb2.InferenceOptions(init_activation=0.95, pad_value=0.05, move_threshold=0.9,
+                                        segment_threshold=0.6, min_segment_size=1000)
+  shape = (72, 90, 101)
+  vol = synthetic.voronoi_phantom(shape, seed=5, cell_volume=12000.0)
+  rng = np.random.RandomState(3)
+  mask = np.zeros(shape, dtype=bool)
+  mask[:, :12, :] = True
+  seed_mask = rng.rand(*shape) > 0.995
+  restrictor = movement.MovementRestrictor(mask=mask, seed_mask=seed_mask)
+  cv = inference.Canvas(model.info, exe.get_client(inference_utils.Counters()), vol, opts, restrictor=restrictor,
+                        voxel_size_zyx=voxel, image_mean=128, image_stddev=33)
+  seg = np.zeros(shape, dtype=np.int32)
+  seg[40:60, 50:80, 20:70] = 7
+  cv.segmentation[...] = seg
+  dev_policy = seed_mod.PolicyPeaks(cv)
+  got = dev_policy.remaining()
+
+  image = (vol.astype(np.float32) - np.float32(128)) / np.float32(33)
+  host = _HostCanvas(image, seg, restrictor, voxel, cv.margin)
+  want = seed_mod.PolicyPeaks(host).remaining()
+  assert want.shape[0] > 20
+  a = set(map(tuple, got.tolist()))
+  b = set(map(tuple, want.tolist()))
+  # float32 rounding of the threshold image may flip a borderline edge voxel; allow a sliver
+  assert len(a & b) >= 0.98 * len(a | b), (len(a), len(b), len(a & b))
+  if a == b:
+    np.testing.assert_array_equal(got, want)
+  assert not any(mask[z, y, x] or seed_mask[z, y, x] or seg[z, y, x] > 0 for z, y, x in got)
+  exe.close()

@@ -20,27 +20,22 @@ G = os.path.join(REPO, 'tests', 'golden')
 W, B = tf_checkpoint.load_convstack_npz(os.path.join(G, 'fib25_convstack.npz'))
 
 
-def peaks_seeds(vol, voxel=(1, 1, 1), mean=128.0, std=33.0):
-  from ffn.inference import seed as seed_mod
-
-  class _C:
-    pass
-  c = _C()
-  c.shape = vol.shape
-  c.margin = np.array([16, 16, 16])
-  c.image = (vol.astype(np.float32) - mean) / std
-  c.segmentation = np.zeros(vol.shape, np.int32)
-  c.restrictor = None
-  c.voxel_size_zyx = voxel
+def device_peaks(cv, voxel=(1, 1, 1), margin=(16, 16, 16)):
+  """PolicyPeaks on the device + the border filter of BaseSeedPolicy (seed.py:81-88)."""
   t0 = time.time()
-  coords = seed_mod.PolicyPeaks(c).remaining()
-  return coords, time.time() - t0
+  noise = np.random.RandomState(seed=42).rand(*cv.shape)
+  t_noise = time.time() - t0
+  coords = cv.seed_peaks(voxel, noise)
+  m = np.asarray(margin)[None]
+  keep = np.all((coords - m >= 0) & (coords + m < np.asarray(cv.shape)[None]), axis=1)
+  return np.ascontiguousarray(coords[keep], dtype=np.int32), time.time() - t0, t_noise
 
 
-def full_canvas(engine, vol, seeds, label, extra=None):
+def full_canvas(engine, vol, label, extra=None, voxel=(1, 1, 1), margin=(16, 16, 16)):
   t0 = time.time()
   cv = eng.DeviceCanvas(engine, vol, eng.make_options(), 128.0, 33.0)
   t_up = time.time() - t0
+  seeds, tseed, tnoise = device_peaks(cv, voxel, margin)
   t0 = time.time()
   origins, overlaps, ctr = cv.segment_all(seeds, overlaps_cap=max(64 * len(seeds), 1 << 16))
   wall = time.time() - t0
@@ -50,8 +45,10 @@ def full_canvas(engine, vol, seeds, label, extra=None):
          'segments': int(ctr.segments), 'segment_at_calls': int(ctr.segment_at_calls),
          'voxels_segmented': int(ctr.voxels_segmented), 'filled_fraction': float((seg > 0).mean()),
          'device_seconds': ctr.device_seconds, 'segment_all_wall_s': wall, 'upload_s': t_up,
+         'seed_policy_s': tseed, 'seed_policy_noise_s': tnoise,
          'steps_per_s_device': ctr.inference_calls / max(ctr.device_seconds, 1e-9),
          'steps_per_s_wall': ctr.inference_calls / wall, 'voxels_per_s_wall': ctr.voxels_segmented / wall,
+         'voxels_per_s_incl_seed_policy': ctr.voxels_segmented / (wall + tseed + t_up),
          'kernel_launches': int(ctr.kernel_launches), 'origins_carry_own_id': bool(ok)}
   if extra:
     out.update(extra)
@@ -122,10 +119,8 @@ def main():
     e = eng.Engine(W, B, (33, 33, 33), (8, 8, 8), device=local)
     n = int(512 * scale)
     t0 = time.time(); vol = voronoi_phantom((n, n, n), 2); tg = time.time() - t0
-    seeds, tseed = peaks_seeds(vol)
-    out, _, _ = full_canvas(e, vol, seeds, '2: full-canvas multi-seed, synthetic %d^3, PolicyPeaks seeds' % n,
-                            {'seed_policy_s': tseed, 'volume_gen_s': tg})
-    out['voxels_per_s_incl_seed_policy'] = out['voxels_segmented'] / (out['segment_all_wall_s'] + tseed)
+    out, _, _ = full_canvas(e, vol, '2: full-canvas multi-seed, synthetic %d^3, device PolicyPeaks seeds' % n,
+                            {'volume_gen_s': tg})
     print(json.dumps(out), flush=True)
     e.close()
 
@@ -134,13 +129,8 @@ def main():
     e = eng.Engine(w9, b9, (17, 33, 33), (4, 8, 8), device=local)
     shape = (int(256 * scale), int(512 * scale), int(512 * scale))
     vol = voronoi_phantom(shape, 4, sigma=(0.5, 1.0, 1.0), voxel_size_zyx=(2.0, 1.0, 1.0))
-    class _C: pass
-    c = _C(); c.shape = vol.shape; c.margin = np.array([8, 16, 16]); c.image = (vol.astype(np.float32) - 128) / 33
-    c.segmentation = np.zeros(vol.shape, np.int32); c.restrictor = None; c.voxel_size_zyx = (2, 1, 1)
-    from ffn.inference import seed as seed_mod
-    t0 = time.time(); seeds = seed_mod.PolicyPeaks(c).remaining(); tseed = time.time() - t0
-    out, _, _ = full_canvas(e, vol, seeds, '4: anisotropic fov (17,33,33) deltas (4,8,8) depth 9 (first 9 FIB-25 modules), synthetic %s' % (shape,),
-                            {'seed_policy_s': tseed})
+    out, _, _ = full_canvas(e, vol, '4: anisotropic fov (17,33,33) deltas (4,8,8) depth 9 (first 9 FIB-25 modules), synthetic %s' % (shape,),
+                            voxel=(2, 1, 1), margin=(8, 16, 16))
     print(json.dumps(out), flush=True)
     e.close()
 
@@ -161,8 +151,7 @@ def main():
     for k in mine:
       lo, sz = boxes[k]
       vol = voronoi_phantom(sz, 3 * 100 + k)      # each slab is an independent synthetic volume of the slab's shape
-      seeds, tseed = peaks_seeds(vol)
-      out, seg, max_id = full_canvas(e, vol, seeds, '3: slab %d of 8 (%s)' % (k, 'x'.join(map(str, sz))), {'seed_policy_s': tseed})
+      out, seg, max_id = full_canvas(e, vol, '3: slab %d of 8 (%s)' % (k, 'x'.join(map(str, sz))))
       results.append(out)
       seg_t = torch.from_numpy(seg).cuda()
       seg_t[seg_t > 0] += total_max

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libffn_b200.so')
+# FFN_B200_LIB: load an experiment build of the same sources (tools/build_variants.py) instead
+LIB_PATH = os.environ.get('FFN_B200_LIB') or os.path.join(HERE, 'libffn_b200.so')
 
 COMPUTE_FP16_TC = 0
 COMPUTE_FP32 = 1

@@ -25,13 +25,16 @@ def up_to_date():
   return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-  if not force and up_to_date():
+def build(force=False, verbose=False, defines=(), out=None):
+  """Builds the engine library.  `defines` / `out` produce an experiment variant next to it
+  (tools/build_variants.py); the product is always the default build."""
+  out = out or OUT
+  if out == OUT and not force and up_to_date():
     return OUT
   cmd = [
       nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--default-stream', 'per-thread',
-      '-Xcompiler', '-fPIC', '-shared', '-o', OUT, SRC, '-lcudart',
-  ]
+      '-Xcompiler', '-fPIC', '-shared', '-o', out, SRC, '-lcudart',
+  ] + ['-D%s' % d for d in defines]
   if verbose:
     cmd.insert(1, '-Xptxas')
     cmd.insert(2, '-v')
@@ -40,7 +43,7 @@ def build(force=False, verbose=False):
     raise RuntimeError('nvcc failed:\n%s\n%s' % (res.stdout, res.stderr))
   if verbose:
     sys.stderr.write(res.stderr)
-  return OUT
+  return out
 
 
 if __name__ == '__main__':

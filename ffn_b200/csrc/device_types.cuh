@@ -12,7 +12,10 @@ namespace ffn {
 constexpr int kThreads = 320;     // warps 0-7: epilogue (2 channel halves x 4 TMEM lane quarters); warp 8: TMA producer; warp 9: UMMA issuer
 constexpr int kLoadWarp = 8;
 constexpr int kMmaWarp = 9;
-constexpr int kActStages = 2;     // shared-memory ring of per-tile activation operands
+#ifndef FFN_ACT_STAGES
+#define FFN_ACT_STAGES 2
+#endif
+constexpr int kActStages = FFN_ACT_STAGES;     // shared-memory ring of per-tile activation operands
 constexpr int kAccSlots = 3;      // TMEM ring of per-tile accumulators
 constexpr int kTileM = 128;       // UMMA M: accumulator rows per tensor-core tile
 constexpr int kTileOut = 126;     // FoV rows a tile OUTPUTS: the dx = -1/+1 partial sums live one row up/down, so

@@ -87,19 +87,60 @@ __device__ __forceinline__ void mbar_wait(const Ctx& c, uint64_t* bar, uint32_t 
 }
 
 // Grid-wide barrier (all CTAs are co-resident: cooperative launch, one CTA per SM).
+// Arrival: one red.release per CTA.  Detection: FFN_BAR_POLLERS threads (lane 0 of the first warps)
+// poll the counter with acquire loads, staggered by a fraction of the L2 round trip so that the
+// expected lag between the last arrival and its observation shrinks; the first to see the full
+// count publishes it through shared memory.
+// Critical-path sensitivity experiments (tools/build_variants.py); all zero in the product build.
+#ifndef FFN_X_LEADER_SPIN
+#define FFN_X_LEADER_SPIN 0
+#endif
+#ifndef FFN_X_CTA0_LAYER_SPIN
+#define FFN_X_CTA0_LAYER_SPIN 0
+#endif
+#ifndef FFN_X_EPI_SPIN
+#define FFN_X_EPI_SPIN 0
+#endif
+#ifndef FFN_X_BAR_SLEEP
+#define FFN_X_BAR_SLEEP 0
+#endif
+__device__ __forceinline__ void x_spin(long long cycles) {
+  if (cycles > 0) {
+    const long long t = clock64();
+    while (clock64() - t < cycles) {
+    }
+  }
+}
+#ifndef FFN_BAR_POLLERS
+#define FFN_BAR_POLLERS 1
+#endif
+#ifndef FFN_BAR_STAGGER
+#define FFN_BAR_STAGGER 400
+#endif
 __device__ __forceinline__ void grid_barrier(Ctx& c) {
   sm100::tc_fence_before();
   __syncthreads();
-  if (c.tid == 0) {
-    c.bar_target += c.G;
+  c.bar_target += c.G;
+  if (c.lane == 0 && c.warp < FFN_BAR_POLLERS) {
+    volatile int* seen = c.s_misc + 6;   // last barrier target some poller of this CTA saw complete
     const long long t0 = prof_now(c);
-    long long tw = 0;
     // release: everything this CTA wrote (ordered before by bar.sync) becomes visible gpu-wide
     // before the arrival is counted
-    sm100::red_release_add(c.p->ws.bar, 1u);
+    if (c.warp == 0) sm100::red_release_add(c.p->ws.bar, 1u);
+    if (FFN_BAR_POLLERS > 1 && c.warp > 0) {
+      const long long ts = clock64();
+      while (clock64() - ts < (long long)c.warp * (FFN_BAR_STAGGER / FFN_BAR_POLLERS)) {
+      }
+    }
+    long long tw = 0;
     unsigned spins = 0;
-    while (sm100::ld_acquire_u32(c.p->ws.bar) < c.bar_target) {
-      __nanosleep(20);   // 147 CTAs poll one L2 line: back off so the leader's loads are not starved
+    for (;;) {
+      if (FFN_BAR_POLLERS > 1 && *seen == (int)c.bar_target) break;
+      if ((int)(sm100::ld_acquire_u32(c.p->ws.bar) - c.bar_target) >= 0) {
+        if (FFN_BAR_POLLERS > 1) *seen = (int)c.bar_target;
+        break;
+      }
+      if (FFN_X_BAR_SLEEP) __nanosleep(FFN_X_BAR_SLEEP);   // every CTA polls one L2 line: back off so the leader's loads are not starved
       if ((++spins & 0xFF) == 0) {
         if (aborted(c)) break;
         const long long now = clock64();
@@ -112,8 +153,10 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
     }
     // the acquire load that observed the full count orders every later read of this CTA (after
     // the bar.sync below) behind the other CTAs' writes
-    sm100::fence_proxy_async();   // later TMA reads must see what other CTAs wrote
-    prof_add(c, 0, prof_now(c) - t0);
+    if (c.tid == 0) {
+      sm100::fence_proxy_async();   // later TMA reads must see what other CTAs wrote
+      prof_add(c, 0, prof_now(c) - t0);
+    }
   }
   __syncthreads();
   sm100::tc_fence_after();
@@ -360,13 +403,11 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
         const int r0 = (c.t_begin + j) * kTileOut;
         unsigned char* dst = act_smem + (size_t)s * stage_bytes;
         sm100::mbar_expect_tx(&c.mb_full[s], (uint32_t)(3 * nch * seg_rows * 16));
-        for (int oi = 0; oi < 3; ++oi) {
-          const int dzi = oi == 0 ? 1 : (oi == 1 ? 0 : 2);   // centre plane first
+        for (int dzi = 0; dzi < 3; ++dzi)
           for (int ch = 0; ch < nch; ++ch)
             sm100::bulk_g2s(dst + (size_t)(dzi * nch + ch) * seg_rows * 16,
                             in + ((size_t)ch * g.rows_alloc + g.guard + r0 + (dzi - 1) * g.pp - g.halo) * 8,
                             (uint32_t)seg_rows * 16, &c.mb_full[s]);
-        }
         ++c.load_cnt;
       }
       // Prefetch the next layer's weights (next step's layer 0 after the last layer) into the other
@@ -485,9 +526,11 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
         }
       }
       if (c.tid == 0) prof_add(c, 5, prof_now(c) - t0);
+      x_spin(FFN_X_EPI_SPIN);
       ++c.epi_cnt;
     }
   }
+  if (c.cta == 0) x_spin(FFN_X_CTA0_LAYER_SPIN);
   // weights: this layer's buffer has been consumed, the other one is in flight
   bit_flip(c, buf);
   bit_set(c, 8 + buf, false);
@@ -896,277 +939,383 @@ __device__ __forceinline__ uint8_t quantize_prob(float logit) {
   return (uint8_t)(k + 1);
 }
 
-// Decides the next collective action; executed by all threads of CTA 0, serial parts on thread 0.
-// Writes *job.action (read by every CTA after the following grid barrier).
-__device__ __forceinline__ void leader_decide(Ctx& c) {
-  const KParams& p = *c.p;
+// FaceMaxMovementPolicy.__next__ + Canvas.is_valid_pos + the per-step checks of segment_at
+// (inference.py:503-509) as a WARP-collective: lane i examines queue entry head + i, so a run of
+// rejected candidates costs two L2 round trips instead of two per candidate.  Exactly equivalent to the
+// sequential loop: a candidate's verdict depends only on state that pops do not modify (the done
+// lattice, the seed / label canvases, the masks), and the counters of the rejected candidates in
+// front of the first accepted one are added up from the ballot masks.
+// Returns true (all lanes) with the next position in z / y / x.
+__device__ __forceinline__ bool warp_pop(const KParams& p, CanvasState* st, bool disco, int lane, int& z, int& y,
+                                         int& x) {
   const Geom& g = p.g;
-  // Work on a shared-memory copy of the state: the serial code below is full of read-after-write
-  // on these fields, and in global memory every one of those is an L2 round trip.
-  CanvasState* st = c.s_state;
-  int* s_phase = c.s_misc + 4;
-  int* s_disco = c.s_misc + 5;
-  if (c.tid == 0) {
-    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.st);
-    unsigned long long* dst = reinterpret_cast<unsigned long long*>(st);
-#pragma unroll 8
-    for (int i = 0; i < (int)(sizeof(CanvasState) / 8); ++i) dst[i] = __ldcg(src + i);
-    *s_phase = st->phase;
-    *s_disco = (st->phase == PH_AFTER_STEP) ? (disco_active(p) ? 1 : 0) : 0;
+  const CanvasDev& cv = p.cv;
+  // inference.py:503-505: value of the object's start voxel — the same for every candidate of this call
+  const bool weak = seed_value(p, st, disco, st->start[0], st->start[1], st->start[2]) < cv.opt.move_threshold;
+  for (;;) {
+    const int head = st->q_head, n = st->q_tail - head;
+    if (n <= 0) return false;
+    const bool act = lane < n;
+    int cz = 0, cy = 0, cx = 0, cls = 0;   // 0 done, 1 below threshold, 2 invalid, 3 valid
+    bool restricted = false;
+    if (act) {
+      const int h = head + lane;
+      cz = __ldcg(cv.q_pos + 3 * h);
+      cy = __ldcg(cv.q_pos + 3 * h + 1);
+      cx = __ldcg(cv.q_pos + 3 * h + 2);
+      const unsigned stamp = __ldcg(cv.lattice + lattice_index(p, st, cz, cy, cx));
+      const bool inside = cz >= 0 && cy >= 0 && cx >= 0 && cz < cv.sz && cy < cv.sy && cx < cv.sx;
+      float v = 0.f, old = 0.f;
+      int sg = 0;
+      bool in_fov = false;
+      if (inside) {
+        const size_t i = cv_index(cv, cz, cy, cx);
+        sg = __ldcg(cv.seg + i);
+        if (cv.mask) restricted = __ldg(cv.mask + i) != 0;
+        if (st->have_cur) {
+          const int fz = cz - (st->cur[0] - g.mz), fy = cy - (st->cur[1] - g.my), fx = cx - (st->cur[2] - g.mx);
+          in_fov = fz >= 0 && fz < g.fz && fy >= 0 && fy < g.fy && fx >= 0 && fx < g.fx;
+          if (in_fov) {
+            const int row = fz * g.pp + fy * g.xp + fx;
+            v = __ldcg(p.ws.logits + row);
+            old = __ldcg(p.ws.seed_raw + row);
+          }
+        }
+        if (!in_fov) v = __ldcg(cv.seed + i);
+      }
+      if (in_fov && disco && old < 0.f && v > old) v = old;
+      const bool border = cz - g.mz < 0 || cy - g.my < 0 || cx - g.mx < 0 || cz + g.mz >= cv.sz ||
+                          cy + g.my >= cv.sy || cx + g.mx >= cv.sx;
+      if (stamp == st->epoch) {
+        cls = 0;
+      } else if (inside && v < cv.opt.move_threshold) {
+        cls = 1;
+      } else if (border || sg > 0) {
+        cls = 2;
+      } else {
+        cls = 3;
+      }
+    }
+    const unsigned full = 0xffffffffu;
+    const unsigned m_act = __ballot_sync(full, act);
+    const unsigned m_thr = __ballot_sync(full, act && cls == 1);
+    const unsigned m_inv = __ballot_sync(full, act && cls == 2);
+    const unsigned m_res = __ballot_sync(full, act && cls == 3 && !weak && restricted);
+    const unsigned m_stop = __ballot_sync(full, act && cls == 3 && (weak || !restricted));
+    const int f = m_stop ? __ffs(m_stop) - 1 : -1;
+    const unsigned before = f >= 0 ? ((1u << f) - 1u) : m_act;
+    if (lane == 0) {
+      st->ctr.skip_threshold += __popc(m_thr & before);
+      st->ctr.skip_invalid_pos += __popc(m_inv & before);
+      st->ctr.skip_restricted_pos += __popc(m_res & before);
+      st->q_head = head + (f >= 0 ? f + 1 : __popc(m_act));
+      if (f >= 0 && weak) {
+        st->ctr.seed_got_too_weak++;
+        st->weak = 1;
+      }
+    }
+    __syncwarp();
+    if (f >= 0) {
+      z = __shfl_sync(full, cz, f);
+      y = __shfl_sync(full, cy, f);
+      x = __shfl_sync(full, cx, f);
+      return !weak;
+    }
   }
-  __syncthreads();
-  const bool disco = *s_disco != 0;
-  const long long t_pol = prof_now(c);
-  if (*s_phase == PH_AFTER_STEP && p.job.mode != MODE_UPDATE_AT) policy_update(c, st, disco);   // movement.py:210-222
-  if (c.tid != 0) return;
-  prof_add(c, 12, prof_now(c) - t_pol);
+}
 
-  int action = ACT_EXIT;
-  int phase = st->phase;
+// The serial reference of warp_pop (thread 0 only): used when the event trace is recording, which
+// needs the per-candidate events in order.
+__device__ __forceinline__ bool serial_pop(const KParams& p, CanvasState* st, bool disco, int& z, int& y, int& x) {
   const CanvasDev& cv = p.cv;
   for (;;) {
-    if (phase == PH_FORCE_STEP) {   // Canvas.update_at driven from the host: one step at st->cur
+    if (!pop_next(p, st, disco, z, y, x)) return false;
+    // inference.py:503-505
+    if (seed_value(p, st, disco, st->start[0], st->start[1], st->start[2]) < cv.opt.move_threshold) {
+      st->ctr.seed_got_too_weak++;
+      st->weak = 1;
+      return false;
+    }
+    // inference.py:507-509
+    if (cv.mask && cv.mask[cv_index(cv, z, y, x)]) {
+      st->ctr.skip_restricted_pos++;
+      continue;
+    }
+    return true;
+  }
+}
+
+// One transition of the canvas state machine (thread 0 of CTA 0).  PH_POP enters here AFTER the
+// queue has been popped: `run` / z / y / x are the outcome.  Returns true when `action` is final.
+__device__ __forceinline__ bool leader_transition(Ctx& c, CanvasState* st, bool disco, int& phase, int& action,
+                                                  bool run, int z, int y, int x) {
+  const KParams& p = *c.p;
+  const Geom& g = p.g;
+  const CanvasDev& cv = p.cv;
+  if (phase == PH_FORCE_STEP) {   // Canvas.update_at driven from the host: one step at st->cur
+    st->have_cur = 1;
+    for (int k = 0; k < 3; ++k) {
+      const int m = k == 0 ? g.mz : k == 1 ? g.my : g.mx;
+      st->dirty_lo[k] = min(st->dirty_lo[k], st->cur[k] - m);
+      st->dirty_hi[k] = max(st->dirty_hi[k], st->cur[k] + m + 1);
+    }
+    phase = PH_AFTER_STEP;
+    action = ACT_STEP;
+    return true;
+  }
+  if (phase == PH_AFTER_STEP && p.job.mode == MODE_UPDATE_AT) {
+    st->ctr.inference_calls++;
+    st->have_cur = 0;
+    phase = PH_SEGMENT_DONE;
+    action = ACT_EXIT;
+    return true;
+  }
+  if (phase == PH_AFTER_STEP) {
+    // inference.py:511-514
+    for (int k = 0; k < 3; ++k) {
+      st->min_pos[k] = min(st->min_pos[k], st->cur[k]);
+      st->max_pos[k] = max(st->max_pos[k], st->cur[k]);
+    }
+    st->iters++;
+    st->ctr.inference_calls++;
+    phase = PH_POP;
+    return false;
+  }
+  if (phase == PH_START_SEGMENT) {
+    st->ctr.segment_at_calls++;
+    st->seg_t0 = sm100::globaltimer_ns();
+    if (st->reset_seed) {
+      phase = PH_AFTER_CLEAR;
+      action = ACT_CLEAR;
+      return true;
+    }
+    phase = PH_POP;
+    return false;
+  }
+  if (phase == PH_AFTER_CLEAR) {
+    // init_seed (inference.py:443-450) + reset_state (:291-310) + first queue item (:492-496)
+    cv.seed[cv_index(cv, st->start[0], st->start[1], st->start[2])] = cv.opt.init_activation;
+    for (int k = 0; k < 3; ++k) {
+      st->dirty_lo[k] = st->start[k];
+      st->dirty_hi[k] = st->start[k] + 1;
+      st->min_pos[k] = st->max_pos[k] = st->start[k];
+    }
+    st->epoch++;
+    st->q_head = st->q_tail = 0;
+    st->iters = 0;
+    st->have_cur = 0;
+    st->weak = 0;
+    push_move(p, st, (float)(cv.opt.policy_score_threshold * 2.0), st->start[0], st->start[1], st->start[2]);
+    phase = PH_POP;
+    return false;
+  }
+  if (phase == PH_POP) {
+    if (p.job.step_budget > 0 && st->ctr.inference_calls >= p.job.step_budget) {
+      action = ACT_EXIT;   // pause: host relaunches with a fresh budget
+      st->have_cur = 0;    // by then every paste has landed in the canvas
+      return true;
+    }
+    if (run) {
+      st->cur[0] = z;
+      st->cur[1] = y;
+      st->cur[2] = x;
       st->have_cur = 1;
+      trace_event(p, st, EV_STEP, z, y, x);
       for (int k = 0; k < 3; ++k) {
-        const int m = k == 0 ? g.mz : k == 1 ? g.my : g.mx;
-        st->dirty_lo[k] = min(st->dirty_lo[k], st->cur[k] - m);
-        st->dirty_hi[k] = max(st->dirty_hi[k], st->cur[k] + m + 1);
+        st->dirty_lo[k] = min(st->dirty_lo[k], st->cur[k] - (k == 0 ? g.mz : k == 1 ? g.my : g.mx));
+        st->dirty_hi[k] = max(st->dirty_hi[k], st->cur[k] + (k == 0 ? g.mz : k == 1 ? g.my : g.mx) + 1);
       }
       phase = PH_AFTER_STEP;
       action = ACT_STEP;
-      break;
+      return true;
     }
-    if (phase == PH_AFTER_STEP && p.job.mode == MODE_UPDATE_AT) {
-      st->ctr.inference_calls++;
-      st->have_cur = 0;
+    // object finished
+    if (!st->seg_all) {
       phase = PH_SEGMENT_DONE;
       action = ACT_EXIT;
-      break;
+      return true;
     }
-    if (phase == PH_AFTER_STEP) {
-      // inference.py:511-514
-      for (int k = 0; k < 3; ++k) {
-        st->min_pos[k] = min(st->min_pos[k], st->cur[k]);
-        st->max_pos[k] = max(st->max_pos[k], st->cur[k]);
-      }
-      st->iters++;
-      st->ctr.inference_calls++;
-      phase = PH_POP;
-      continue;
-    }
-    if (phase == PH_START_SEGMENT) {
-      st->ctr.segment_at_calls++;
-      st->seg_t0 = sm100::globaltimer_ns();
-      if (st->reset_seed) {
-        phase = PH_AFTER_CLEAR;
-        action = ACT_CLEAR;
-        break;
-      }
-      phase = PH_POP;
-      continue;
-    }
-    if (phase == PH_AFTER_CLEAR) {
-      // init_seed (inference.py:443-450) + reset_state (:291-310) + first queue item (:492-496)
-      cv.seed[cv_index(cv, st->start[0], st->start[1], st->start[2])] = cv.opt.init_activation;
-      for (int k = 0; k < 3; ++k) {
-        st->dirty_lo[k] = st->start[k];
-        st->dirty_hi[k] = st->start[k] + 1;
-        st->min_pos[k] = st->max_pos[k] = st->start[k];
-      }
-      st->epoch++;
-      st->q_head = st->q_tail = 0;
-      st->iters = 0;
-      st->have_cur = 0;
-      st->weak = 0;
-      push_move(p, st, (float)(cv.opt.policy_score_threshold * 2.0), st->start[0], st->start[1], st->start[2]);
-      phase = PH_POP;
-      continue;
-    }
-    if (phase == PH_POP) {
-      if (p.job.step_budget > 0 && st->ctr.inference_calls >= p.job.step_budget) {
-        action = ACT_EXIT;   // pause: host relaunches with a fresh budget
-        st->have_cur = 0;    // by then every paste has landed in the canvas
-        break;
-      }
-      bool run = false;
-      int z = 0, y = 0, x = 0;
-      const long long t_pop = prof_now(c);
-      for (;;) {
-        if (!pop_next(p, st, disco, z, y, x)) break;
-        // inference.py:503-505
-        if (seed_value(p, st, disco, st->start[0], st->start[1], st->start[2]) < cv.opt.move_threshold) {
-          st->ctr.seed_got_too_weak++;
-          st->weak = 1;
-          break;
-        }
-        // inference.py:507-509
-        if (cv.mask && cv.mask[cv_index(cv, z, y, x)]) {
-          st->ctr.skip_restricted_pos++;
-          continue;
-        }
-        run = true;
-        break;
-      }
-      prof_add(c, 13, prof_now(c) - t_pop);
-      if (run) {
-        st->cur[0] = z;
-        st->cur[1] = y;
-        st->cur[2] = x;
-        st->have_cur = 1;
-        trace_event(p, st, EV_STEP, z, y, x);
-        for (int k = 0; k < 3; ++k) {
-          st->dirty_lo[k] = min(st->dirty_lo[k], st->cur[k] - (k == 0 ? g.mz : k == 1 ? g.my : g.mx));
-          st->dirty_hi[k] = max(st->dirty_hi[k], st->cur[k] + (k == 0 ? g.mz : k == 1 ? g.my : g.mx) + 1);
-        }
-        phase = PH_AFTER_STEP;
-        action = ACT_STEP;
-        break;
-      }
-      // object finished
-      if (!st->seg_all) {
-        phase = PH_SEGMENT_DONE;
-        action = ACT_EXIT;
-        break;
-      }
-      // segment_all post-processing (inference.py:593-620)
-      const size_t si = cv_index(cv, st->start[0], st->start[1], st->start[2]);
-      if (st->iters <= 0) {
-        st->ctr.invalid_other++;
-        phase = PH_NEXT_SEED;
-        continue;
-      }
-      if (seed_value(p, st, disco, st->start[0], st->start[1], st->start[2]) < cv.opt.move_threshold) {
-        if (cv.seg[si] == 0) cv.seg[si] = -1;
-        st->ctr.invalid_weak++;
-        phase = PH_NEXT_SEED;
-        continue;
-      }
-      const int half[3] = {g.fz / 2, g.fy / 2, g.fx / 2};
-      const int shp[3] = {cv.sz, cv.sy, cv.sx};
-      for (int k = 0; k < 3; ++k) {
-        st->box_lo[k] = max(st->min_pos[k] - half[k], 0);
-        st->box_hi[k] = min(st->max_pos[k] + half[k] + 1, shp[k]);
-      }
-      st->cnt_raw = st->cnt_actual = 0ull;
-      st->n_touched = 0;
-      phase = PH_AFTER_COUNT;
-      action = ACT_COUNT;
-      break;
-    }
-    if (phase == PH_AFTER_COUNT) {
-      const size_t si = cv_index(cv, st->start[0], st->start[1], st->start[2]);
-      const long long raw = (long long)st->cnt_raw, actual = (long long)st->cnt_actual;
-      if (actual < (long long)cv.opt.min_segment_size) {   // inference.py:639-646
-        if (cv.seg[si] == 0) cv.seg[si] = -1;
-        st->ctr.invalid_small++;
-        for (int i = 0; i < st->n_touched; ++i) p.job.ovl_count[p.job.ovl_touched[i]] = 0;
-        st->n_touched = 0;
-        phase = PH_NEXT_SEED;
-        continue;
-      }
-      st->ctr.voxels_segmented += actual;
-      st->ctr.voxels_overlapping += raw - actual;
-      st->max_id++;
-      st->cur_sid = st->max_id;
-      st->ctr.max_id = st->max_id;
-      st->ctr.segments++;
-      for (int i = 0; i < st->n_touched; ++i) {       // Canvas.overlaps (inference.py:668)
-        const int id = p.job.ovl_touched[i];
-        if (st->n_overlaps < p.job.overlaps_cap) {
-          FfnOverlap o;
-          o.id = st->cur_sid;
-          o.other_id = id;
-          o.count = p.job.ovl_count[id];
-          p.job.overlaps[st->n_overlaps] = o;
-        } else {
-          st->overflow |= 2;
-        }
-        st->n_overlaps++;
-        p.job.ovl_count[id] = 0;
-      }
-      st->n_touched = 0;
-      if (st->n_origins < p.job.origins_cap) {        // Canvas.origins (inference.py:671)
-        FfnOrigin o;
-        o.id = st->cur_sid;
-        o.start_zyx[0] = st->start[0];
-        o.start_zyx[1] = st->start[1];
-        o.start_zyx[2] = st->start[2];
-        o.iters = st->iters;
-        o.walltime_sec = (double)(sm100::globaltimer_ns() - st->seg_t0) * 1e-9;
-        p.job.origins[st->n_origins] = o;
-      } else {
-        st->overflow |= 4;
-      }
-      st->n_origins++;
-      phase = PH_AFTER_WRITE;
-      action = ACT_WRITE;
-      break;
-    }
-    if (phase == PH_AFTER_WRITE) {
+    // segment_all post-processing (inference.py:593-620)
+    const size_t si = cv_index(cv, st->start[0], st->start[1], st->start[2]);
+    if (st->iters <= 0) {
+      st->ctr.invalid_other++;
       phase = PH_NEXT_SEED;
-      continue;
+      return false;
     }
-    if (phase == PH_NEXT_SEED) {
-      bool found = false;
-      while (st->seed_idx < p.job.n_seeds) {
-        const long long k = st->seed_idx++;
-        const int z = p.job.seeds[3 * k], y = p.job.seeds[3 * k + 1], x = p.job.seeds[3 * k + 2];
-        // seed.py:81-88 border filter (BaseSeedPolicy.__next__)
-        if (z - g.mz < 0 || y - g.my < 0 || x - g.mx < 0 || z + g.mz >= cv.sz || y + g.my >= cv.sy ||
-            x + g.mx >= cv.sx)
-          continue;
-        st->ctr.seeds_examined++;
-        st->have_cur = 0;
-        if (!is_valid_pos(p, st, false, z, y, x, true)) continue;       // inference.py:562-568
-        const size_t i = cv_index(cv, z, y, x);
-        if (cv.mask && cv.mask[i]) continue;
-        if (cv.seed_mask && cv.seed_mask[i]) continue;
-        // inference.py:573-581 (numpy slice semantics: negative start would wrap; positions here
-        // are >= margin >= min_boundary_dist is NOT guaranteed, so clamp like a slice that is
-        // empty-safe: the reference would index from the end — unreachable for mbd <= margin)
-        bool close = false;
-        const int* mbd = cv.opt.min_boundary_dist_zyx;
-        for (int zz = max(z - mbd[0], 0); zz < min(z + mbd[0] + 1, cv.sz) && !close; ++zz)
-          for (int yy = max(y - mbd[1], 0); yy < min(y + mbd[1] + 1, cv.sy) && !close; ++yy)
-            for (int xx = max(x - mbd[2], 0); xx < min(x + mbd[2] + 1, cv.sx); ++xx)
-              if (__ldcg(cv.seg + cv_index(cv, zz, yy, xx)) > 0) {
-                close = true;
-                break;
-              }
-        if (close) {
-          cv.seg[i] = -1;
-          continue;
-        }
-        st->start[0] = z;
-        st->start[1] = y;
-        st->start[2] = x;
-        st->reset_seed = 1;
-        found = true;
-        break;
-      }
-      if (!found) {
-        phase = PH_ALL_DONE;
-        action = ACT_EXIT;
-        break;
-      }
-      phase = PH_START_SEGMENT;
-      continue;
+    if (seed_value(p, st, disco, st->start[0], st->start[1], st->start[2]) < cv.opt.move_threshold) {
+      if (cv.seg[si] == 0) cv.seg[si] = -1;
+      st->ctr.invalid_weak++;
+      phase = PH_NEXT_SEED;
+      return false;
     }
-    // PH_IDLE / PH_SEGMENT_DONE / PH_ALL_DONE
-    action = ACT_EXIT;
-    break;
+    const int half[3] = {g.fz / 2, g.fy / 2, g.fx / 2};
+    const int shp[3] = {cv.sz, cv.sy, cv.sx};
+    for (int k = 0; k < 3; ++k) {
+      st->box_lo[k] = max(st->min_pos[k] - half[k], 0);
+      st->box_hi[k] = min(st->max_pos[k] + half[k] + 1, shp[k]);
+    }
+    st->cnt_raw = st->cnt_actual = 0ull;
+    st->n_touched = 0;
+    phase = PH_AFTER_COUNT;
+    action = ACT_COUNT;
+    return true;
   }
-  st->phase = phase;
-  {
-    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st);
-    unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.st);
-#pragma unroll 8
-    for (int i = 0; i < (int)(sizeof(CanvasState) / 8); ++i) dst[i] = src[i];
+  if (phase == PH_AFTER_COUNT) {
+    const size_t si = cv_index(cv, st->start[0], st->start[1], st->start[2]);
+    const long long raw = (long long)st->cnt_raw, actual = (long long)st->cnt_actual;
+    if (actual < (long long)cv.opt.min_segment_size) {   // inference.py:639-646
+      if (cv.seg[si] == 0) cv.seg[si] = -1;
+      st->ctr.invalid_small++;
+      for (int i = 0; i < st->n_touched; ++i) p.job.ovl_count[p.job.ovl_touched[i]] = 0;
+      st->n_touched = 0;
+      phase = PH_NEXT_SEED;
+      return false;
+    }
+    st->ctr.voxels_segmented += actual;
+    st->ctr.voxels_overlapping += raw - actual;
+    st->max_id++;
+    st->cur_sid = st->max_id;
+    st->ctr.max_id = st->max_id;
+    st->ctr.segments++;
+    for (int i = 0; i < st->n_touched; ++i) {       // Canvas.overlaps (inference.py:668)
+      const int id = p.job.ovl_touched[i];
+      if (st->n_overlaps < p.job.overlaps_cap) {
+        FfnOverlap o;
+        o.id = st->cur_sid;
+        o.other_id = id;
+        o.count = p.job.ovl_count[id];
+        p.job.overlaps[st->n_overlaps] = o;
+      } else {
+        st->overflow |= 2;
+      }
+      st->n_overlaps++;
+      p.job.ovl_count[id] = 0;
+    }
+    st->n_touched = 0;
+    if (st->n_origins < p.job.origins_cap) {        // Canvas.origins (inference.py:671)
+      FfnOrigin o;
+      o.id = st->cur_sid;
+      o.start_zyx[0] = st->start[0];
+      o.start_zyx[1] = st->start[1];
+      o.start_zyx[2] = st->start[2];
+      o.iters = st->iters;
+      o.walltime_sec = (double)(sm100::globaltimer_ns() - st->seg_t0) * 1e-9;
+      p.job.origins[st->n_origins] = o;
+    } else {
+      st->overflow |= 4;
+    }
+    st->n_origins++;
+    phase = PH_AFTER_WRITE;
+    action = ACT_WRITE;
+    return true;
   }
-  *p.job.action = action;
-  const long long t_f = prof_now(c);
-  __threadfence();
-  prof_add(c, 14, prof_now(c) - t_f);
+  if (phase == PH_AFTER_WRITE) {
+    phase = PH_NEXT_SEED;
+    return false;
+  }
+  if (phase == PH_NEXT_SEED) {
+    bool found = false;
+    while (st->seed_idx < p.job.n_seeds) {
+      const long long k = st->seed_idx++;
+      const int sz = p.job.seeds[3 * k], sy = p.job.seeds[3 * k + 1], sx = p.job.seeds[3 * k + 2];
+      // seed.py:81-88 border filter (BaseSeedPolicy.__next__)
+      if (sz - g.mz < 0 || sy - g.my < 0 || sx - g.mx < 0 || sz + g.mz >= cv.sz || sy + g.my >= cv.sy ||
+          sx + g.mx >= cv.sx)
+        continue;
+      st->ctr.seeds_examined++;
+      st->have_cur = 0;
+      if (!is_valid_pos(p, st, false, sz, sy, sx, true)) continue;       // inference.py:562-568
+      const size_t i = cv_index(cv, sz, sy, sx);
+      if (cv.mask && cv.mask[i]) continue;
+      if (cv.seed_mask && cv.seed_mask[i]) continue;
+      // inference.py:573-581 (numpy slice semantics: negative start would wrap; positions here
+      // are >= margin >= min_boundary_dist is NOT guaranteed, so clamp like a slice that is
+      // empty-safe: the reference would index from the end — unreachable for mbd <= margin)
+      bool close = false;
+      const int* mbd = cv.opt.min_boundary_dist_zyx;
+      for (int zz = max(sz - mbd[0], 0); zz < min(sz + mbd[0] + 1, cv.sz) && !close; ++zz)
+        for (int yy = max(sy - mbd[1], 0); yy < min(sy + mbd[1] + 1, cv.sy) && !close; ++yy)
+          for (int xx = max(sx - mbd[2], 0); xx < min(sx + mbd[2] + 1, cv.sx); ++xx)
+            if (__ldcg(cv.seg + cv_index(cv, zz, yy, xx)) > 0) {
+              close = true;
+              break;
+            }
+      if (close) {
+        cv.seg[i] = -1;
+        continue;
+      }
+      st->start[0] = sz;
+      st->start[1] = sy;
+      st->start[2] = sx;
+      st->reset_seed = 1;
+      found = true;
+      break;
+    }
+    if (!found) {
+      phase = PH_ALL_DONE;
+      action = ACT_EXIT;
+      return true;
+    }
+    phase = PH_START_SEGMENT;
+    return false;
+  }
+  // PH_IDLE / PH_SEGMENT_DONE / PH_ALL_DONE
+  action = ACT_EXIT;
+  return true;
+}
+
+// Decides the next collective action; executed by all threads of CTA 0: the movement-policy update
+// uses six warps, the state machine runs on warp 0 (serial transitions on lane 0, queue pops as a
+// warp collective).  Writes *job.action (read by every CTA after the following grid barrier).
+__device__ __forceinline__ void leader_decide(Ctx& c) {
+  const KParams& p = *c.p;
+  // Work on a shared-memory copy of the state: the serial code is full of read-after-write on these
+  // fields, and in global memory every one of those is an L2 round trip.
+  CanvasState* st = c.s_state;
+  constexpr int kStateWords = (int)(sizeof(CanvasState) / 8);
+  static_assert(kStateWords < 64, "state copy uses threads 0..63, the disco test thread 64");
+  int* s_disco = c.s_misc + 5;
+  if (c.tid < kStateWords)
+    reinterpret_cast<unsigned long long*>(st)[c.tid] = __ldcg(reinterpret_cast<const unsigned long long*>(p.st) + c.tid);
+  if (c.tid == 64) *s_disco = disco_active(p) ? 1 : 0;   // only meaningful after a step
+  __syncthreads();
+  const bool after_step = st->phase == PH_AFTER_STEP;
+  const bool disco = after_step && *s_disco != 0;
+  const long long t_pol = prof_now(c);
+  if (after_step && p.job.mode != MODE_UPDATE_AT) policy_update(c, st, disco);   // movement.py:210-222
+  if (c.warp != 0) return;
+  if (c.tid == 0) prof_add(c, 12, prof_now(c) - t_pol);
+  x_spin(FFN_X_LEADER_SPIN);
+
+  const unsigned full = 0xffffffffu;
+  int action = ACT_EXIT;
+  int phase = st->phase;
+  for (;;) {
+    bool run = false;
+    int z = 0, y = 0, x = 0;
+    if (phase == PH_POP && !(p.job.step_budget > 0 && st->ctr.inference_calls >= p.job.step_budget)) {
+      const long long t_pop = prof_now(c);
+      if (p.cv.trace) {
+        if (c.lane == 0) run = serial_pop(p, st, disco, z, y, x);
+        run = __shfl_sync(full, (int)run, 0) != 0;
+      } else {
+        run = warp_pop(p, st, disco, c.lane, z, y, x);
+      }
+      if (c.tid == 0) prof_add(c, 13, prof_now(c) - t_pop);
+    }
+    int done = 0;
+    if (c.lane == 0) done = leader_transition(c, st, disco, phase, action, run, z, y, x) ? 1 : 0;
+    __syncwarp();   // lane 0's state writes -> every lane's next reads
+    phase = __shfl_sync(full, phase, 0);
+    action = __shfl_sync(full, action, 0);
+    if (__shfl_sync(full, done, 0)) break;
+  }
+  if (c.lane == 0) st->phase = phase;
+  __syncwarp();
+  for (int i = c.lane; i < kStateWords; i += 32)
+    reinterpret_cast<unsigned long long*>(p.st)[i] = reinterpret_cast<const unsigned long long*>(st)[i];
+  if (c.lane == 0) *p.job.action = action;
+  // no fence here: the grid barrier that follows releases every store of this CTA (bar.sync + red.release)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1283,6 +1432,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   const long long t_kernel = prof_now(c);
   c.bits = 0;
   c.tmem_base = 0;
+  if (c.tid == 0) c.s_misc[6] = 0;   // grid_barrier: no target seen yet
   const bool tc = p.compute_mode == FFN_COMPUTE_FP16_TC;
 
   for (int i = c.tid; i < p.g.nconv * 32; i += kThreads) c.s_bias[i] = p.w.bias[i];

@@ -86,11 +86,6 @@ __device__ __forceinline__ void mbar_wait(const Ctx& c, uint64_t* bar, uint32_t 
   }
 }
 
-// Grid-wide barrier (all CTAs are co-resident: cooperative launch, one CTA per SM).
-// Arrival: one red.release per CTA.  Detection: FFN_BAR_POLLERS threads (lane 0 of the first warps)
-// poll the counter with acquire loads, staggered by a fraction of the L2 round trip so that the
-// expected lag between the last arrival and its observation shrinks; the first to see the full
-// count publishes it through shared memory.
 // Critical-path sensitivity experiments (tools/build_variants.py); all zero in the product build.
 #ifndef FFN_X_LEADER_SPIN
 #define FFN_X_LEADER_SPIN 0
@@ -111,54 +106,47 @@ __device__ __forceinline__ void x_spin(long long cycles) {
     }
   }
 }
-#ifndef FFN_BAR_POLLERS
-#define FFN_BAR_POLLERS 1
-#endif
-#ifndef FFN_BAR_STAGGER
-#define FFN_BAR_STAGGER 400
-#endif
+
+// Grid-wide barrier (all CTAs are co-resident: cooperative launch, one CTA per SM).
+// One red.release per CTA counts the arrival; the TMA producer thread polls the counter with acquire
+// loads and, having seen the full count, releases the other warps through a named barrier it only
+// ARRIVES at — so the first bulk copies of the next layer are issued without a CTA-wide wake-up in
+// between.  (Several staggered pollers per CTA, or a back-off sleep in the poll loop, measured slower.)
 __device__ __forceinline__ void grid_barrier(Ctx& c) {
   sm100::tc_fence_before();
   __syncthreads();
   c.bar_target += c.G;
-  if (c.lane == 0 && c.warp < FFN_BAR_POLLERS) {
-    volatile int* seen = c.s_misc + 6;   // last barrier target some poller of this CTA saw complete
-    const long long t0 = prof_now(c);
-    // release: everything this CTA wrote (ordered before by bar.sync) becomes visible gpu-wide
-    // before the arrival is counted
-    if (c.warp == 0) sm100::red_release_add(c.p->ws.bar, 1u);
-    if (FFN_BAR_POLLERS > 1 && c.warp > 0) {
-      const long long ts = clock64();
-      while (clock64() - ts < (long long)c.warp * (FFN_BAR_STAGGER / FFN_BAR_POLLERS)) {
-      }
-    }
-    long long tw = 0;
-    unsigned spins = 0;
-    for (;;) {
-      if (FFN_BAR_POLLERS > 1 && *seen == (int)c.bar_target) break;
-      if ((int)(sm100::ld_acquire_u32(c.p->ws.bar) - c.bar_target) >= 0) {
-        if (FFN_BAR_POLLERS > 1) *seen = (int)c.bar_target;
-        break;
-      }
-      if (FFN_X_BAR_SLEEP) __nanosleep(FFN_X_BAR_SLEEP);   // every CTA polls one L2 line: back off so the leader's loads are not starved
-      if ((++spins & 0xFF) == 0) {
-        if (aborted(c)) break;
-        const long long now = clock64();
-        if (tw == 0) tw = now;
-        if (now - tw > (1ll << 32)) {
-          atomicExch(c.p->ws.abort_flag, 1);
-          break;
+  if (c.warp == kLoadWarp) {
+    if (c.lane == 0) {
+      const long long t0 = prof_now(c);
+      // release: everything this CTA wrote (ordered before by bar.sync) becomes visible gpu-wide
+      // before the arrival is counted
+      sm100::red_release_add(c.p->ws.bar, 1u);
+      long long tw = 0;
+      unsigned spins = 0;
+      while ((int)(sm100::ld_acquire_u32(c.p->ws.bar) - c.bar_target) < 0) {
+        if (FFN_X_BAR_SLEEP) __nanosleep(FFN_X_BAR_SLEEP);
+        if ((++spins & 0xFF) == 0) {
+          if (aborted(c)) break;
+          const long long now = clock64();
+          if (tw == 0) tw = now;
+          if (now - tw > (1ll << 32)) {
+            atomicExch(c.p->ws.abort_flag, 1);
+            break;
+          }
         }
       }
-    }
-    // the acquire load that observed the full count orders every later read of this CTA (after
-    // the bar.sync below) behind the other CTAs' writes
-    if (c.tid == 0) {
-      sm100::fence_proxy_async();   // later TMA reads must see what other CTAs wrote
+      // the acquire load that observed the full count orders every later read of this CTA (after
+      // the named barrier below) behind the other CTAs' writes
+      sm100::fence_proxy_async();   // this thread's TMA reads must see what other CTAs wrote
       prof_add(c, 0, prof_now(c) - t0);
     }
+    __syncwarp();
+    // named barriers count whole warps: the producer WARP arrives (without waiting), the nine others sync
+    asm volatile("bar.arrive 4, %0;" ::"n"(kThreads) : "memory");
+  } else {
+    asm volatile("bar.sync 4, %0;" ::"n"(kThreads) : "memory");
   }
-  __syncthreads();
   sm100::tc_fence_after();
 }
 
@@ -399,7 +387,9 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
       sm100::fence_proxy_async();   // other CTAs' generic-proxy stores (ordered by the barrier) -> async proxy
       for (int j = 0; j < ntiles; ++j) {
         const int s = c.load_cnt % kActStages;
-        mbar_wait(c, &c.mb_empty[s], ((c.load_cnt / kActStages) & 1u) ^ 1u);
+        // every stage is free when a layer starts (the previous layer's UMMAs have completed): only a
+        // stage reused WITHIN the layer is waited for — even a satisfied mbarrier wait costs ~90 cycles
+        if (j >= kActStages) mbar_wait(c, &c.mb_empty[s], ((c.load_cnt / kActStages) & 1u) ^ 1u);
         const int r0 = (c.t_begin + j) * kTileOut;
         unsigned char* dst = act_smem + (size_t)s * stage_bytes;
         sm100::mbar_expect_tx(&c.mb_full[s], (uint32_t)(3 * nch * seg_rows * 16));
@@ -427,7 +417,7 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
         t0 = prof_now(c);
         mbar_wait(c, &c.mb_full[s], (c.mma_cnt / kActStages) & 1u);
         prof_add(c, 1, prof_now(c) - t0);
-        mbar_wait(c, &c.mb_tempty[slot], ((c.mma_cnt / kAccSlots) & 1u) ^ 1u);
+        if (j >= kAccSlots) mbar_wait(c, &c.mb_tempty[slot], ((c.mma_cnt / kAccSlots) & 1u) ^ 1u);   // ditto
         sm100::tc_fence_after();
         t0 = prof_now(c);
         const uint32_t a_lo = ((sm100::smem_u32(act_smem + (size_t)s * stage_bytes) >> 4) & 0x3FFFu) | ((uint32_t)seg_rows << 16);
@@ -534,10 +524,7 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
   // weights: this layer's buffer has been consumed, the other one is in flight
   bit_flip(c, buf);
   bit_set(c, 8 + buf, false);
-  sm100::tc_fence_before();
-  const long long t_sync = prof_now(c);
-  __syncthreads();   // every role has finished the layer (stores issued, UMMAs committed and drained)
-  if (c.tid == 0) prof_add(c, 15, prof_now(c) - t_sync);
+  // no CTA-wide sync here: the grid barrier that follows every layer starts with one
   if (last) {
     hit = __reduce_add_sync(0xffffffffu, hit);
     if (c.lane == 0 && hit) atomicAdd(&c.s_misc[0], hit);
@@ -1432,7 +1419,6 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   const long long t_kernel = prof_now(c);
   c.bits = 0;
   c.tmem_base = 0;
-  if (c.tid == 0) c.s_misc[6] = 0;   // grid_barrier: no target seen yet
   const bool tc = p.compute_mode == FFN_COMPUTE_FP16_TC;
 
   for (int i = c.tid; i < p.g.nconv * 32; i += kThreads) c.s_bias[i] = p.w.bias[i];

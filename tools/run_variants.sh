@@ -3,5 +3,5 @@
 args="$1"; shift
 for v in "$@"; do
   if [ "$v" = default ]; then unset FFN_B200_LIB; else export FFN_B200_LIB=$PWD/variants/libffn_b200_$v.so; fi
-  timeout 300 python tools/profile_modes.py $args 2>&1 | grep -E '^\{|Error|error' 
+  timeout 100 python tools/profile_modes.py $args 2>&1 | grep -E '^\{|Error|error' 
 done

@@ -274,49 +274,6 @@ __device__ __forceinline__ void epilogue_row(const Ctx& c, int layer, int r, flo
   }
 }
 
-// Tensor-core epilogue for one FoV row and ONE HALF of the feature maps (16 channels): the two
-// epilogue quads split every tile by channel so a tile's latency is halved.  Same arithmetic as
-// epilogue_row; for the last layer returns this half's share of <relu(net), w_lom>.
-__device__ __forceinline__ float epilogue_half(const Ctx& c, int layer, int r, float (&v)[16], int half,
-                                               float (&res)[16], const float (&bias)[16], __half* out_base,
-                                               size_t chunk_stride) {
-  const Geom& g = c.p->g;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) v[k] += bias[k];
-  const bool is_b = (layer & 1) != 0;
-  const bool last = layer == g.nconv - 1;
-  if (is_b) {
-    // fp32 residual stream: `res` comes from / goes back to this thread's TMEM lane (tc_layer)
-    if (layer > 1) {
-#pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] += res[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) res[k] = v[k];
-  }
-#pragma unroll
-  for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
-  if (last) {
-    const float* wl = c.s_bias + g.nconv * 32 + half * 16;
-    float upd = 0.f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) upd = fmaf(v[k], wl[k], upd);
-    return upd;
-  }
-  __half* dst = out_base + (size_t)r * 8;   // [k-chunk][row][8 halfs]; this half owns chunks 2*half, 2*half+1
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    uint4 o;
-    __half2 h;
-    h = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]); o.x = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]); o.y = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]); o.z = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]); o.w = *reinterpret_cast<uint32_t*>(&h);
-    *reinterpret_cast<uint4*>(dst + q * chunk_stride) = o;
-  }
-  return 0.f;
-}
-
 // ------------------------------------------------------------------------------------------
 // Tensor-core layer: implicit GEMM, M = 128 FoV rows, N = 32 features, K = 27 taps x Cin.
 // A = activation rows (K-major, no swizzle: [k-chunk][row] 16-byte units, so a tap is a shifted
@@ -354,6 +311,151 @@ __device__ __forceinline__ void quad_sync(int quad) {   // the four epilogue war
   asm volatile("bar.sync %0, 128;" ::"r"(quad + 1) : "memory");
 }
 
+// Epilogue of the tensor-core layer (warps 0-7; 2 channel halves x 4 TMEM lane quarters), specialised
+// by layer kind so that the residual / conv_lom paths cost nothing where they do not apply:
+//   EPI_A        "_a" convolutions   : out = relu(v + b)                          (convstack_3d.py:38,45)
+//   EPI_B_FIRST  conv0_b             : net = v + b            ; out = relu(net)   (:39) starts the residual stream
+//   EPI_B        conv{i}_b, i >= 1   : net = v + b + residual ; out = relu(net)   (:46-49)
+//   EPI_LAST     the final "_b"      : as EPI_B, then logits = seed + b_lom + <relu(net), w_lom> (:51-54, model.py:176-177)
+// The fp32 residual stream lives in this thread's TMEM lane, columns behind the accumulator ring.
+// Accumulator row m of a tile holds, for the FoV row u = tile_row0 - 1 + m,
+//   D[u][dx*32 + co] = sum_{dz,dy,ci} act[u + dz*pp + dy*xp][ci] * W[dz,dy,dx][ci][co]
+// and the convolution output is out[v] = D[v-1][dx=-1] + D[v][dx=0] + D[v+1][dx=+1]: one lane up /
+// down, done with warp shuffles (+ a 2 KB shared-memory exchange at the three warp boundaries).
+enum EpiKind : int { EPI_A = 0, EPI_B_FIRST = 1, EPI_B = 2, EPI_LAST = 3 };
+
+template <int KIND>
+__device__ __forceinline__ int tc_epilogue(Ctx& c, int layer, int ntiles) {
+  const KParams& p = *c.p;
+  const Geom& g = p.g;
+  constexpr bool kReadRes = KIND == EPI_B || KIND == EPI_LAST;
+  constexpr bool kWriteRes = KIND == EPI_B_FIRST || KIND == EPI_B;
+  const int half = c.warp >> 2, wq = c.warp & 3;
+  float bias[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) bias[k] = c.s_bias[layer * 32 + half * 16 + k];
+  const size_t chunk_stride = (size_t)g.rows_alloc * 8;
+  __half* out_base = p.ws.act_h[layer & 1] + (size_t)(half * 2) * chunk_stride + (size_t)g.guard * 8;
+  int hit = 0;
+  for (int j = 0; j < ntiles; ++j) {
+    const int slot = c.epi_cnt % kAccSlots;
+    float* xch = c.s_xchg + ((j & 1) * 2 + half) * (4 * 2 * 16);   // double-buffered by tile parity
+    const int m = wq * 32 + c.lane;                                 // accumulator row of this thread
+    const int r = (c.t_begin + j) * kTileOut - 1 + m;               // FoV row it holds partial sums for
+    int z = 0, y = 0, x = 1;
+    const bool valid = m >= 1 && m <= kTileOut && r >= 0 && row_to_zyx(g, r, z, y, x);
+    long long t0 = prof_now(c);
+    mbar_wait(c, &c.mb_tfull[slot], (c.epi_cnt / kAccSlots) & 1u);
+    if (c.tid == 0) prof_add(c, 4, prof_now(c) - t0);
+    t0 = prof_now(c);
+    sm100::tc_fence_after();
+    const uint32_t tbase = c.tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(slot * kStackN + half * 16);
+    const uint32_t tres = c.tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(kAccSlots * kStackN + j * kFeat + half * 16);
+    uint32_t a[16], b[16], d2[16], rr[16];
+    sm100::tmem_ld16(tbase, a);          // dx = -1 block: consumed by the lane above (m + 1)
+    sm100::tmem_ld16(tbase + 32, b);     // dx =  0 block
+    sm100::tmem_ld16(tbase + 64, d2);    // dx = +1 block: consumed by the lane below (m - 1)
+    if (kReadRes) sm100::tmem_ld16(tres, rr);
+    sm100::tmem_ld_wait();
+    // the accumulators are in registers: hand the TMEM slot back to the UMMA issuer
+    sm100::tc_fence_before();
+    __syncwarp();
+    if (c.lane == 0) sm100::mbar_arrive(&c.mb_tempty[slot]);
+    if (c.lane == 31) {
+      float4* q = reinterpret_cast<float4*>(xch + (wq * 2 + 0) * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        q[i] = make_float4(__uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]), __uint_as_float(a[4 * i + 2]),
+                           __uint_as_float(a[4 * i + 3]));
+    }
+    if (c.lane == 0) {
+      float4* q = reinterpret_cast<float4*>(xch + (wq * 2 + 1) * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        q[i] = make_float4(__uint_as_float(d2[4 * i]), __uint_as_float(d2[4 * i + 1]), __uint_as_float(d2[4 * i + 2]),
+                           __uint_as_float(d2[4 * i + 3]));
+    }
+    quad_sync(half);
+    // out[v] = D[v-1][dx=-1] + D[v][dx=0] + D[v+1][dx=+1]
+    float up[16], dn[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      up[k] = __shfl_up_sync(0xffffffffu, __uint_as_float(a[k]), 1);      // from lane - 1
+      dn[k] = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k]), 1);   // from lane + 1
+    }
+    if (c.lane == 0 && wq > 0) {     // row m - 1 lives in the previous warp
+      const float4* q = reinterpret_cast<const float4*>(xch + ((wq - 1) * 2 + 0) * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = q[i];
+        up[4 * i] = t.x; up[4 * i + 1] = t.y; up[4 * i + 2] = t.z; up[4 * i + 3] = t.w;
+      }
+    }
+    if (c.lane == 31 && wq < 3) {    // row m + 1 lives in the next warp
+      const float4* q = reinterpret_cast<const float4*>(xch + ((wq + 1) * 2 + 1) * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = q[i];
+        dn[4 * i] = t.x; dn[4 * i + 1] = t.y; dn[4 * i + 2] = t.z; dn[4 * i + 3] = t.w;
+      }
+    }
+    // SAME padding in x: at x = 0 / x = fx-1 row v-1 / v+1 belongs to the neighbouring line (mask 0);
+    // all partial sums are finite (pad rows multiply zero activations), so 0 * value is exact
+    const float m_up = x == 0 ? 0.f : 1.f, m_dn = x == g.fx - 1 ? 0.f : 1.f;
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      v[k] = fmaf(up[k], m_up, fmaf(dn[k], m_dn, __uint_as_float(b[k]))) + bias[k];
+      if (kReadRes) v[k] += __uint_as_float(rr[k]);
+    }
+    if (kWriteRes) {
+      // rows outside the FoV carry values nobody reads; storing them unconditionally keeps the warp converged
+#pragma unroll
+      for (int k = 0; k < 16; ++k) rr[k] = __float_as_uint(v[k]);
+      sm100::tmem_st16(tres, rr);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
+    if (KIND != EPI_LAST) {
+      if (valid) {
+        __half* dst = out_base + (size_t)r * 8;   // [k-chunk][row][8 halfs]; this half owns chunks 2*half, 2*half+1
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint4 o;
+          __half2 h;
+          h = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+          *reinterpret_cast<uint4*>(dst + q * chunk_stride) = o;
+        }
+      }
+    } else {
+      // conv_lom: this half's share of <relu(net), w_lom>; combine the halves, then logits = seed + update
+      const float* wl = c.s_bias + g.nconv * 32;
+      float part = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) part = fmaf(v[k], wl[half * 16 + k], part);
+      float* dot = c.s_dot + (j & 1) * kTileM;
+      if (half == 1) dot[m] = part;
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      if (half == 0 && valid) {
+        const float upd = part + dot[m] + wl[32];
+        const float raw = p.ws.seed_raw[r];
+        const float fed = isnan(raw) ? p.cv.opt.pad_value : raw;
+        const float logit = fed + upd;
+        p.ws.logits[r] = logit;
+        hit += (logit >= p.cv.opt.move_threshold) ? 1 : 0;
+      }
+    }
+    if (kWriteRes) sm100::tmem_st_wait();
+    if (c.tid == 0) prof_add(c, 5, prof_now(c) - t0);
+    x_spin(FFN_X_EPI_SPIN);
+    ++c.epi_cnt;
+  }
+  return hit;
+}
+
 // Tensor-core layer as a warp-specialised ring pipeline over this CTA's tiles:
 //   warp 8  TMA producer : per tile, 12 bulk copies (3 z-planes x k-chunks, 126 + 2*halo rows) into a
 //                          2-stage shared-memory ring              full[stage]  <-  empty[stage]
@@ -375,7 +477,6 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
   const int seg_rows = kTileOut + 2 * g.halo;                 // k-chunk plane pitch of a stage (rows)
   const int stage_bytes = 3 * 4 * seg_rows * 16;
   const int ntiles = c.t_end - c.t_begin;
-  const bool need_res = (layer & 1) && layer > 1;
   const bool last = layer == g.nconv - 1;
   int hit = 0;
 
@@ -436,88 +537,14 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-7)
-    const int half = c.warp >> 2, wq = c.warp & 3;
-    float bias[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) bias[k] = c.s_bias[layer * 32 + half * 16 + k];
-    const size_t chunk_stride = (size_t)g.rows_alloc * 8;
-    __half* out_base = p.ws.act_h[layer & 1] + (size_t)(half * 2) * chunk_stride + (size_t)g.guard * 8;
-    for (int j = 0; j < ntiles; ++j) {
-      const int slot = c.epi_cnt % kAccSlots;
-      float* xch = c.s_xchg + ((j & 1) * 2 + half) * (4 * 2 * 16);   // double-buffered by tile parity
-      const int m = wq * 32 + c.lane;                                 // accumulator row of this thread
-      const int r = (c.t_begin + j) * kTileOut - 1 + m;               // FoV row it holds partial sums for
-      int z = 0, y = 0, x = 1;
-      const bool valid = m >= 1 && m <= kTileOut && r >= 0 && row_to_zyx(g, r, z, y, x);
-      long long t0 = prof_now(c);
-      mbar_wait(c, &c.mb_tfull[slot], (c.epi_cnt / kAccSlots) & 1u);
-      if (c.tid == 0) prof_add(c, 4, prof_now(c) - t0);
-      t0 = prof_now(c);
-      sm100::tc_fence_after();
-      const uint32_t tbase = c.tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(slot * kStackN + half * 16);
-      // residual stream of this row / channel half: TMEM columns behind the accumulator ring
-      const uint32_t tres = c.tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(kAccSlots * kStackN + j * kFeat + half * 16);
-      uint32_t a[16], b[16], d2[16], rr[16];
-      sm100::tmem_ld16(tbase, a);          // dx = -1 block: consumed by the lane above (m + 1)
-      sm100::tmem_ld16(tbase + 32, b);     // dx =  0 block
-      sm100::tmem_ld16(tbase + 64, d2);    // dx = +1 block: consumed by the lane below (m - 1)
-      if (need_res) sm100::tmem_ld16(tres, rr);
-      sm100::tmem_ld_wait();
-      // the accumulators are in registers: hand the TMEM slot back to the UMMA issuer
-      sm100::tc_fence_before();
-      __syncwarp();
-      if (c.lane == 0) sm100::mbar_arrive(&c.mb_tempty[slot]);
-      if (c.lane == 31) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) xch[(wq * 2 + 0) * 16 + k] = __uint_as_float(a[k]);
-      }
-      if (c.lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) xch[(wq * 2 + 1) * 16 + k] = __uint_as_float(d2[k]);
-      }
-      quad_sync(half);
-      // out[v] = D[v-1][dx=-1] + D[v][dx=0] + D[v+1][dx=+1]
-      float v[16];
-      const float m_up = x == 0 ? 0.f : 1.f, m_dn = x == g.fx - 1 ? 0.f : 1.f;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        float up = __shfl_up_sync(0xffffffffu, __uint_as_float(a[k]), 1);      // from lane - 1
-        float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k]), 1);   // from lane + 1
-        if (c.lane == 0 && wq > 0) up = xch[((wq - 1) * 2 + 0) * 16 + k];
-        if (c.lane == 31 && wq < 3) dn = xch[((wq + 1) * 2 + 1) * 16 + k];
-        // SAME padding in x: at x = 0 / x = fx-1 row v-1 / v+1 belongs to the neighbouring line (mask 0);
-        // all partial sums are finite (pad rows multiply zero activations), so 0 * value is exact
-        v[k] = fmaf(up, m_up, fmaf(dn, m_dn, __uint_as_float(b[k])));
-      }
-      float part = 0.f;
-      float res[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) res[k] = need_res ? __uint_as_float(rr[k]) : 0.f;
-      if (valid) part = epilogue_half(c, layer, r, v, half, res, bias, out_base, chunk_stride);
-      if ((layer & 1) && !last) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) rr[k] = __float_as_uint(res[k]);
-        sm100::tmem_st16(tres, rr);
-        sm100::tmem_st_wait();
-      }
-      if (last) {
-        // conv_lom: combine the two halves' dot products, then logits = seed + update
-        float* dot = c.s_dot + (j & 1) * kTileM;
-        if (half == 1) dot[m] = part;
-        asm volatile("bar.sync 3, 256;" ::: "memory");
-        if (half == 0 && valid) {
-          const float* wl = c.s_bias + g.nconv * 32;
-          const float upd = part + dot[m] + wl[32];
-          const float raw = p.ws.seed_raw[r];
-          const float fed = isnan(raw) ? p.cv.opt.pad_value : raw;
-          const float logit = fed + upd;
-          p.ws.logits[r] = logit;
-          hit += (logit >= p.cv.opt.move_threshold) ? 1 : 0;
-        }
-      }
-      if (c.tid == 0) prof_add(c, 5, prof_now(c) - t0);
-      x_spin(FFN_X_EPI_SPIN);
-      ++c.epi_cnt;
+    if (last) {
+      hit = tc_epilogue<EPI_LAST>(c, layer, ntiles);
+    } else if (!(layer & 1)) {
+      tc_epilogue<EPI_A>(c, layer, ntiles);
+    } else if (layer == 1) {
+      tc_epilogue<EPI_B_FIRST>(c, layer, ntiles);
+    } else {
+      tc_epilogue<EPI_B>(c, layer, ntiles);
     }
   }
   if (c.cta == 0) x_spin(FFN_X_CTA0_LAYER_SPIN);

@@ -9,7 +9,17 @@
 #include <vector>
 
 #include "device_types.cuh"
+// the persistent kernel, twice: the product build and one with device cycle counters
+#define FFN_KNS plain
+#define FFN_PROFILE 0
 #include "flood_kernel.cuh"
+#undef FFN_KNS
+#undef FFN_PROFILE
+#define FFN_KNS profiled
+#define FFN_PROFILE 1
+#include "flood_kernel.cuh"
+#undef FFN_KNS
+#undef FFN_PROFILE
 #include "seed_kernels.cuh"
 #include "selftest.cuh"
 
@@ -128,7 +138,8 @@ int launch(FfnEngine* e, const CanvasDev& cv, CanvasState* d_state, const Job& j
   CUDA_OK(cudaMemsetAsync(e->d_action, 0, sizeof(int), cudaStreamPerThread));
   void* args[] = {&p};
   CUDA_OK(cudaEventRecord(e->ev0, cudaStreamPerThread));
-  CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(ffn_flood_kernel), dim3(e->grid),
+  CUDA_OK(cudaLaunchCooperativeKernel(e->profiling ? reinterpret_cast<const void*>(profiled::ffn_flood_kernel)
+                                                   : reinterpret_cast<const void*>(plain::ffn_flood_kernel), dim3(e->grid),
                                       dim3(kThreads), args, (size_t)e->smem_bytes, cudaStreamPerThread));
   CUDA_OK(cudaEventRecord(e->ev1, cudaStreamPerThread));
   CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
@@ -259,9 +270,10 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   e->smem_bytes = L.total;
   if ((size_t)L.total > prop.sharedMemPerBlockOptin)
     return fail("field of view too large for the shared-memory operand staging");
-  CUDA_OK(cudaFuncSetAttribute(ffn_flood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  CUDA_OK(cudaFuncSetAttribute(plain::ffn_flood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  CUDA_OK(cudaFuncSetAttribute(profiled::ffn_flood_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
   int per_sm = 0;
-  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffn_flood_kernel, kThreads, L.total));
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plain::ffn_flood_kernel, kThreads, L.total));
   if (per_sm < 1) return fail("persistent kernel does not fit on an SM");
   e->grid = std::min(e->sm_count, g.nt);
   if ((g.nt + e->grid - 1) / e->grid > kMaxTilesPerCta)

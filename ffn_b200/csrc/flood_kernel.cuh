@@ -16,7 +16,9 @@
 //   validity     ffn/inference/inference.py:312-346
 //   object loop  ffn/inference/inference.py:460-533
 //   canvas loop  ffn/inference/inference.py:538-683; ffn/inference/storage.py:137-143
-#pragma once
+// Included TWICE by engine.cu: namespace FFN_KNS = plain (FFN_PROFILE 0, the product kernel) and
+// = profiled (FFN_PROFILE 1: device cycle counters, ffn_engine_profile), so that the timing code costs
+// the product kernel nothing.
 
 #include <math_constants.h>
 
@@ -24,6 +26,7 @@
 #include "sm100.cuh"
 
 namespace ffn {
+namespace FFN_KNS {
 
 // ------------------------------------------------------------------------------------------
 // Per-CTA context
@@ -64,10 +67,15 @@ __device__ __forceinline__ bool aborted(const Ctx& c) {
 
 // Profiling is opt-in (ffn_engine_profile_enable): reading the clock is not free, and CTA G-1 —
 // one of the two profiled CTAs — is on the critical path of every layer.
+#if FFN_PROFILE
 __device__ __forceinline__ long long prof_now(const Ctx& c) { return c.prof ? clock64() : 0ll; }
 __device__ __forceinline__ void prof_add(const Ctx& c, int slot, long long dt) {
   if (c.prof) c.prof[slot] += dt;
 }
+#else
+__device__ __forceinline__ long long prof_now(const Ctx&) { return 0ll; }
+__device__ __forceinline__ void prof_add(const Ctx&, int, long long) {}
+#endif
 
 // Bounded spin on an mbarrier phase; a timeout raises the abort flag instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(const Ctx& c, uint64_t* bar, uint32_t parity) {
@@ -414,19 +422,17 @@ __device__ __forceinline__ int tc_epilogue(Ctx& c, int layer, int ntiles) {
       for (int k = 0; k < 16; ++k) rr[k] = __float_as_uint(v[k]);
       sm100::tmem_st16(tres, rr);
     }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
     if (KIND != EPI_LAST) {
       if (valid) {
+        // out = relu(.) as fp16: the ReLU rides on the conversion (cvt.rn.relu.f16x2.f32)
         __half* dst = out_base + (size_t)r * 8;   // [k-chunk][row][8 halfs]; this half owns chunks 2*half, 2*half+1
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           uint4 o;
-          __half2 h;
-          h = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]); o.x = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]); o.y = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]); o.z = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+          o.x = sm100::cvt_relu_f16x2(v[8 * q + 0], v[8 * q + 1]);
+          o.y = sm100::cvt_relu_f16x2(v[8 * q + 2], v[8 * q + 3]);
+          o.z = sm100::cvt_relu_f16x2(v[8 * q + 4], v[8 * q + 5]);
+          o.w = sm100::cvt_relu_f16x2(v[8 * q + 6], v[8 * q + 7]);
           *reinterpret_cast<uint4*>(dst + q * chunk_stride) = o;
         }
       }
@@ -435,7 +441,7 @@ __device__ __forceinline__ int tc_epilogue(Ctx& c, int layer, int ntiles) {
       const float* wl = c.s_bias + g.nconv * 32;
       float part = 0.f;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) part = fmaf(v[k], wl[half * 16 + k], part);
+      for (int k = 0; k < 16; ++k) part = fmaf(fmaxf(v[k], 0.f), wl[half * 16 + k], part);
       float* dot = c.s_dot + (j & 1) * kTileM;
       if (half == 1) dot[m] = part;
       asm volatile("bar.sync 3, 256;" ::: "memory");
@@ -1439,7 +1445,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   c.s_state = reinterpret_cast<CanvasState*>(smem_raw + L.bars + 4096);
   static_assert(sizeof(CanvasState) <= 512 && sizeof(CanvasState) % 8 == 0, "state copy area");
   c.prof = nullptr;
-  if (p.ws.prof && (c.cta == 0 || c.cta == c.G - 1)) {
+  if (FFN_PROFILE && p.ws.prof && (c.cta == 0 || c.cta == c.G - 1)) {
     c.prof = reinterpret_cast<long long*>(smem_raw + L.bars + 512);
     if (c.tid < 16) c.prof[c.tid] = 0;
   }
@@ -1533,6 +1539,10 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   }
 }
 
+}  // namespace FFN_KNS
+
+#ifndef FFN_MISC_KERNELS_DEFINED
+#define FFN_MISC_KERNELS_DEFINED
 // Adds `offset` to every label > 0 (multi-GPU merge). HBM-bound, grid-stride.
 __global__ void relabel_offset_kernel(int* seg, size_t n, int offset) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -1553,5 +1563,7 @@ __global__ void fill_f32_kernel(float* dst, size_t n, float v) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
 }
+
+#endif  // FFN_MISC_KERNELS_DEFINED
 
 }  // namespace ffn

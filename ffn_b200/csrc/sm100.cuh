@@ -169,6 +169,13 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p) {
   asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// {lo, hi} -> packed fp16x2 of max(., 0): ReLU fused into the conversion.
+__device__ __forceinline__ uint32_t cvt_relu_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -741,15 +741,17 @@ __device__ __forceinline__ void push_move(const KParams& p, CanvasState* st, flo
 }
 
 // FaceMaxMovementPolicy.update (movement.py:210-222) for the step just executed at st->cur.
-// All threads of CTA 0 call this; warps 0-5 each reduce one face.  (No dynamically indexed local
-// arrays here: local memory lives behind the L1 that every grid barrier invalidates.)
+// All threads of CTA 0 call this.  Warps 0-5 each reduce one face (every load of a face in flight at
+// once); then lanes 0-5 of warp 0 each own one face's move and work out, with shuffles, whether it is
+// a duplicate and its rank in the descending (score, (dz, dy, dx)) order — the position it is written
+// to in the queue.  (No dynamically indexed local arrays here: local memory lives behind the L1 that
+// every grid barrier invalidates.)
 __device__ __forceinline__ void policy_update(Ctx& c, CanvasState* st, bool disco) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
   float* s_score = reinterpret_cast<float*>(c.s_misc + 8);
   int* s_rel = c.s_misc + 16;     // [6][3]
   int* s_ok = c.s_misc + 40;      // [6]
-  int* s_order = c.s_misc + 48;   // [6]
   const int cz = g.fz / 2, cy = g.fy / 2, cx = g.fx / 2;
   if (c.warp < 6) {
     const int axis = c.warp >> 1;
@@ -763,11 +765,11 @@ __device__ __forceinline__ void policy_update(Ctx& c, CanvasState* st, bool disc
     if (dax != 0) {
       float best = -CUDART_INF_F;
       int best_i = 0x7fffffff;
-      // eight independent L2 loads in flight per lane, then the (ordered) comparisons
-      for (int base = c.lane; base < n0 * n1; base += 256) {
-        float lg[8], od[8];
+      constexpr int kPerLane = 10;   // 320 >= 17 x 17 face elements: one L2 round trip for a whole face
+      for (int base = c.lane; base < n0 * n1; base += 32 * kPerLane) {
+        float lg[kPerLane], od[kPerLane];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kPerLane; ++u) {
           const int e = base + 32 * u;
           lg[u] = 0.f;
           od[u] = 0.f;
@@ -782,7 +784,7 @@ __device__ __forceinline__ void policy_update(Ctx& c, CanvasState* st, bool disc
           }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kPerLane; ++u) {
           const int e = base + 32 * u;
           if (e < n0 * n1) {
             float v = lg[u];
@@ -818,47 +820,55 @@ __device__ __forceinline__ void policy_update(Ctx& c, CanvasState* st, bool disc
     if (c.lane == 0) s_ok[c.warp] = ok;
   }
   __syncthreads();
-  if (c.tid == 0) {
-    p.cv.lattice[lattice_index(p, st, st->cur[0], st->cur[1], st->cur[2])] = st->epoch;
-    int n = 0;
-    for (int f = 0; f < 6; ++f) {
-      if (!s_ok[f]) continue;
-      // movement.py:95-99: identical (score, offset) tuples are yielded once — two faces share an
-      // edge, and the same edge voxel can be the arg-max of both.
-      bool dup = false;
-      for (int i = 0; i < n; ++i) {
-        const int h = s_order[i];
-        dup |= s_rel[3 * f] == s_rel[3 * h] && s_rel[3 * f + 1] == s_rel[3 * h + 1] &&
-               s_rel[3 * f + 2] == s_rel[3 * h + 2] && s_score[f] == s_score[h];
-      }
-      if (!dup) s_order[n++] = f;
+  if (c.warp == 0) {
+    const unsigned full = 0xffffffffu;
+    const int f = c.lane;
+    const bool mine = f < 6 && s_ok[f] != 0;
+    const float sc = f < 6 ? s_score[f] : 0.f;
+    const int rz = f < 6 ? s_rel[3 * f] : 0, ry = f < 6 ? s_rel[3 * f + 1] : 0, rx = f < 6 ? s_rel[3 * f + 2] : 0;
+    // movement.py:95-99: identical (score, offset) tuples are yielded once — two faces share an
+    // edge, and the same edge voxel can be the arg-max of both: the later face's copy is dropped
+    bool dropped = false;
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      const bool oh = __shfl_sync(full, (int)mine, h) != 0;
+      const float sh = __shfl_sync(full, sc, h);
+      const int zh = __shfl_sync(full, rz, h), yh = __shfl_sync(full, ry, h), xh = __shfl_sync(full, rx, h);
+      if (h < f && oh && sh == sc && zh == rz && yh == ry && xh == rx) dropped = true;
     }
-    // sorted(..., reverse=True) on (score, (dz, dy, dx)) tuples (movement.py:218)
-    for (int i = 1; i < n; ++i) {
-      const int f = s_order[i];
-      int j = i - 1;
-      while (j >= 0) {
-        const int h = s_order[j];
-        bool greater = s_score[f] > s_score[h];
-        if (s_score[f] == s_score[h]) {
-          greater = false;
-          for (int k = 0; k < 3; ++k) {
-            if (s_rel[3 * f + k] != s_rel[3 * h + k]) {
-              greater = s_rel[3 * f + k] > s_rel[3 * h + k];
-              break;
-            }
-          }
-        }
-        if (!greater) break;
-        s_order[j + 1] = h;
-        --j;
-      }
-      s_order[j + 1] = f;
+    const bool keep = mine && !dropped;
+    // sorted(..., reverse=True) on (score, (dz, dy, dx)) tuples (movement.py:218): rank = kept moves ahead of mine
+    int rank = 0;
+#pragma unroll
+    for (int h = 0; h < 6; ++h) {
+      const bool kh = __shfl_sync(full, (int)keep, h) != 0;
+      const float sh = __shfl_sync(full, sc, h);
+      const int zh = __shfl_sync(full, rz, h), yh = __shfl_sync(full, ry, h), xh = __shfl_sync(full, rx, h);
+      bool ahead = sh > sc;
+      if (sh == sc) ahead = zh != rz ? zh > rz : (yh != ry ? yh > ry : xh > rx);
+      if (kh && h != f && ahead) ++rank;
     }
-    for (int i = 0; i < n; ++i) {
-      const int f = s_order[i];
-      push_move(p, st, s_score[f], st->cur[0] + s_rel[3 * f], st->cur[1] + s_rel[3 * f + 1],
-                st->cur[2] + s_rel[3 * f + 2]);
+    const int n = __popc(__ballot_sync(full, keep));
+    const int tail = st->q_tail;
+    const int room = max(p.cv.q_cap - tail, 0);
+    if (keep && rank < room) {
+      const int t = tail + rank;
+      p.cv.q_score[t] = sc;
+      p.cv.q_pos[3 * t + 0] = st->cur[0] + rz;
+      p.cv.q_pos[3 * t + 1] = st->cur[1] + ry;
+      p.cv.q_pos[3 * t + 2] = st->cur[2] + rx;
+    }
+    __syncwarp();
+    if (c.lane == 0) {
+      p.cv.lattice[lattice_index(p, st, st->cur[0], st->cur[1], st->cur[2])] = st->epoch;
+      if (n > room) st->overflow |= 1;
+      const int wrote = min(n, room);
+      if (p.cv.trace) {
+        for (int i = 0; i < wrote; ++i)
+          trace_event(p, st, EV_PUSH, __ldcg(p.cv.q_pos + 3 * (tail + i)), __ldcg(p.cv.q_pos + 3 * (tail + i) + 1),
+                      __ldcg(p.cv.q_pos + 3 * (tail + i) + 2));
+      }
+      st->q_tail = tail + wrote;
     }
   }
   __syncthreads();

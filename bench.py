@@ -273,6 +273,7 @@ def main():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--compute', default='fp16', choices=['fp16', 'fp32'])
   ap.add_argument('--cpu-baseline-steps', type=int, default=24)
+  ap.add_argument('--skip-extras', action='store_true', help='no throughput_mode / cpu_baseline legs (profiler runs)')
   args = ap.parse_args()
   rank = int(os.environ.get('RANK', '0'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -394,14 +395,14 @@ def main():
     # ---- throughput mode (extra, N = 1 only): the reference batches FoVs of several canvases per executor
     # (InferenceRequest.batch_size); here three engines with 49 SMs each flood-fill three independent 256^3
     # volumes concurrently, one host thread per canvas.  Reported beside, never instead of, `value`.
-    if world == 1 and args.compute == 'fp16':
+    if world == 1 and args.compute == 'fp16' and not args.skip_extras:
       try:
         line['throughput_mode'] = throughput_mode(3, args.steps)
       except Exception as e:  # pylint: disable=broad-except
         line['throughput_mode'] = {'error': repr(e)}
     # ---- CPU baseline: the restated reference path on this box's host cores, bounded sample
     try:
-      if world == 1:
+      if world == 1 and not args.skip_extras:
         threads = best_cpu_threads()
         csteps, csecs = run_cpu_steps(vol, pts, args.cpu_baseline_steps, threads)
         line['cpu_baseline'] = {'value': csteps / csecs, 'unit': 'FoV steps/s', 'cores': threads, 'kind': 'port',

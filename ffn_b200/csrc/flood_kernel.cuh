@@ -302,7 +302,9 @@ template <int NCH>
 __device__ __forceinline__ void tc_issue_tile(uint32_t d, uint32_t a_lo, uint32_t b_lo, int seg_rows, int xp) {
   const uint32_t idesc = sm100::umma_idesc_f16(kTileM, kStackN);
   const uint64_t hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
-#pragma unroll
+  // one (dz, dy) tap-row per iteration: fully unrolled, the 36 descriptors overflow the uniform register
+  // file into ordinary registers
+#pragma unroll 1
   for (int row = 0; row < 9; ++row) {
     const int tz = row / 3, ty = row % 3;
 #pragma unroll
@@ -339,9 +341,7 @@ __device__ __forceinline__ int tc_epilogue(Ctx& c, int layer, int ntiles) {
   constexpr bool kReadRes = KIND == EPI_B || KIND == EPI_LAST;
   constexpr bool kWriteRes = KIND == EPI_B_FIRST || KIND == EPI_B;
   const int half = c.warp >> 2, wq = c.warp & 3;
-  float bias[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) bias[k] = c.s_bias[layer * 32 + half * 16 + k];
+  const float4* bias4 = reinterpret_cast<const float4*>(c.s_bias + layer * 32 + half * 16);   // re-read per tile: 16 registers less
   const size_t chunk_stride = (size_t)g.rows_alloc * 8;
   __half* out_base = p.ws.act_h[layer & 1] + (size_t)(half * 2) * chunk_stride + (size_t)g.guard * 8;
   int hit = 0;
@@ -412,9 +412,15 @@ __device__ __forceinline__ int tc_epilogue(Ctx& c, int layer, int ntiles) {
     const float m_up = x == 0 ? 0.f : 1.f, m_dn = x == g.fx - 1 ? 0.f : 1.f;
     float v[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      v[k] = fmaf(up[k], m_up, fmaf(dn[k], m_dn, __uint_as_float(b[k]))) + bias[k];
-      if (kReadRes) v[k] += __uint_as_float(rr[k]);
+    for (int i = 0; i < 4; ++i) {
+      const float4 bi = bias4[i];
+      const float bias[4] = {bi.x, bi.y, bi.z, bi.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = 4 * i + e;
+        v[k] = fmaf(up[k], m_up, fmaf(dn[k], m_dn, __uint_as_float(b[k]))) + bias[e];
+        if (kReadRes) v[k] += __uint_as_float(rr[k]);
+      }
     }
     if (kWriteRes) {
       // rows outside the FoV carry values nobody reads; storing them unconditionally keeps the warp converged
@@ -488,47 +494,52 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
 
   bit_set(c, 8 + ((layer + 1) & 1), true);   // the next layer's weights are prefetched below
 
+  // The two single-issuer roles run with the WHOLE warp converged (c.warp is warp-uniform by
+  // construction, see the kernel entry) and elect one lane only for the instructions with side effects:
+  // addresses and descriptors then live in uniform registers, instead of being broadcast from one
+  // lane's registers (ELECT / R2UR loop) in front of every bulk copy and every UMMA.
   if (c.warp == kLoadWarp) {
-    if (c.lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      sm100::fence_proxy_async();   // other CTAs' generic-proxy stores (ordered by the barrier) -> async proxy
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = c.load_cnt % kActStages;
-        // every stage is free when a layer starts (the previous layer's UMMAs have completed): only a
-        // stage reused WITHIN the layer is waited for — even a satisfied mbarrier wait costs ~90 cycles
-        if (j >= kActStages) mbar_wait(c, &c.mb_empty[s], ((c.load_cnt / kActStages) & 1u) ^ 1u);
-        const int r0 = (c.t_begin + j) * kTileOut;
-        unsigned char* dst = act_smem + (size_t)s * stage_bytes;
+    // ------------------------------------------------------------------ TMA producer
+    sm100::fence_proxy_async();   // other CTAs' generic-proxy stores (ordered by the barrier) -> async proxy
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = c.load_cnt % kActStages;
+      // every stage is free when a layer starts (the previous layer's UMMAs have completed): only a
+      // stage reused WITHIN the layer is waited for — even a satisfied mbarrier wait costs ~90 cycles
+      if (j >= kActStages) mbar_wait(c, &c.mb_empty[s], ((c.load_cnt / kActStages) & 1u) ^ 1u);
+      const int r0 = (c.t_begin + j) * kTileOut;
+      unsigned char* dst = act_smem + (size_t)s * stage_bytes;
+      if (sm100::elect_one()) {
         sm100::mbar_expect_tx(&c.mb_full[s], (uint32_t)(3 * nch * seg_rows * 16));
         for (int dzi = 0; dzi < 3; ++dzi)
           for (int ch = 0; ch < nch; ++ch)
             sm100::bulk_g2s(dst + (size_t)(dzi * nch + ch) * seg_rows * 16,
                             in + ((size_t)ch * g.rows_alloc + g.guard + r0 + (dzi - 1) * g.pp - g.halo) * 8,
                             (uint32_t)seg_rows * 16, &c.mb_full[s]);
-        ++c.load_cnt;
       }
-      // Prefetch the next layer's weights (next step's layer 0 after the last layer) into the other
-      // buffer — its previous user (layer - 1) has completed all MMAs — behind this layer's operands.
-      tc_issue_weight_load(c, (layer + 1 == g.nconv) ? 0 : layer + 1);
+      __syncwarp();
+      ++c.load_cnt;
     }
+    // Prefetch the next layer's weights (next step's layer 0 after the last layer) into the other
+    // buffer — its previous user (layer - 1) has completed all MMAs — behind this layer's operands.
+    if (sm100::elect_one()) tc_issue_weight_load(c, (layer + 1 == g.nconv) ? 0 : layer + 1);
     __syncwarp();
   } else if (c.warp == kMmaWarp) {
-    if (c.lane == 0) {
-      // ---------------------------------------------------------------- UMMA issuer
-      long long t0 = prof_now(c);
-      mbar_wait(c, &c.mb_w[buf], bit_get(c, buf));
-      prof_add(c, 2, prof_now(c) - t0);
-      const uint32_t b_lo = ((sm100::smem_u32(c.smem + buf * (27 * 4 * 512)) >> 4) & 0x3FFFu) | ((12u * 128u >> 4) << 16);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = c.mma_cnt % kActStages, slot = c.mma_cnt % kAccSlots;
-        t0 = prof_now(c);
-        mbar_wait(c, &c.mb_full[s], (c.mma_cnt / kActStages) & 1u);
-        prof_add(c, 1, prof_now(c) - t0);
-        if (j >= kAccSlots) mbar_wait(c, &c.mb_tempty[slot], ((c.mma_cnt / kAccSlots) & 1u) ^ 1u);   // ditto
-        sm100::tc_fence_after();
-        t0 = prof_now(c);
-        const uint32_t a_lo = ((sm100::smem_u32(act_smem + (size_t)s * stage_bytes) >> 4) & 0x3FFFu) | ((uint32_t)seg_rows << 16);
-        const uint32_t d = c.tmem_base + (uint32_t)(slot * kStackN);
+    // ------------------------------------------------------------------ UMMA issuer
+    long long t0 = prof_now(c);
+    mbar_wait(c, &c.mb_w[buf], bit_get(c, buf));
+    if (c.lane == 0) prof_add(c, 2, prof_now(c) - t0);
+    const uint32_t b_lo = ((sm100::smem_u32(c.smem + buf * (27 * 4 * 512)) >> 4) & 0x3FFFu) | ((12u * 128u >> 4) << 16);
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = c.mma_cnt % kActStages, slot = c.mma_cnt % kAccSlots;
+      t0 = prof_now(c);
+      mbar_wait(c, &c.mb_full[s], (c.mma_cnt / kActStages) & 1u);
+      if (c.lane == 0) prof_add(c, 1, prof_now(c) - t0);
+      if (j >= kAccSlots) mbar_wait(c, &c.mb_tempty[slot], ((c.mma_cnt / kAccSlots) & 1u) ^ 1u);   // ditto
+      sm100::tc_fence_after();
+      t0 = prof_now(c);
+      const uint32_t a_lo = ((sm100::smem_u32(act_smem + (size_t)s * stage_bytes) >> 4) & 0x3FFFu) | ((uint32_t)seg_rows << 16);
+      const uint32_t d = c.tmem_base + (uint32_t)(slot * kStackN);
+      if (sm100::elect_one()) {
         if (layer == 0) {
           tc_issue_tile<2>(d, a_lo, b_lo, seg_rows, g.xp);
         } else {
@@ -536,11 +547,11 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
         }
         sm100::umma_commit(&c.mb_tfull[slot]);   // accumulators of this tile complete
         sm100::umma_commit(&c.mb_empty[s]);      // ... and its shared-memory stage is free again
-        prof_add(c, 3, prof_now(c) - t0);
-        ++c.mma_cnt;
       }
+      __syncwarp();
+      if (c.lane == 0) prof_add(c, 3, prof_now(c) - t0);
+      ++c.mma_cnt;
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-7)
     if (last) {
@@ -1432,7 +1443,8 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   Ctx c;
   c.p = &p;
   c.tid = threadIdx.x;
-  c.warp = threadIdx.x >> 5;
+  // warp-uniform BY CONSTRUCTION (a shuffle from lane 0): role branches on it are uniform branches
+  c.warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   c.lane = threadIdx.x & 31;
   c.cta = blockIdx.x;
   c.G = gridDim.x;
@@ -1486,7 +1498,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
     sm100::tc_fence_before();
     __syncthreads();
     sm100::tc_fence_after();
-    c.tmem_base = *c.s_tmem;
+    c.tmem_base = __shfl_sync(0xffffffffu, *c.s_tmem, 0);
     if (c.warp == kLoadWarp && c.lane == 0) tc_issue_weight_load(c, 0);
     bit_set(c, 8, true);
   }

@@ -169,6 +169,19 @@ __device__ __forceinline__ int ld_volatile_s32(const int* p) {
   asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// True in exactly one lane of a fully converged warp (elect.sync).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // {lo, hi} -> packed fp16x2 of max(., 0): ReLU fused into the conversion.
 __device__ __forceinline__ uint32_t cvt_relu_f16x2(float lo, float hi) {
   uint32_t d;

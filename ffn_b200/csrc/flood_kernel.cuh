@@ -145,8 +145,7 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
         }
       }
       // the acquire load that observed the full count orders every later read of this CTA (after
-      // the named barrier below) behind the other CTAs' writes
-      sm100::fence_proxy_async();   // this thread's TMA reads must see what other CTAs wrote
+      // the named barrier below) behind the other CTAs' writes; the TMA producer adds its proxy fence
       prof_add(c, 0, prof_now(c) - t0);
     }
     __syncwarp();
@@ -500,7 +499,7 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
   // lane's registers (ELECT / R2UR loop) in front of every bulk copy and every UMMA.
   if (c.warp == kLoadWarp) {
     // ------------------------------------------------------------------ TMA producer
-    sm100::fence_proxy_async();   // other CTAs' generic-proxy stores (ordered by the barrier) -> async proxy
+    sm100::fence_proxy_async_global();   // other CTAs' generic-proxy stores (ordered by the barrier) -> async proxy
     for (int j = 0; j < ntiles; ++j) {
       const int s = c.load_cnt % kActStages;
       // every stage is free when a layer starts (the previous layer's UMMAs have completed): only a

@@ -40,6 +40,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Global state space only: generic-proxy writes to global memory (made visible by an acquire) before this
+// thread's async-proxy (bulk copy) reads of them.  One FENCE.VIEW.ASYNC.G — the unqualified form above
+// adds a MEMBAR.ALL.GPU.
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }

@@ -1519,13 +1519,15 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
         if (c.tid == 0) prof_add(c, 8, prof_now(c) - t0);
       }
       grid_barrier(c);
-      if (aborted(c)) break;
+      // one L2 round trip for everything the leader published, not one per dependent branch
+      const int abort_now = sm100::ld_volatile_s32(p.ws.abort_flag);
       const int action = sm100::ld_volatile_s32(p.job.action);
+      const int pz = sm100::ld_volatile_s32(&p.st->cur[0]);
+      const int py = sm100::ld_volatile_s32(&p.st->cur[1]);
+      const int px = sm100::ld_volatile_s32(&p.st->cur[2]);
+      if (abort_now != 0) break;
       if (action == ACT_EXIT) break;
       if (action == ACT_STEP) {
-        const int pz = sm100::ld_volatile_s32(&p.st->cur[0]);
-        const int py = sm100::ld_volatile_s32(&p.st->cur[1]);
-        const int px = sm100::ld_volatile_s32(&p.st->cur[2]);
         long long t0 = prof_now(c);
         stage_fov(c, pz, py, px, 0);
         if (c.tid == 0) prof_add(c, 6, prof_now(c) - t0);

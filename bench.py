@@ -219,11 +219,12 @@ def throughput_mode(chains, steps):
     c0 = cv.counters()
     gate.wait()
     t0 = time.perf_counter()
-    done = 0
+    done = ncalls = 0
     while done < steps:
       done += int(cv.segment_at(pts[k % len(pts)], max_steps=steps - done).iters)
       k += 1
-    out[i] = (done, time.perf_counter() - t0, cv.counters().device_seconds - c0.device_seconds)
+      ncalls += 1
+    out[i] = (done, time.perf_counter() - t0, cv.counters().device_seconds - c0.device_seconds, ncalls)
     cv.close()
   threads = [threading.Thread(target=worker, args=(i,)) for i in range(chains)]
   for t in threads:
@@ -235,7 +236,8 @@ def throughput_mode(chains, steps):
   total = sum(o[0] for o in out)
   wall = max(o[1] for o in out)
   return {'chains': chains, 'sms_per_chain': sms // chains, 'value': total / wall, 'unit': 'FoV steps/s (aggregate, wall clock)',
-          'per_chain_steps_per_s_device': [o[0] / o[2] for o in out],
+          'per_chain_steps_per_s_device': [o[0] / o[2] for o in out], 'per_chain_wall_s': [o[1] for o in out],
+          'per_chain_calls': [o[3] for o in out],
           'roofline_frac': total / wall * flops_per_step() / 1e12 / measured_peaks()[0]}
 
 

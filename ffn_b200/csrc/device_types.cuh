@@ -68,7 +68,7 @@ struct Workspace {
   float* seed_raw;     // [nt*128] seed FoV as read from the canvas (NaN preserved)
   float* logits;       // [nt*128] network output (seed + update), before the disco merge
   unsigned* bar;       // grid barrier counter
-  unsigned* count;     // voxels with logit >= move threshold in the current step
+  unsigned* count;     // [2] current step: voxels with logit >= move threshold; Canvas.history_deleted
   int* abort_flag;     // != 0: a wait timed out, everybody bails
   long long* prof;     // [2][16] cycle counters of CTA 0 and CTA G-1 (debug/profiling)
 };

@@ -316,7 +316,7 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   if (dev_alloc(&ws.seed_raw, (size_t)g.nt * kTileM)) return 1;
   if (dev_alloc(&ws.logits, (size_t)g.nt * kTileM)) return 1;
   if (dev_alloc(&ws.bar, 1)) return 1;
-  if (dev_alloc(&ws.count, 1)) return 1;
+  if (dev_alloc(&ws.count, 2)) return 1;
   if (dev_alloc(&ws.abort_flag, 1)) return 1;
   if (dev_alloc(&ws.prof, 32)) return 1;
   if (dev_alloc(&e->d_action, 1)) return 1;

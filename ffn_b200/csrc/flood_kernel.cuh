@@ -206,7 +206,10 @@ __device__ __forceinline__ void stage_fov(Ctx& c, int pz, int py, int px, int ba
       p.ws.act0_f[(size_t)g.guard + r] = make_float4(img, fed, 0.f, 0.f);
     }
   }
-  if (c.cta == 0 && c.tid == 0) *p.ws.count = 0u;
+  if (c.cta == 0 && c.tid == 0) {
+    p.ws.count[0] = 0u;   // voxels >= move threshold
+    p.ws.count[1] = 0u;   // Canvas.history_deleted of this step
+  }
   if (c.tid == 0) c.s_misc[0] = 0;
 }
 
@@ -219,6 +222,16 @@ __device__ __forceinline__ void stage_fov(Ctx& c, int pz, int py, int px, int ba
 // `out` feeds the next convolution: the pre-activation ReLU of the next residual module and the
 // ReLU before conv_lom are applied here, once, when the value is produced.
 // ------------------------------------------------------------------------------------------
+// Per-row contribution to the two per-step counters, packed (low 16 bits: voxels with logit >= move
+// threshold, inference.py:423; high bits: Canvas.history_deleted, inference.py:420-422 — old seed >= logit(0.8)
+// turned into logit < logit(0.5), counted only while the event trace records history).
+__device__ __forceinline__ int step_counts(const KParams& p, float raw, float logit) {
+  int v = (logit >= p.cv.opt.move_threshold) ? 1 : 0;
+  if (p.cv.trace && p.cv.opt.disco_seed_threshold >= 0.f && (double)raw >= 1.3862943611198908 && logit < 0.f)
+    v += 1 << 16;
+  return v;
+}
+
 __device__ __forceinline__ void epilogue_row(const Ctx& c, int layer, int r, float (&v)[32], int& hit,
                                              const float4* pre_res = nullptr) {
   const KParams& p = *c.p;
@@ -258,7 +271,7 @@ __device__ __forceinline__ void epilogue_row(const Ctx& c, int layer, int r, flo
     const float fed = isnan(raw) ? p.cv.opt.pad_value : raw;
     const float logit = fed + upd;
     p.ws.logits[r] = logit;
-    hit += (logit >= p.cv.opt.move_threshold) ? 1 : 0;
+    hit += step_counts(p, raw, logit);
     return;
   }
   if (p.compute_mode == FFN_COMPUTE_FP16_TC) {
@@ -456,7 +469,7 @@ __device__ __forceinline__ int tc_epilogue(Ctx& c, int layer, int ntiles) {
         const float fed = isnan(raw) ? p.cv.opt.pad_value : raw;
         const float logit = fed + upd;
         p.ws.logits[r] = logit;
-        hit += (logit >= p.cv.opt.move_threshold) ? 1 : 0;
+        hit += step_counts(p, raw, logit);
       }
     }
     if (kWriteRes) sm100::tmem_st_wait();
@@ -645,7 +658,11 @@ __device__ __forceinline__ void run_network(Ctx& c) {
     }
     if (layer == p.g.nconv - 1) {
       __syncthreads();
-      if (c.tid == 0 && c.s_misc[0]) atomicAdd(p.ws.count, (unsigned)c.s_misc[0]);
+      if (c.tid == 0 && c.s_misc[0]) {   // packed per-CTA sums (step_counts): <= 882 rows per CTA, so no carry
+        const unsigned packed = (unsigned)c.s_misc[0];
+        if (packed & 0xffffu) atomicAdd(p.ws.count, packed & 0xffffu);
+        if (packed >> 16) atomicAdd(p.ws.count + 1, packed >> 16);
+      }
     }
     grid_barrier(c);
   }
@@ -725,7 +742,7 @@ __device__ __forceinline__ float seed_value(const KParams& p, const CanvasState*
 
 // Optional event log for debugging / history export (thread 0 of CTA 0 only).
 enum TraceEvent : int { EV_PUSH = 1, EV_POP_VALID = 2, EV_POP_INVALID = 3, EV_POP_THRESHOLD = 4, EV_POP_DONE = 5,
-                        EV_STEP = 6, EV_SEED_INVALID = 7, EV_SEED_START = 8 };
+                        EV_STEP = 6, EV_SEED_INVALID = 7, EV_SEED_START = 8, EV_DELETED = 9 };
 __device__ __forceinline__ void trace_event(const KParams& p, CanvasState* st, int type, int z, int y, int x) {
   if (!p.cv.trace) return;
   const int i = st->n_trace++;
@@ -1103,6 +1120,8 @@ __device__ __forceinline__ bool leader_transition(Ctx& c, CanvasState* st, bool 
     action = ACT_STEP;
     return true;
   }
+  if (phase == PH_AFTER_STEP && p.cv.trace && cv.opt.disco_seed_threshold >= 0.f)
+    trace_event(p, st, EV_DELETED, (int)__ldcg(p.ws.count + 1), 0, 0);   // inference.py:420-422
   if (phase == PH_AFTER_STEP && p.job.mode == MODE_UPDATE_AT) {
     st->ctr.inference_calls++;
     st->have_cur = 0;
@@ -1122,6 +1141,7 @@ __device__ __forceinline__ bool leader_transition(Ctx& c, CanvasState* st, bool 
     return false;
   }
   if (phase == PH_START_SEGMENT) {
+    trace_event(p, st, EV_SEED_START, st->start[0], st->start[1], st->start[2]);
     st->ctr.segment_at_calls++;
     st->seg_t0 = sm100::globaltimer_ns();
     if (st->reset_seed) {

@@ -234,12 +234,14 @@ class DeviceCanvas:
     self._trace_cap = int(capacity)
     _lib.check(self._lib.ffn_canvas_trace(self._h, int(capacity), None, None))
 
-  def get_trace(self) -> np.ndarray:
-    """[n, 4] int32 rows (type, z, y, x); see ffn_canvas_trace."""
+  def get_trace(self, with_total: bool = False):
+    """[n, 4] int32 rows (type, z, y, x); see ffn_canvas_trace.  `with_total` also returns the number of
+    events produced (more than n when the log overflowed)."""
     buf = np.zeros((getattr(self, '_trace_cap', 0), 4), dtype=np.int32)
     n = C.c_int64(0)
     _lib.check(self._lib.ffn_canvas_trace(self._h, 0, _lib.ptr(buf), C.byref(n)))
-    return buf[:min(int(n.value), buf.shape[0])]
+    events = buf[:min(int(n.value), buf.shape[0])]
+    return (events, int(n.value)) if with_total else events
 
   def seed_peaks(self, voxel_size_zyx=(1, 1, 1), noise: Optional[np.ndarray] = None, cap: Optional[int] = None):
     """Device PolicyPeaks: returns the peak coordinates [N, 3] (z, y, x), lexicographically sorted."""

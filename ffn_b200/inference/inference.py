@@ -38,6 +38,10 @@ from .inference_utils import timer_counter
 MSEC_IN_SEC = 1000
 MAX_SELF_CONSISTENT_ITERS = 32
 SEED_CHUNK = 4096   # seeds handed to the device per call (checkpoint granularity)
+# keep_history: capacity of the device event log between two collections (16 bytes per event, about
+# 15 events per FoV step: pushes, pops and their verdicts, the step, its history_deleted count)
+HISTORY_TRACE_EVENTS = 1 << 21
+_EV_STEP, _EV_SEED_START, _EV_DELETED = 6, 8, 9
 
 
 class DeviceArray:
@@ -161,8 +165,6 @@ class Canvas:
     if not isinstance(exec_client, executor.B200ExecutorClient):
       raise TypeError('Canvas runs its flood-fill loop on the GPU and needs a B200ExecutorClient '
                       '(from B200Executor.get_client); got %r' % type(exec_client))
-    if keep_history:
-      raise NotImplementedError('keep_history: per-step history is not exported by the device loop')
     del storage_cls
     self._exec_client = exec_client
     self._exec_client_id = None
@@ -177,7 +179,7 @@ class Canvas:
     self.checkpoint_interval_sec = checkpoint_interval_sec
     self.checkpoint_path = checkpoint_path
     self.checkpoint_last = time.time()
-    self._keep_history = False
+    self._keep_history = bool(keep_history)
     self.corner_zyx = corner_zyx
 
     raw_u8 = image_mean is not None and image_stddev is not None
@@ -238,6 +240,9 @@ class Canvas:
     self.segmentation = DeviceArray(self._dev, _lib.ARRAY_SEGMENTATION, np.int32, 0)
     self.keep_probability_maps = keep_probability_maps
     self.seg_prob = DeviceArray(self._dev, _lib.ARRAY_QPROB, np.uint8, 0) if keep_probability_maps else None
+    if self._keep_history:
+      with exec_client.engine_lock:
+        self._dev.start_trace(HISTORY_TRACE_EVENTS)
 
     self.global_to_local_ids = {}
     self.local_to_global_ids = {}
@@ -357,11 +362,31 @@ class Canvas:
       self.t_last_predict = time.time()
     return fetches.pop('logits')[..., 0]
 
+  def _collect_history(self):
+    """keep_history (inference.py:168-170): turns the device event log recorded since the last call into
+    `history` (positions visited, :520-521) and `history_deleted` (:420-422), then restarts the log.
+    A new object (`segment_all` only) restarts both lists, like `reset_state` (:303-304)."""
+    if not self._keep_history:
+      return
+    with self._exec_client.engine_lock:
+      events, produced = self._dev.get_trace(with_total=True)
+      self._dev.start_trace(HISTORY_TRACE_EVENTS)
+    if produced > events.shape[0]:
+      logging.warning('history log overflow: %d of %d events kept', events.shape[0], produced)
+    for ev, z, y, x in events.tolist():
+      if ev == _EV_SEED_START:
+        self.history, self.history_deleted = [], []
+      elif ev == _EV_STEP:
+        self.history.append((z, y, x))
+      elif ev == _EV_DELETED:
+        self.history_deleted.append(z)
+
   def update_at(self, pos):
     """One FoV step on the device: gather, network, disco merge, paste (inference.py:386-441)."""
     with self._exec_client.engine_lock:
       pred = self._dev.update_at(tuple(int(p) for p in pos))
     self._sync_counters()
+    self._collect_history()
     return pred
 
   def init_seed(self, pos):
@@ -390,6 +415,7 @@ class Canvas:
       self._min_pos = np.array(list(st.min_pos))
       self._max_pos = np.array(list(st.max_pos))
       self._sync_counters()
+      self._collect_history()
     self._last_segment_finished = bool(st.finished)
     return int(st.iters)
 
@@ -418,6 +444,7 @@ class Canvas:
         pos += chunk.shape[0]
         self.seed_policy.idx += chunk.shape[0]
         ctr = self._sync_counters()
+        self._collect_history()
         self.counters['segment_at-loop-calls'].Set(int(ctr.segment_at_calls))
         per_id = {}
         for ov in overlaps:

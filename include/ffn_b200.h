@@ -191,7 +191,8 @@ int ffn_canvas_set_resume(FfnCanvas* canvas, int64_t iters, const int32_t min_po
 /* Event log of the device loop (debugging, Canvas.history export).  Call with capacity > 0 and
  * events_out == NULL to (re)start logging, capacity == 0 to stop; call with events_out != NULL to
  * fetch: rows of (type, z, y, x), type 1 push, 2 pop valid, 3 pop invalid, 4 pop below threshold,
- * 5 pop already done, 6 FoV step, 7 seed invalid.  *n_events = events produced (may exceed capacity). */
+ * 5 pop already done, 6 FoV step, 7 seed invalid, 8 object start, 9 (count, 0, 0) = Canvas.history_deleted of the step just
+ * executed (inference.py:420-422).  *n_events = events produced (may exceed capacity). */
 int ffn_canvas_trace(FfnCanvas* canvas, int64_t capacity, int32_t* events_out, int64_t* n_events);
 /* PolicyPeaks on the device (ffn/inference/seed.py:142-199): Sobel magnitude -> gaussian(sigma 49/6)
  * adaptive threshold -> exact Euclidean distance transform (anisotropy = voxel size) -> local maxima

@@ -161,6 +161,8 @@ class Canvas:
     self.max_pos = np.zeros(3, np.int64)
     # Diagnostics for the parity report.
     self.trace: List[Tuple[int, int, int]] = []      # every FoV position, in order
+    self.history: List[Tuple[int, int, int]] = []    # Canvas.history of the current object
+    self.history_deleted: List[int] = []             # Canvas.history_deleted of the current object
     self.min_margin = float('inf')                   # closest |value - threshold| of any decision
 
   # -- helpers ------------------------------------------------------------------------------
@@ -203,6 +205,10 @@ class Canvas:
     self.counters['inference-calls'] += 1
 
     if self.disco_seed_threshold >= 0:
+      # Canvas.history_deleted (inference.py:420-422; kept unconditionally here, the reference keeps it
+      # under keep_history): float32 old seed against the float64 logit(0.8), raw logits against logit(0.5)
+      with np.errstate(invalid='ignore'):
+        self.history_deleted.append(int(np.sum((old >= 1.3862943611198908) & (logits < 0.0))))
       if np.mean(logits >= self.move_threshold) > self.disco_seed_threshold:
         with np.errstate(invalid='ignore'):
           keep_old = (old < np.float32(0.0)) & (logits > old)   # logit(0.5) == 0
@@ -222,6 +228,7 @@ class Canvas:
     start_pos = tuple(int(p) for p in start_pos)
     self.init_seed(start_pos)
     self.policy.reset(start_pos)
+    self.history, self.history_deleted = [], []     # reset_state (inference.py:303-304)
     self.min_pos = np.asarray(start_pos, dtype=np.int64)
     self.max_pos = np.asarray(start_pos, dtype=np.int64)
     self.policy.queue.append((self.policy.score_threshold * 2, start_pos))
@@ -241,6 +248,7 @@ class Canvas:
         continue
       logits = self.update_at(pos)
       self.trace.append(pos)
+      self.history.append(pos)                        # inference.py:520-521
       self.min_pos = np.minimum(self.min_pos, pos)
       self.max_pos = np.maximum(self.max_pos, pos)
       iters += 1

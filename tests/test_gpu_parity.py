@@ -459,3 +459,95 @@ def test_device_policy_peaks_matches_host_policy(golden_dir, voxel):
     np.testing.assert_array_equal(got, want)
   assert not any(mask[z, y, x] or seed_mask[z, y, x] or seg[z, y, x] > 0 for z, y, x in got)
   exe.close()
+
+
+def test_keep_history_matches_reference_golden(golden_dir, g64):
+  """Canvas(keep_history=True): history (positions visited) and history_deleted (per step, voxels whose
+  old seed >= logit(0.8) got a raw logit < 0) equal the reference's own run (inference.py:420-422,
+  :520-521; fixture from tests/golden/make_golden_history.py), in the label-exact fp32 mode."""
+  from ffn.inference import executor, inference, inference_pb2, inference_utils
+  from ffn.training.models import convstack_3d
+  from ffn_b200 import _lib
+  h = np.load(os.path.join(golden_dir, 'segment_at_history_64.npz'))
+  model = convstack_3d.ConvStack3DFFNModel(fov_size=[33, 33, 33], deltas=[8, 8, 8], depth=12)
+  exe = executor.B200Executor(executor.ExecutorInterface(), model, inference_utils.Counters(),
+                              checkpoint_path=os.path.join(golden_dir, 'fib25_convstack.npz'),
+                              compute_mode=_lib.COMPUTE_FP32)
+  opts = inference_pb2.InferenceOptions(init_activation=0.95, pad_value=0.05, move_threshold=0.9,
+                                        segment_threshold=0.6, min_segment_size=1000)
+  opts.min_boundary_dist.x = opts.min_boundary_dist.y = opts.min_boundary_dist.z = 1
+  cv = inference.Canvas(model.info, exe.get_client(inference_utils.Counters()), g64['volume'], opts,
+                        keep_history=True, image_mean=128, image_stddev=33)
+  n = cv.segment_at(tuple(int(v) for v in h['start']))
+  assert n == h['history'].shape[0]
+  np.testing.assert_array_equal(np.asarray(cv.history, np.int32).reshape(-1, 3), h['history'])
+  np.testing.assert_array_equal(np.asarray(cv.history_deleted, np.int64), h['history_deleted'])
+  cv.segment_at(tuple(int(v) for v in h['second_start']))
+  np.testing.assert_array_equal(np.asarray(cv.history, np.int32).reshape(-1, 3), h['second_history'])
+  np.testing.assert_array_equal(np.asarray(cv.history_deleted, np.int64), h['second_history_deleted'])
+  exe.close()
+
+
+def test_resegmentation_process_point(tmp_path, golden_dir):
+  """resegmentation.process_point (resegmentation.py:114-293) through Runner + the device canvas with
+  keep_history: a pair point between two ground-truth cells and an endpoint; the re-grown objects recover
+  the cells they were seeded in, histories / deletes have one entry per FoV step."""
+  from google.protobuf import text_format
+  from ffn.inference import inference_pb2, resegmentation, runner as runner_mod
+  from ffn_b200 import synthetic
+  shape = (96, 96, 96)
+  vol, cells = synthetic.voronoi_phantom(shape, seed=7, cell_volume=45000.0, return_cells=True)
+  np.save(tmp_path / 'vol.npy', vol)
+  np.save(tmp_path / 'seg.npy', cells[np.newaxis].astype(np.uint64))
+  # a decision point: a membrane voxel near the centre whose two nearest cells differ along x
+  c = 48
+  found = None
+  for z in range(c - 6, c + 7):
+    for y in range(c - 6, c + 7):
+      for x in range(c - 6, c + 6):
+        a, b = int(cells[z, y, x]), int(cells[z, y, x + 1])
+        if a != b and a > 0 and b > 0 and found is None:
+          found = (z, y, x, a, b)
+  assert found is not None
+  z, y, x, id_a, id_b = found
+  req = inference_pb2.ResegmentationRequest()
+  text_format.Parse('''inference { image { hdf5: "%s:raw" } init_segmentation { hdf5: "%s:seg" }
+      image_mean: 128 image_stddev: 33 seed_policy: "PolicyPeaks" model_checkpoint_path: "%s"
+      model_name: "convstack_3d.ConvStack3DFFNModel"
+      model_args: "{\\"depth\\": 12, \\"fov_size\\": [33, 33, 33], \\"deltas\\": [8, 8, 8]}"
+      segmentation_output_dir: "%s"
+      inference_options { init_activation: 0.95 pad_value: 0.05 move_threshold: 0.9 min_boundary_dist { x: 1 y: 1 z: 1}
+                          segment_threshold: 0.6 min_segment_size: 1000 } }
+      radius { x: 40 y: 40 z: 40 } output_directory: "%s" max_retry_iters: 2
+      exclusion_radius { x: 4 y: 4 z: 4 } analysis_radius { x: 24 y: 24 z: 24 }''' % (
+          tmp_path / 'vol.npy', tmp_path / 'seg.npy', os.path.join(golden_dir, 'fib25_convstack.npz'),
+          tmp_path / 'segout', tmp_path / 'reseg'), req)
+  for ids in ((id_a, id_b), (id_a,)):
+    pt = req.points.add()
+    pt.id_a = ids[0]
+    if len(ids) > 1:
+      pt.id_b = ids[1]
+    pt.point.x, pt.point.y, pt.point.z = x, y, z
+  runner = runner_mod.Runner()
+  runner.start(req.inference)
+  resegmentation.process(req, runner)
+  runner.stop_executor()
+
+  sub = cells[z - 40:z + 41, y - 40:y + 41, x - 40:x + 41]
+  for n, ids in enumerate(((id_a, id_b), (id_a,))):
+    path = resegmentation.get_target_path(req, n)
+    assert path is None                                                  # i.e. the result exists
+    name = '%d-%d_at_%d_%d_%d.npz' % (ids[0], ids[1] if len(ids) > 1 else 0, x, y, z)
+    out = np.load(tmp_path / 'reseg' / name, allow_pickle=True)
+    assert out['probs'].shape == (len(ids), 81, 81, 81) and out['raw_probs'].dtype == np.uint8
+    assert tuple(out['corner_zyx']) == (z - 40, y - 40, x - 40) and not bool(out['is_shift'])
+    assert inference_pb2.ResegmentationRequest.FromString(out['request'].tobytes() if hasattr(out['request'], 'tobytes')
+                                                           else bytes(out['request'])).radius.x == 40
+    for k, sid in enumerate(ids):
+      hist, dele, starts = out['histories'][k], out['deletes'][k], out['start_points'][k]
+      assert len(starts) >= 1 and len(hist) == len(dele) and len(hist) > 3
+      grown = out['raw_probs'][k] >= 154                                 # quantised 0.6
+      orig = sub == sid
+      # the object re-grown from inside cell `sid` recovers most of it and stays mostly inside it
+      assert (grown & orig).sum() > 0.5 * orig.sum(), ((grown & orig).sum(), orig.sum())
+      assert (grown & orig).sum() > 0.8 * grown.sum()

@@ -197,3 +197,26 @@ def test_slab_partition_and_offsets():
   assert (cover == 1).all()
   assert distributed.exclusive_offsets([3, 0, 5]) == [0, 3, 3]
   assert distributed.slabs_of_rank(8, 1, 2) == [4, 5, 6, 7]
+
+
+def test_resegmentation_helpers(tmp_path):
+  """get_starting_location / get_target_path (resegmentation.py:37-80)."""
+  from ffn.inference import inference_pb2, resegmentation
+  req = inference_pb2.ResegmentationRequest()
+  req.output_directory = str(tmp_path / 'out')
+  req.exclusion_radius.x, req.exclusion_radius.y, req.exclusion_radius.z = 2, 1, 1
+  pt = req.points.add()
+  pt.id_a, pt.id_b = 7, 11
+  pt.point.x, pt.point.y, pt.point.z = 30, 20, 10
+  d = np.zeros((8, 9, 10))
+  d[4, 5, 6], d[4, 5, 8], d[4, 5, 9], d[1, 1, 1] = 5.0, 4.0, 3.5, 1.0
+  assert resegmentation.get_starting_location(d, req.exclusion_radius) == (4, 5, 6)
+  assert d[4, 5, 6] == 0 and d[4, 5, 8] == 0 and d[4, 5, 9] == 3.5      # x radius 2 cleared, 3 kept
+  assert resegmentation.get_starting_location(d, req.exclusion_radius) == (4, 5, 9)
+  path = resegmentation.get_target_path(req, 0)
+  assert path == os.path.join(req.output_directory, '7-11_at_30_20_10.npz')
+  open(path, 'wb').close()
+  assert resegmentation.get_target_path(req, 0) is None                  # finished points are skipped
+  req.subdir_digits = 3
+  sharded = resegmentation.get_target_path(req, 0)
+  assert os.path.basename(os.path.dirname(sharded)) == __import__('hashlib').md5(b'711').hexdigest()[:3]

@@ -128,3 +128,23 @@ def test_golden_sample_summary(golden_dir):
   assert s['num_segments'] == 254 == s['num_origins'] == s['origins_carry_own_id']
   assert s['counters']['inference-calls'] == 25799
   assert s['counters']['voxels-segmented'] == 13867123
+
+
+def test_oracle_history_matches_reference_keep_history(golden_dir):
+  """Canvas.history / history_deleted (keep_history=True) of the reference's own segment_at,
+  recorded by tests/golden/make_golden_history.py, for two objects on the 64x72x80 phantom."""
+  from oracle import flood_fill as ff
+  from oracle.network import ConvStackOracle
+  from ffn_b200 import tf_checkpoint
+  g = np.load(os.path.join(golden_dir, 'flood_fill_64.npz'))
+  h = np.load(os.path.join(golden_dir, 'segment_at_history_64.npz'))
+  w, b = tf_checkpoint.load_convstack_npz(os.path.join(golden_dir, 'fib25_convstack.npz'))
+  image = (g['volume'].astype(np.float32) - 128.0) / 33.0
+  cv = ff.Canvas(ConvStackOracle(w, b), image, (33, 33, 33), (8, 8, 8), ff.Options())
+  cv.segment_at(tuple(int(v) for v in h['start']))
+  np.testing.assert_array_equal(np.asarray(cv.history, np.int32).reshape(-1, 3), h['history'])
+  np.testing.assert_array_equal(np.asarray(cv.history_deleted, np.int64), h['history_deleted'])
+  assert h['history_deleted'].sum() > 0
+  cv.segment_at(tuple(int(v) for v in h['second_start']))
+  np.testing.assert_array_equal(np.asarray(cv.history, np.int32).reshape(-1, 3), h['second_history'])
+  np.testing.assert_array_equal(np.asarray(cv.history_deleted, np.int64), h['second_history_deleted'])

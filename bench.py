@@ -124,6 +124,26 @@ class ClockSampler:
             'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def ncu_dram_traffic():
+  """DRAM bytes (read + write) of one flood-kernel launch from the committed `ncu --set full` capture
+  (profiles/r01_ncu_full_flood_kernel_steps16.txt: one launch = 16 FoV steps), or None."""
+  path = os.path.join(REPO, 'profiles', 'r01_ncu_full_flood_kernel_steps16.txt')
+  scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+  total, seen = 0.0, 0
+  try:
+    with open(path) as f:
+      for line in f:
+        for key in ('dram__bytes_read.sum [', 'dram__bytes_write.sum ['):
+          if line.startswith(key):
+            unit = line[len(key):line.index(']')]
+            total += float(line.split('=')[1]) * scale[unit]
+            seen += 1
+  except (OSError, ValueError, KeyError):
+    return None
+  return {'bytes_per_launch': total, 'steps_per_launch': 16, 'bytes_per_step': total / 16,
+          'source': 'profiles/r01_ncu_full_flood_kernel_steps16.txt'} if seen == 2 else None
+
+
 def measured_peaks():
   path = os.path.join(REPO, 'MEASURED_PEAKS.json')
   if os.path.exists(path):
@@ -392,7 +412,7 @@ def main():
                 'path': 'ffn_canvas_create (pinned uint8 volume H2D) + ffn_canvas_segment_at + ffn_canvas_read'},
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': burst, 'unit': 'TFLOP/s',
                      'frac': achieved / burst, 'frac_of_sustained': achieved / sustained, 'peak_source': src,
-                     'flops_per_step': flops_per_step(), 'traffic': None},
+                     'flops_per_step': flops_per_step(), 'traffic': ncu_dram_traffic()},
     }
     # ---- throughput mode (extra, N = 1 only): the reference batches FoVs of several canvases per executor
     # (InferenceRequest.batch_size); here three engines with 49 SMs each flood-fill three independent 256^3

@@ -237,7 +237,7 @@ class DeviceCanvas:
   def get_trace(self, with_total: bool = False):
     """[n, 4] int32 rows (type, z, y, x); see ffn_canvas_trace.  `with_total` also returns the number of
     events produced (more than n when the log overflowed)."""
-    buf = np.zeros((getattr(self, '_trace_cap', 0), 4), dtype=np.int32)
+    buf = np.empty((getattr(self, '_trace_cap', 0), 4), dtype=np.int32)   # only the produced rows are filled
     n = C.c_int64(0)
     _lib.check(self._lib.ffn_canvas_trace(self._h, 0, _lib.ptr(buf), C.byref(n)))
     events = buf[:min(int(n.value), buf.shape[0])]

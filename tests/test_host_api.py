@@ -220,3 +220,82 @@ def test_resegmentation_helpers(tmp_path):
   req.subdir_digits = 3
   sharded = resegmentation.get_target_path(req, 0)
   assert os.path.basename(os.path.dirname(sharded)) == __import__('hashlib').md5(b'711').hexdigest()[:3]
+
+
+def test_resegmentation_process_point_host_logic(tmp_path):
+  """process_point (resegmentation.py:114-293) with a stand-in canvas: segment clearing, EDT seeding with
+  margins and retries, recovery test, result file keys (ragged histories as object arrays)."""
+  from ffn.inference import align, inference_pb2, inference_utils, resegmentation
+  from ffn_b200 import synthetic
+  _, cells = synthetic.voronoi_phantom((96, 96, 96), seed=7, cell_volume=45000.0, return_cells=True)
+  z, y, x, a, b = 40, 40, 49, 14, 18
+  made = []
+
+  class FakeCanvas:
+    def __init__(self, corner, size):
+      self.corner_zyx = np.asarray(corner)
+      sel = tuple(slice(c, c + s) for c, s in zip(corner, size))
+      self.segmentation = cells[sel].astype(np.int32).copy()
+      self.seg_prob = np.full(size, 255, np.uint8)
+      self.seed = np.full(size, np.nan, np.float32)
+      self.margin = np.array([16, 16, 16])
+      self.restrictor = None
+      self.counters = inference_utils.Counters()
+      self.history, self.history_deleted, self.calls = [], [], []
+
+    def local_id(self, i):
+      return i
+
+    def log_info(self, *args, **kwargs):
+      pass
+
+    def _deregister_client(self):
+      pass
+
+    def segment_at(self, pos):
+      assert self.segmentation[pos] == 0                      # the segment in question was cleared first
+      self.calls.append(pos)
+      self.seed[...] = np.nan
+      self.seed[tuple(slice(p - 10, p + 11) for p in pos)] = 3.0
+      n = 3 + len(self.calls)
+      self.history, self.history_deleted = [pos] * n, [0] * n
+
+  class FakeRunner:
+    counters = inference_utils.Counters()
+    init_seg_volume = cells[np.newaxis]
+
+    def make_canvas(self, corner, size, **kwargs):
+      assert kwargs == {'keep_history': True}
+      made.append(FakeCanvas(corner, size))
+      return made[-1], align.Alignment(corner, size)
+
+  req = inference_pb2.ResegmentationRequest()
+  req.radius.x = req.radius.y = req.radius.z = 40
+  req.output_directory = str(tmp_path)
+  req.max_retry_iters = 2
+  req.exclusion_radius.x = req.exclusion_radius.y = req.exclusion_radius.z = 4
+  req.analysis_radius.x = req.analysis_radius.y = req.analysis_radius.z = 24
+  req.inference.inference_options.segment_threshold = 0.6
+  req.inference.inference_options.min_segment_size = 100000     # never recovered: every retry is used
+  for ids in ((a, b), (a,), (a, 999)):
+    pt = req.points.add()
+    pt.id_a = ids[0]
+    if len(ids) > 1:
+      pt.id_b = ids[1]
+    pt.point.x, pt.point.y, pt.point.z = x, y, z
+  resegmentation.process(req, FakeRunner())
+
+  pair = np.load(tmp_path / ('%d-%d_at_%d_%d_%d.npz' % (a, b, x, y, z)), allow_pickle=True)
+  assert pair['probs'].shape == (2, 81, 81, 81) and pair['raw_probs'].dtype == np.uint8
+  assert [len(h) for h in pair['histories']] == [5, 7] and [len(d) for d in pair['deletes']] == [5, 7]
+  assert [len(s) for s in pair['start_points']] == [2, 2]
+  assert len(made[0].calls) == 4 and tuple(pair['corner_zyx']) == (0, 0, 9)
+  # context is kept: other labels untouched, the two segments and their probabilities cleared
+  sub = cells[0:81, 0:81, 9:90]
+  keep = (sub != a) & (sub != b)
+  np.testing.assert_array_equal(made[0].segmentation[keep], sub[keep])
+  assert not made[0].segmentation[~keep].any() and not made[0].seg_prob[~keep].any()
+  assert inference_pb2.ResegmentationRequest.FromString(pair['request'].tobytes()).max_retry_iters == 2
+  end = np.load(tmp_path / ('%d-0_at_%d_%d_%d.npz' % (a, x, y, z)), allow_pickle=True)
+  assert end['probs'].shape == (1, 81, 81, 81) and not made[1].segmentation.any()     # endpoint: everything cleared
+  assert not os.path.exists(tmp_path / ('%d-999_at_%d_%d_%d.npz' % (a, x, y, z)))      # id not present: skipped

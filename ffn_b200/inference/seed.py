@@ -102,6 +102,18 @@ def _find_peaks(distances, min_distance, threshold_abs=0, threshold_rel=0):
   return _peak_local_max(distances + rng.rand(*distances.shape) * 1e-4, min_distance, threshold_abs)
 
 
+_NOISE_CACHE = {}
+
+
+def _tie_break_noise(shape):
+  """RandomState(42).rand(*shape) (seed.py:133-139), cached for the most recent shape: a run over many
+  equally sized subvolumes draws the same 8 bytes / voxel every time (0.7 s for 512^3)."""
+  if shape not in _NOISE_CACHE:
+    _NOISE_CACHE.clear()
+    _NOISE_CACHE[shape] = np.random.RandomState(seed=42).rand(*shape)
+  return _NOISE_CACHE[shape]
+
+
 class PolicyPeaks(BaseSeedPolicy):
   """Sobel edges -> adaptive threshold -> distance transform -> local maxima (seed.py:142-199)."""
 
@@ -109,8 +121,7 @@ class PolicyPeaks(BaseSeedPolicy):
     dev = getattr(self.canvas, '_dev', None)
     if dev is not None:
       # device path: the canvas' image / segmentation / masks are already resident in HBM
-      rng = np.random.RandomState(seed=42)               # seed.py:133-139 tie-break noise
-      noise = rng.rand(*self.canvas.shape)
+      noise = _tie_break_noise(tuple(int(v) for v in self.canvas.shape))
       with self.canvas._exec_client.engine_lock:         # pylint: disable=protected-access
         self.coords = dev.seed_peaks(self.canvas.voxel_size_zyx, noise).astype(np.int64).reshape(-1, 3)
       return

@@ -231,8 +231,11 @@ class Canvas:
       else:
         self._dev = engine_lib.DeviceCanvas(eng, self._image_f32, dev_opts,
                                             keep_probability_maps=keep_probability_maps)
-      if self.restrictor.mask is not None:
-        self._dev.set_mask(_lib.MASK_MOVEMENT, self.restrictor.mask)
+      # positions the FoV may not enter: the position mask, plus — evaluated once for every voxel —
+      # the shift-mask rule of MovementRestrictor.is_valid_pos (movement.py:312-334)
+      movement_mask = self.restrictor.movement_mask(self.shape)
+      if movement_mask is not None:
+        self._dev.set_mask(_lib.MASK_MOVEMENT, movement_mask)
       if self.restrictor.seed_mask is not None:
         self._dev.set_mask(_lib.MASK_SEED, self.restrictor.seed_mask)
 

@@ -142,20 +142,74 @@ def get_policy_fn(request, model_info):
 
 
 class MovementRestrictor:
-  """Excludes areas from segmentation (movement.py:247-336).  `mask` and `seed_mask` are
-  uploaded to the device; shift masks are not supported by the device loop."""
+  """Excludes areas from segmentation (movement.py:247-336).
+
+  `mask` and `seed_mask` live on the device next to the canvas.  A shift mask (a 2-d shift vector field per
+  section: positions whose FoV box contains a shift component >= `shift_mask_threshold` are not entered,
+  :312-334) is folded on the host into the per-voxel movement mask the device loop consults
+  (`movement_mask`): `is_valid_pos` is a pure function of the position, so evaluating it for every voxel
+  once gives the device exactly the reference's verdicts (and the same 'skip_restriced_pos' counts).
+  """
 
   def __init__(self, mask=None, shift_mask=None, shift_mask_fov=None, shift_mask_threshold=4,
                shift_mask_scale=1, seed_mask=None):
-    if shift_mask is not None:
-      raise NotImplementedError('shift_mask restriction has no device implementation')
-    del shift_mask_fov, shift_mask_threshold, shift_mask_scale
     self.mask = mask
     self.seed_mask = seed_mask
+    self._shift_mask_scale = shift_mask_scale
     self.shift_mask = None
+    if shift_mask is not None:
+      self.shift_mask = np.max(np.abs(shift_mask), axis=0) >= shift_mask_threshold
+      assert shift_mask_fov is not None
+      # the box is given in (x, y, z); start may be negative
+      self._shift_mask_fov_pre_offset = np.asarray(shift_mask_fov.start)[::-1]
+      self._shift_mask_fov_post_offset = np.asarray(shift_mask_fov.end)[::-1] - 1
 
   def is_valid_seed(self, pos):
     return not (self.seed_mask is not None and self.seed_mask[tuple(pos)])
 
   def is_valid_pos(self, pos):
-    return not (self.mask is not None and self.mask[tuple(pos)])
+    if self.mask is not None and self.mask[tuple(pos)]:
+      return False
+    if self.shift_mask is not None:
+      np_pos = np.array(pos)
+      fov_low = np.maximum(np_pos + self._shift_mask_fov_pre_offset, 0)
+      fov_high = np_pos + self._shift_mask_fov_post_offset
+      start = fov_low // self._shift_mask_scale
+      end = fov_high // self._shift_mask_scale
+      # z is a section index (not scaled), y / x are in shift-mask pixels (movement.py:323-331)
+      if np.any(self.shift_mask[fov_low[0]:fov_high[0] + 1, start[1]:end[1] + 1, start[2]:end[2] + 1]):
+        return False
+    return True
+
+  def movement_mask(self, shape):
+    """Boolean [Z, Y, X]: True where `is_valid_pos` is False (None when nothing is restricted)."""
+    shape = tuple(int(v) for v in shape)
+    blocked = None if self.mask is None else np.asarray(self.mask).astype(bool)
+    if self.shift_mask is None:
+      return blocked
+    sm = np.asarray(self.shift_mask)
+    # summed-area table with a zero border: box sums for every position from eight gathers
+    sat = np.zeros(tuple(d + 1 for d in sm.shape), dtype=np.int64)
+    sat[1:, 1:, 1:] = sm.astype(np.int64).cumsum(0).cumsum(1).cumsum(2)
+    bounds = []
+    for axis in range(3):
+      scale = 1 if axis == 0 else self._shift_mask_scale
+      pre, post = int(self._shift_mask_fov_pre_offset[axis]), int(self._shift_mask_fov_post_offset[axis])
+      lo = np.empty(shape[axis], dtype=np.int64)
+      hi = np.empty(shape[axis], dtype=np.int64)
+      for p in range(shape[axis]):
+        first = max(p + pre, 0)
+        last = p + post
+        if axis:
+          first, last = first // scale, last // scale
+        b, e, _ = slice(first, last + 1).indices(sm.shape[axis])     # numpy's clipping, negative stops included
+        lo[p], hi[p] = b, max(e, b)
+      bounds.append((lo, hi))
+    (z0, z1), (y0, y1), (x0, x1) = bounds
+
+    def corner(zi, yi, xi):
+      return sat[np.ix_(zi, yi, xi)]
+    total = (corner(z1, y1, x1) - corner(z0, y1, x1) - corner(z1, y0, x1) - corner(z1, y1, x0) +
+             corner(z0, y0, x1) + corner(z0, y1, x0) + corner(z1, y0, x0) - corner(z0, y0, x0))
+    shifted = total > 0
+    return shifted if blocked is None else (blocked | shifted)

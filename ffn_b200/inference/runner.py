@@ -23,6 +23,7 @@ import numpy as np
 
 from .. import _lib
 from ..training import import_util
+from ..utils import bounding_box
 from . import align
 from . import executor
 from . import inference
@@ -98,7 +99,9 @@ class Runner:
       else:
         self.init_seg_volume = None
       if request.shift_mask.WhichOneof('volume_path') is not None:
-        raise NotImplementedError('shift_mask restriction has no device implementation')
+        self._shift_mask_volume = storage.decorated_volume(request.shift_mask)
+      else:
+        self._shift_mask_volume = None
       self._mask_volumes = {}
       opts = request.alignment_options
       if opts.type != inference_pb2.AlignmentOptions.NO_ALIGNMENT:
@@ -126,6 +129,29 @@ class Runner:
           logging.info('All seeds masked.')
           return self.ALL_MASKED
         kwargs['seed_mask'] = seed_mask
+    if self._shift_mask_volume is not None:
+      # runner.py:256-300: the 2-d shift field of the subvolume, y / x at `shift_mask_scale` resolution
+      with timer_counter(self.counters, 'load-shift-mask'):
+        s = self.request.shift_mask_scale or 1   # unset in the request: full resolution
+        scale = np.array((1, s, s))
+        shift_corner = np.array(corner) // scale
+        shift_size = -(-np.array(subvol_size) // scale)
+        shift_alignment = alignment.rescaled(np.array((1.0, 1.0, 1.0)) / scale)
+        src_corner, src_size = shift_alignment.expand_bounds(shift_corner, shift_size, forward=False)
+        src_corner, src_size = storage.clip_subvolume_to_bounds(src_corner, src_size, self._shift_mask_volume)
+        src_end = src_corner + src_size
+        expanded = np.asarray(self._shift_mask_volume[0:2, src_corner[0]:src_end[0], src_corner[1]:src_end[1],
+                                                      src_corner[2]:src_end[2]])
+        shift_mask = np.array([shift_alignment.align_and_crop(src_corner, expanded[i], shift_corner, shift_size)
+                               for i in range(2)])
+        shift_mask = alignment.transform_shift_mask(corner, s, shift_mask)
+        if self.request.HasField('shift_mask_fov'):
+          fov = bounding_box.BoundingBox(start=self.request.shift_mask_fov.start, size=self.request.shift_mask_fov.size)
+        else:
+          diameter = np.array(self._model_info.input_image_size)
+          fov = bounding_box.BoundingBox(start=-(diameter // 2), size=diameter)
+        kwargs.update(shift_mask=shift_mask, shift_mask_fov=fov, shift_mask_scale=s,
+                      shift_mask_threshold=self.request.shift_mask_threshold)
     return movement.MovementRestrictor(**kwargs) if kwargs else None
 
   def make_canvas(self, corner, subvol_size, **canvas_kwargs):

@@ -119,7 +119,10 @@ class PolicyPeaks(BaseSeedPolicy):
 
   def init_coords(self):
     dev = getattr(self.canvas, '_dev', None)
-    if dev is not None:
+    restrictor = self.canvas.restrictor
+    # The device's movement mask also carries the shift-mask rule, which seed.py:170-173 does not apply
+    # to the edge map: with a shift mask the seeds are computed by the host restatement below.
+    if dev is not None and getattr(restrictor, 'shift_mask', None) is None:
       # device path: the canvas' image / segmentation / masks are already resident in HBM
       noise = _tie_break_noise(tuple(int(v) for v in self.canvas.shape))
       with self.canvas._exec_client.engine_lock:         # pylint: disable=protected-access

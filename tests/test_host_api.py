@@ -299,3 +299,65 @@ def test_resegmentation_process_point_host_logic(tmp_path):
   end = np.load(tmp_path / ('%d-0_at_%d_%d_%d.npz' % (a, x, y, z)), allow_pickle=True)
   assert end['probs'].shape == (1, 81, 81, 81) and not made[1].segmentation.any()     # endpoint: everything cleared
   assert not os.path.exists(tmp_path / ('%d-999_at_%d_%d_%d.npz' % (a, x, y, z)))      # id not present: skipped
+
+
+def test_shift_mask_restriction_matches_reference(golden_dir):
+  """MovementRestrictor with a shift mask: the per-voxel movement mask handed to the device equals the
+  reference's own is_valid_pos at every position (fixture: tests/golden/make_golden_restrictor.py;
+  movement.py:247-336), for scales 1 / 2 / 4 and boxes that start outside the volume."""
+  from ffn.inference import movement
+  from ffn.utils import bounding_box
+  g = np.load(os.path.join(golden_dir, 'restrictor_shift.npz'))
+  informative = 0
+  for i in range(int(g['n'])):
+    fov = bounding_box.BoundingBox(start=g['fov_start_%d' % i], size=g['fov_size_%d' % i])
+    r = movement.MovementRestrictor(mask=g['mask_%d' % i], shift_mask=g['shift_%d' % i], shift_mask_fov=fov,
+                                    shift_mask_threshold=int(g['threshold_%d' % i]),
+                                    shift_mask_scale=int(g['scale_%d' % i]))
+    valid = g['valid_%d' % i]
+    np.testing.assert_array_equal(r.movement_mask(valid.shape), ~valid)
+    rng = np.random.RandomState(i)
+    for _ in range(50):
+      pos = tuple(int(rng.randint(0, d)) for d in valid.shape)
+      assert r.is_valid_pos(pos) == bool(valid[pos])
+    informative += 0.05 < valid.mean() < 0.95
+  assert informative >= 6
+  # without a shift mask the movement mask is the position mask itself
+  plain = movement.MovementRestrictor(mask=g['mask_0'])
+  np.testing.assert_array_equal(plain.movement_mask(g['mask_0'].shape), g['mask_0'])
+  assert movement.MovementRestrictor().movement_mask((3, 4, 5)) is None
+
+
+def test_runner_make_restrictor_with_shift_mask(tmp_path):
+  """Runner.make_restrictor (runner.py:218-305) crops the shift field of the subvolume at
+  `shift_mask_scale` resolution and the resulting movement mask blocks exactly the positions whose
+  default FoV box (the model's input size) contains a large shift."""
+  from ffn.inference import align, inference_pb2, inference_utils, runner as runner_mod
+  from ffn.training import model as ffn_model
+  vol_shape = (40, 64, 72)
+  scale = 2
+  shift = np.zeros((2, vol_shape[0], vol_shape[1] // scale, vol_shape[2] // scale), dtype=np.float32)
+  shift[1, 20, 12, 20] = 9.0                                  # one distorted patch: section 20, y ~ 24, x ~ 40
+  np.save(tmp_path / 'shift.npy', shift)
+  r = runner_mod.Runner()
+  r.request = inference_pb2.InferenceRequest()
+  r.request.shift_mask.hdf5 = '%s:shift' % (tmp_path / 'shift.npy')
+  r.request.shift_mask_scale = scale
+  r.request.shift_mask_threshold = 4
+  from ffn.inference import storage
+  r._shift_mask_volume = storage.decorated_volume(r.request.shift_mask)
+  r._model_info = ffn_model.ModelInfo(np.array([4, 4, 2]), np.array([17, 17, 9]), np.array([17, 17, 9]),
+                                      np.array([17, 17, 9]))
+  r.counters = inference_utils.Counters()
+  corner, size = np.array([8, 10, 14]), np.array([24, 40, 44])
+  restrictor = r.make_restrictor(corner, size, None, align.Alignment(corner, size))
+  assert restrictor.shift_mask.shape == (24, 20, 22) and restrictor.shift_mask.sum() == 1
+  mm = restrictor.movement_mask(tuple(size))
+  # blocked <=> the (9, 17, 17) box around the position covers section 20 and shift-mask pixel (12, 20)
+  z, y, x = np.indices(tuple(size))
+  gz, gy, gx = z + corner[0], y + corner[1], x + corner[2]
+  want = ((np.abs(gz - 20) <= 4) & ((np.maximum(y - 8, 0)) // scale + corner[1] // scale <= 12) &
+          ((y + 8) // scale + corner[1] // scale >= 12) &
+          ((np.maximum(x - 8, 0)) // scale + corner[2] // scale <= 20) & ((x + 8) // scale + corner[2] // scale >= 20))
+  np.testing.assert_array_equal(mm, want)
+  assert 0 < mm.sum() < mm.size

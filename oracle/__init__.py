@@ -11,7 +11,10 @@ Parity pinning status (see DESIGN.md "Oracle"):
 * flood-fill logic (Canvas.update_at/segment_at/segment_all, FaceMaxMovementPolicy,
   get_scored_move_offsets, quantize_probability, PolicyGrid3d): PINNED — checked against outputs of
   the reference's own Python modules imported in the build container with third-party stubs
-  (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``).
+  (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``); likewise the masked run (mask, seed_mask,
+  shift mask via MovementRestrictor), the anisotropic geometry of configs[4]
+  (``make_golden_masks.py``), Canvas.history / history_deleted (``make_golden_history.py``) and
+  MovementRestrictor.is_valid_pos at every voxel (``make_golden_restrictor.py``).
 * network arithmetic (TensorFlow Conv3D/BiasAdd/Relu via tf_slim, un-vendored and not
   installable offline): PARITY UNPINNED — restated with torch CPU ``conv3d`` from
   ffn/training/models/convstack_3d.py:26-56,83-95 and ffn/training/model.py:168-183; the only

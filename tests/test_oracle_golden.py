@@ -148,3 +148,35 @@ def test_oracle_history_matches_reference_keep_history(golden_dir):
   cv.segment_at(tuple(int(v) for v in h['second_start']))
   np.testing.assert_array_equal(np.asarray(cv.history, np.int32).reshape(-1, 3), h['second_history'])
   np.testing.assert_array_equal(np.asarray(cv.history_deleted, np.int64), h['second_history_deleted'])
+
+
+def test_toy_masked_flood_fill_bit_exact(golden_dir):
+  """segment_all behind a MovementRestrictor with mask, seed_mask and a shift mask — the reference's own
+  run (tests/golden/make_golden_masks.py).  The oracle (like the device) gets the shift rule folded into
+  the movement mask by ffn_b200's MovementRestrictor.movement_mask."""
+  from ffn_b200.inference import movement
+  from ffn_b200.utils import bounding_box
+  g = _load(golden_dir, 'toy_masks_flood_fill.npz')
+  restrictor = movement.MovementRestrictor(
+      mask=g['mask'], seed_mask=g['seed_mask'], shift_mask=g['shift'],
+      shift_mask_fov=bounding_box.BoundingBox(start=g['fov_start'], size=g['fov_size']),
+      shift_mask_threshold=int(g['shift_threshold']), shift_mask_scale=int(g['shift_scale']))
+  opts = ff.Options(min_segment_size=int(g['min_segment_size']),
+                    min_boundary_dist=tuple(int(v) for v in g['min_boundary_dist']))
+  canvas = ff.Canvas(toy_net, toy_image(g['cells']), (33, 33, 33), (8, 8, 8), opts,
+                     mask=restrictor.movement_mask(g['cells'].shape), seed_mask=g['seed_mask'])
+  canvas.segment_all(g['seeds'])
+  _check_canvas(canvas, g, exact_seed=True)
+  want = json.loads(str(g['counters']))
+  assert want['skip_restriced_pos'] > 0 and canvas.counters['skip_restriced_pos'] == want['skip_restriced_pos']
+
+
+def test_toy_anisotropic_flood_fill_bit_exact(golden_dir):
+  """fov (17, 33, 33), deltas (4, 8, 8) — the geometry of BASELINE configs[4] — against the reference."""
+  g = _load(golden_dir, 'toy_aniso_flood_fill.npz')
+  opts = ff.Options(min_segment_size=int(g['min_segment_size']),
+                    min_boundary_dist=tuple(int(v) for v in g['min_boundary_dist']))
+  canvas = ff.Canvas(toy_net, toy_image(g['cells']), (17, 33, 33), (4, 8, 8), opts)
+  canvas.segment_all(g['seeds'])
+  _check_canvas(canvas, g, exact_seed=True)
+  assert g['trace'].shape[0] > 100

@@ -361,3 +361,30 @@ def test_runner_make_restrictor_with_shift_mask(tmp_path):
           ((np.maximum(x - 8, 0)) // scale + corner[2] // scale <= 20) & ((x + 8) // scale + corner[2] // scale >= 20))
   np.testing.assert_array_equal(mm, want)
   assert 0 < mm.sum() < mm.size
+
+
+def test_bench_reference_arm_contract():
+  """`bench.py --impl reference` (the CPU restatement timed on the host cores) prints ONE JSON line with the
+  contract's keys; the GPU arm's extra objects are checked on the GPU box by the driver."""
+  import json
+  import subprocess
+  import sys
+  repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  res = subprocess.run([sys.executable, os.path.join(repo, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                        '--warmup', '1'], capture_output=True, text=True, timeout=600, cwd=repo)
+  assert res.returncode == 0, res.stderr[-2000:]
+  lines = [ln for ln in res.stdout.splitlines() if ln.startswith('{')]
+  assert len(lines) == 1
+  d = json.loads(lines[0])
+  assert d['impl'] == 'reference' and d['metric'] == 'fov_steps_per_sec' and d['higher_is_better'] is True
+  assert d['n_gpus'] == 1 and d['steps'] == 1 and d['warmup'] == 1 and d['value'] > 0
+  assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+  assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+  assert 'workload' in d['config'] and d['data'] == 'synthetic' and d['vs_baseline'] is None
+
+
+def test_bench_traffic_comes_from_committed_ncu_capture():
+  import bench
+  t = bench.ncu_dram_traffic()
+  assert t is not None and t['steps_per_launch'] == 16
+  assert 1e5 < t['bytes_per_step'] < 431244 * 2      # at most about the compulsory 431 KB/step (u8 image, L2 reuse)

@@ -167,6 +167,54 @@ __global__ void bulk_kernel(const unsigned char* src, int pieces, int piece_byte
   if (threadIdx.x == 0) cycles_out[blockIdx.x] = clock64() - t0;
 }
 
+// ---- variant 5: what does tcgen05.shift.down do? ------------------------------------------------
+// Lane l, column c of a 64-column TMEM block is filled with 1000 * c + l; after ONE
+// `tcgen05.shift.cta_group::1.down [base + col0]` every value is read back, so the host can tell which
+// lanes / columns moved (candidate for a shuffle-free epilogue: the dx taps of the stacked accumulator are
+// one row apart).  All waits bounded.
+__global__ void tmem_shift_probe_kernel(int col0, float* out) {
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    sm100::mbar_init(&bar, 1);
+    sm100::fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 0) sm100::tmem_alloc<64>(&tmem_slot);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int blk = 0; blk < 4; ++blk) {
+    uint32_t v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = __float_as_uint(1000.f * (float)(blk * 16 + k) + (float)tid);
+    sm100::tmem_st16(lane_base + blk * 16, v);
+  }
+  sm100::tmem_st_wait();
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  if (tid == 0) {
+    asm volatile("tcgen05.shift.cta_group::1.down [%0];" ::"r"(tmem + (uint32_t)col0) : "memory");
+    sm100::umma_commit(&bar);
+  }
+  __syncwarp();
+  bounded_wait(&bar, 0);
+  sm100::tc_fence_after();
+  for (int blk = 0; blk < 4; ++blk) {
+    uint32_t v[16];
+    sm100::tmem_ld16(lane_base + blk * 16, v);
+    sm100::tmem_ld_wait();
+    for (int k = 0; k < 16; ++k) out[(size_t)tid * 64 + blk * 16 + k] = __uint_as_float(v[k]);
+  }
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) sm100::tmem_dealloc<64>(tmem);
+}
+
 inline float host_half_round(float v) { return __half2float(__float2half_rn(v)); }
 
 #define ST_CUDA(expr)                                                                      \
@@ -321,6 +369,39 @@ inline int run(int device, int variant, double* out, int n_out, std::string* err
     out[1] = (double)pieces * piece;
     cudaFree(d_src);
     cudaFree(d_c);
+    return 0;
+  }
+  if (variant == 5) {
+    // out[0] = columns that changed, out[1] = first / out[2] = last changed column, out[3] = lanes that changed;
+    // out[4 + i] (i < 12): source lane now held by probe lane {0,1,2,31,32,33,63,64,65,96,126,127}[i] in the
+    // first changed column (-1: unchanged pattern not recognised)
+    if (n_out < 16) {
+      *err = "need 16 output slots";
+      return 1;
+    }
+    float* d_o = nullptr;
+    ST_CUDA(cudaMalloc(&d_o, 128 * 64 * 4));
+    ST_CUDA(cudaMemset(d_o, 0, 128 * 64 * 4));
+    tmem_shift_probe_kernel<<<1, 128>>>(0, d_o);
+    ST_CUDA(cudaGetLastError());
+    ST_CUDA(cudaDeviceSynchronize());
+    std::vector<float> o(128 * 64);
+    ST_CUDA(cudaMemcpy(o.data(), d_o, o.size() * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_o);
+    int first = -1, last = -1, ncols = 0, nlanes = 0;
+    for (int c = 0; c < 64; ++c) {
+      bool changed = false;
+      for (int l = 0; l < 128; ++l) changed |= o[(size_t)l * 64 + c] != 1000.f * c + l;
+      if (changed) {
+        if (first < 0) first = c;
+        last = c;
+        ++ncols;
+      }
+    }
+    const int probe[12] = {0, 1, 2, 31, 32, 33, 63, 64, 65, 96, 126, 127};
+    for (int l = 0; l < 128 && first >= 0; ++l) nlanes += o[(size_t)l * 64 + first] != 1000.f * first + l;
+    out[0] = ncols; out[1] = first; out[2] = last; out[3] = nlanes;
+    for (int i = 0; i < 12; ++i) out[4 + i] = first >= 0 ? (double)(o[(size_t)probe[i] * 64 + first] - 1000.f * first) : -1.0;
     return 0;
   }
   *err = "unknown selftest variant";

@@ -25,7 +25,7 @@ from ffn_b200 import _lib, engine as eng, tf_checkpoint
 w, b = tf_checkpoint.load_convstack_npz(os.path.join(G, 'fib25_convstack.npz'))
 which = sys.argv[1:] or ['selftest', 'fp32', 'tc']
 
-for v, nm in ((0, 'kat'), (1, 'rate_1cta'), (4, 'rate_allsm'), (2, 'barrier'), (3, 'bulk')):
+for v, nm in ((0, 'kat'), (1, 'rate_1cta'), (4, 'rate_allsm'), (2, 'barrier'), (3, 'bulk'), (5, 'tmem_shift')):
   if 'selftest%d' % v in which:
     @stage('selftest_' + nm)
     def _():

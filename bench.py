@@ -293,7 +293,7 @@ def main():
   ap.add_argument('--steps', type=int, default=256)
   ap.add_argument('--warmup', type=int, default=8)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-  ap.add_argument('--compute', default='fp16', choices=['fp16', 'fp32'])
+  ap.add_argument('--compute', default='fp16', choices=['fp16', 'fp32', 'x2'])
   ap.add_argument('--cpu-baseline-steps', type=int, default=24)
   ap.add_argument('--skip-extras', action='store_true', help='no throughput_mode / cpu_baseline legs (profiler runs)')
   args = ap.parse_args()
@@ -316,7 +316,7 @@ def main():
   from ffn_b200 import _lib
   from ffn_b200 import engine as eng
   (w, b), wdesc = load_weights()
-  mode = _lib.COMPUTE_FP16_TC if args.compute == 'fp16' else _lib.COMPUTE_FP32
+  mode = {'fp16': _lib.COMPUTE_FP16_TC, 'fp32': _lib.COMPUTE_FP32, 'x2': _lib.COMPUTE_FP16X2_TC}[args.compute]
   engine = eng.Engine(w, b, FOV, DELTAS, device=local_rank, compute_mode=mode)
   vol = make_volume(1 + rank)
   pts = seed_points(vol, 256)
@@ -397,7 +397,7 @@ def main():
         'metric': 'fov_steps_per_sec', 'value': value, 'unit': 'FoV steps/s', 'n_gpus': world,
         'steps': int(steps_done), 'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * dev_seconds / steps_done,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f16' if args.compute == 'fp16' else 'f32', 'data': 'synthetic',
+        'dtype': {'fp16': 'f16', 'fp32': 'f32', 'x2': 'f16x2 (hi+lo split, ~f32)'}[args.compute], 'data': 'synthetic',
         'config': {
             'workload': 'configs[1]: single-seed flood-fill, depth 12 fov 33^3 deltas 8, synthetic 256^3 per GPU',
             'weights': wdesc, 'volume_seed': '1 + rank', 'accumulate': 'f32',

@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get('FFN_B200_LIB') or os.path.join(HERE, 'libffn_b200.so'
 
 COMPUTE_FP16_TC = 0
 COMPUTE_FP32 = 1
+COMPUTE_FP16X2_TC = 2   # fp16 hi+lo split operands on the tensor cores: near-fp32, label-exact parity mode
 IMAGE_U8 = 0
 IMAGE_F32 = 1
 ARRAY_SEED = 0

@@ -24,6 +24,9 @@ constexpr int kStackN = 96;       // UMMA N: the three dx taps of a (dz, dy) tap
 constexpr int kFeat = 32;         // feature maps of every hidden layer (UMMA N)
 constexpr int kGroupTiles = 3;    // accumulator slots in TMEM (the residual stream starts behind them)
 constexpr int kMaxConv = 32;      // 2 * depth limit
+constexpr int kMaxChains = 3;     // flood-fill chains (objects in flight) time-multiplexed over the SMs of one kernel
+constexpr int kSplitShift = 10;   // FFN_COMPUTE_FP16X2_TC: weights are split as w * 2^10 = hi + lo (keeps lo a normal fp16
+                                  // number for |w| down to ~1e-4); the epilogue scales the accumulators back (exact)
 constexpr int kTmemCols = 512;    // accumulators (kGroupTiles * kStackN columns) + fp32 residual stream (32 per tile)
 constexpr int kMaxTilesPerCta = (kTmemCols - kGroupTiles * kStackN) / kFeat;   // 7: bound by the TMEM-resident residual
 
@@ -53,22 +56,21 @@ struct Geom {
 struct Weights {
   const __half* w16;   // per layer [9 tap-rows][kchunk][12 n-groups][8 n][8 k] fp16 (UMMA K-major, no swizzle),
                        // n = dx * 32 + cout
+  const __half* w16x2; // FFN_COMPUTE_FP16X2_TC: per layer the same packing twice, [hi | lo] parts of w * 2^kSplitShift
   const float* w32;    // per layer [27][cin_padded][32] fp32
   const float* bias;   // [nconv][32]
   const float* w_lom;  // [32]
   float b_lom;
 };
 
+// Buffers shared by all chains (the fp32 / split-fp16 parity modes run one chain at a time).
 struct Workspace {
-  __half* act0_h;      // [2][rows_alloc][8] (chunk 1 stays zero)
-  __half* act_h[2];    // [4][rows_alloc][8]
+  __half* act0_l;      // fp16 lo parts (FFN_COMPUTE_FP16X2_TC): x = hi + lo with hi = fp16(x), lo = fp16(x - hi)
+  __half* act_l[2];
   float4* act0_f;      // [1][rows_alloc]  (image, seed, 0, 0)
   float4* act_f[2];    // [8][rows_alloc]
-  float4* res;         // [8][rows_alloc] fp32 residual stream
-  float* seed_raw;     // [nt*128] seed FoV as read from the canvas (NaN preserved)
-  float* logits;       // [nt*128] network output (seed + update), before the disco merge
+  float4* res;         // [8][rows_alloc] fp32 residual stream (fp32 mode)
   unsigned* bar;       // grid barrier counter
-  unsigned* count;     // [2] current step: voxels with logit >= move threshold; Canvas.history_deleted
   int* abort_flag;     // != 0: a wait timed out, everybody bails
   long long* prof;     // [2][16] cycle counters of CTA 0 and CTA G-1 (debug/profiling)
 };
@@ -77,7 +79,6 @@ struct CanvasDev {
   const void* image;
   int image_is_u8;
   float mean, stddev;
-  float* seed;
   int* seg;
   uint8_t* qprob;             // may be null
   const uint8_t* mask;        // may be null
@@ -85,14 +86,30 @@ struct CanvasDev {
   int sz, sy, sx;
   FfnOptions opt;
   float policy_th_f32;        // smallest float32 >= opt.policy_score_threshold
-  // movement policy storage
-  float* q_score;
-  int* q_pos;                 // [cap][3]
-  int q_cap;
-  unsigned* lattice;          // epoch stamps over the quantised lattice
+  int q_cap;                  // capacity of every chain's FIFO
+  int traj_cap;               // capacity of every chain's trajectory log
   int* trace;                 // optional event log [cap][4]: (type, z, y, x); null = off
   int trace_cap;
   int lat_dim[3], lat_off[3];
+};
+
+// One flood-fill chain: the private state of ONE object in flight (what the reference keeps in Canvas.seed and
+// the FaceMaxMovementPolicy object) plus the step workspace of its FoV.  Chain 0 owns the canvas's own seed
+// array; chains 1.. grow objects speculatively in private seed arrays (see Sched).
+struct CanvasState;
+struct ChainDev {
+  float* seed;                // seed canvas of this chain (NaN = unvisited)
+  float* q_score;             // movement policy FIFO
+  int* q_pos;                 // [cap][3]
+  unsigned* lattice;          // epoch stamps over the quantised lattice (done set)
+  int* traj;                  // [traj_cap][3] FoV positions of the object in flight (speculation check)
+  CanvasState* st;
+  __half* act0_h;             // [2][rows_alloc][8] (chunk 1 stays zero)
+  __half* act_h[2];           // [4][rows_alloc][8]
+  float* seed_raw[2];         // [nt*128] seed FoV as read from the canvas (NaN preserved), by round parity
+  float* logits;              // [nt*128] network output (seed + update), before the disco merge
+  unsigned* count;            // [2 round parities][2]: voxels with logit >= move threshold; Canvas.history_deleted
+  unsigned* bar;              // split-phase barrier of this chain: arrivals of the epilogue groups
 };
 
 enum Phase : int {
@@ -107,6 +124,8 @@ enum Phase : int {
   PH_SEGMENT_DONE,
   PH_ALL_DONE,
   PH_FORCE_STEP,       // update_at: run exactly one step at `cur`
+  PH_FINISHED,         // segment_all: the object's flood fill ended; waits for its pastes to land / for its turn to commit
+  PH_FREE,             // segment_all: chain has no object (asks the scheduler for a seed every round)
 };
 
 // Persistent per-canvas state (global memory) — what the reference keeps in the Canvas and
@@ -121,25 +140,55 @@ struct CanvasState {
   int min_pos[3], max_pos[3];
   long long iters;            // steps of the current object
   int dirty_lo[3], dirty_hi[3];   // box of the seed canvas that may hold non-NaN values (hi exclusive)
-  long long seed_idx;
-  int max_id;
+  long long seed_index;       // segment_all: index (into the seed list) of the object in flight, -1: restored from a checkpoint
+  int spec;                   // segment_all: the object was started ahead of its turn (speculatively)
+  int fin_round;              // round in which the object finished (its last paste is visible one round later)
   int reset_seed;             // segment_at: init_seed before starting
   int seg_all;                // 1: segment_all mode, 0: segment_at mode
   int weak;                   // last object ended by 'seed_got_too_weak'
+  int popped, pop_run, pop_pos[3];   // leader scratch: queue already popped for this round (phase A)
   // commit scratch
   int box_lo[3], box_hi[3];
   unsigned long long cnt_raw, cnt_actual;
   int cur_sid;
   int n_touched;
   unsigned long long seg_t0;  // globaltimer at segment start
-  long long n_origins, n_overlaps;
-  int overflow;               // origins / overlaps / queue capacity exceeded
+  int overflow;               // queue / trajectory capacity exceeded
   int n_trace;                // events written to the trace log
-  FfnCounters ctr;
+  FfnCounters ctr;            // segment_at / update_at: cumulative; segment_all: counters of the object in flight
+};
+
+// Canvas-wide state of segment_all.  The reference processes seeds strictly one after the other
+// (inference.py:538-683).  Here up to kMaxChains objects are in flight: the one whose turn it is (`owner`,
+// holding seed `commit_idx`) and objects started AHEAD of their turn in private seed arrays.  An object's
+// flood fill reads shared state only through `segmentation > 0` tests (inference.py:341,573-581,635), labels
+// are only ever added, and every label is written at commit time, in seed order.  So an early run is exactly
+// the run the reference would have done iff, when its turn comes, (a) the in-order seed gating still accepts
+// the seed and (b) no FoV position it stepped on has been labelled meanwhile; otherwise it is discarded and
+// redone in turn.  Results (labels, ids, origins, overlaps, counters) are therefore identical to the
+// sequential order, for any number of chains and any choice of early seeds.
+struct Sched {
+  long long commit_idx;       // seeds [0, commit_idx) are final
+  int owner;                  // chain holding seed commit_idx (or the restored in-flight object); -1: none
+  int nchains;
+  int max_id;
+  int overflow;               // 1: queue, 2: overlaps, 4: origins, 8: trajectory
+  long long n_origins, n_overlaps;
+  long long steps_executed;   // FoV steps run, incl. early runs that were discarded
+  long long spec_runs, spec_discarded, spec_steps_discarded;
+  unsigned round;             // rounds completed (all launches)
+  int all_done;
+  FfnCounters ctr;            // committed counters (== the reference's)
+};
+
+// Leader -> every CTA, once per round.
+struct Ctl {
+  int action[kMaxChains];
+  int pos[kMaxChains][3];
 };
 
 enum Mode : int { MODE_PREDICT = 0, MODE_UPDATE_AT = 1, MODE_SEGMENT = 2 };
-enum Action : int { ACT_EXIT = 0, ACT_STEP, ACT_CLEAR, ACT_COUNT, ACT_WRITE };
+enum Action : int { ACT_EXIT = 0, ACT_STEP, ACT_CLEAR, ACT_COUNT, ACT_WRITE, ACT_IDLE };
 
 struct Job {
   int mode;
@@ -162,7 +211,7 @@ struct Job {
   int* ovl_count;      // [ovl_ids]
   int* ovl_touched;    // [ovl_ids]
   int ovl_ids;
-  int* action;         // broadcast slot written by the leader
+  unsigned char* seed_status;   // [n_seeds] 0: not started, 1: taken by a chain
 };
 
 struct KParams {
@@ -170,7 +219,11 @@ struct KParams {
   Weights w;
   Workspace ws;
   CanvasDev cv;
-  CanvasState* st;
+  int nchains;
+  ChainDev ch[kMaxChains];
+  Sched* sched;
+  Ctl* ctl;
+  unsigned* round_flag;   // rounds published by the leader (release / acquire)
   Job job;
   int compute_mode;
   int act_smem_bytes;   // 3 * 4 * seg_rows_max * 16
@@ -193,7 +246,7 @@ __host__ __device__ inline SmemLayout smem_layout(const Geom& g) {
   const int act_bytes = kActStages * 3 * 4 * seg_rows * 16;
   s.bias = s.act + act_bytes;
   s.bars = s.bias + (kMaxConv + 1) * 32 * 4 + 16;
-  s.total = s.bars + 4096 + 512;    // barriers/misc | prof | epilogue exchange + conv_lom dots | leader's state copy
+  s.total = s.bars + 4096 + 2560;   // barriers/misc | prof | epilogue exchange + conv_lom dots | leader's chain-state / scheduler copies
   return s;
 }
 

@@ -71,6 +71,11 @@ struct FfnEngine {
   double last_kernel_seconds = 0.0;
   bool profiling = false;
   long long launches = 0;
+  // Lifetime: canvases hold a raw pointer to their engine.  ffn_engine_destroy with canvases still alive
+  // only marks the engine as closing — it stays fully usable through those canvases (reading results after
+  // Runner.stop_executor() is the common case) — and the last ffn_canvas_destroy releases it.
+  int live_canvases = 0;
+  bool closing = false;
 };
 
 struct FfnCanvas {
@@ -94,6 +99,18 @@ using namespace ffn;
 int set_device(const FfnEngine* e) {
   CUDA_OK(cudaSetDevice(e->device));
   return 0;
+}
+
+void engine_free(FfnEngine* e) {
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (void* p : e->owned) cudaFree(p);
+  cudaFree(e->d_in_seed);
+  cudaFree(e->d_in_image);
+  cudaFree(e->d_out);
+  cudaEventDestroy(e->ev0);
+  cudaEventDestroy(e->ev1);
+  delete e;
 }
 
 Geom make_geom(const FfnModelDesc& m) {
@@ -164,15 +181,19 @@ int push_state(FfnCanvas* c) {
   return 0;
 }
 
-void pack_weights(const Geom& g, const float* const* w, std::vector<__half>& w16, std::vector<float>& w32) {
+void pack_weights(const Geom& g, const float* const* w, std::vector<__half>& w16, std::vector<__half>& w16x2,
+                  std::vector<float>& w32) {
   const int nconv = g.nconv;
   w16.assign(w16_layer_offset_halfs(nconv), __float2half(0.f));
+  w16x2.assign(2 * w16_layer_offset_halfs(nconv), __float2half(0.f));
   w32.assign(w32_layer_offset_floats(nconv), 0.f);
   for (int l = 0; l < nconv; ++l) {
     const int cin = l == 0 ? 2 : 32;
     const int nch = l == 0 ? 2 : 4;
     const int cin_pad = l == 0 ? 4 : 32;
     __half* d16 = w16.data() + w16_layer_offset_halfs(l);
+    __half* d16hi = w16x2.data() + 2 * w16_layer_offset_halfs(l);
+    __half* d16lo = d16hi + (w16_layer_offset_halfs(l + 1) - w16_layer_offset_halfs(l));
     float* d32 = w32.data() + w32_layer_offset_floats(l);
     for (int tap = 0; tap < 27; ++tap)
       for (int ci = 0; ci < cin; ++ci)
@@ -180,7 +201,14 @@ void pack_weights(const Geom& g, const float* const* w, std::vector<__half>& w16
           const float v = w[l][((size_t)tap * cin + ci) * 32 + co];   // DHWIO: tap = kz*9 + ky*3 + kx
           {
             const int row = tap / 3, n = (tap % 3) * 32 + co;   // tap-row (kz, ky); n stacks kx
-            d16[(((size_t)row * nch + ci / 8) * 12 + n / 8) * 64 + (n % 8) * 8 + (ci % 8)] = __float2half_rn(v);
+            const size_t at = (((size_t)row * nch + ci / 8) * 12 + n / 8) * 64 + (n % 8) * 8 + (ci % 8);
+            d16[at] = __float2half_rn(v);
+            // split mode: w * 2^kSplitShift = hi + lo (the scaling is exact and keeps lo out of the fp16
+            // subnormal range; the epilogue multiplies the accumulators by 2^-kSplitShift)
+            const float vs = v * (float)(1 << kSplitShift);
+            const __half h = __float2half_rn(vs);
+            d16hi[at] = h;
+            d16lo[at] = __float2half_rn(vs - __half2float(h));
           }
           d32[((size_t)tap * cin_pad + ci) * 32 + co] = v;
         }
@@ -281,10 +309,14 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
                 " tiles per SM: the TMEM-resident residual stream does not fit (too few SMs for this FoV)");
 
   // weights
-  std::vector<__half> w16;
+  std::vector<__half> w16, w16x2;
   std::vector<float> w32;
-  pack_weights(g, weights_dhwio, w16, w32);
+  pack_weights(g, weights_dhwio, w16, w16x2, w32);
   __half* d_w16 = nullptr;
+  __half* d_w16x2 = nullptr;
+  if (dev_alloc(&d_w16x2, w16x2.size())) return 1;
+  CUDA_OK(cudaMemcpy(d_w16x2, w16x2.data(), w16x2.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  e->w.w16x2 = d_w16x2;
   float *d_w32 = nullptr, *d_bias = nullptr, *d_wlom = nullptr;
   if (dev_alloc(&d_w16, w16.size())) return 1;
   if (dev_alloc(&d_w32, w32.size())) return 1;
@@ -301,7 +333,7 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   e->w.bias = d_bias;
   e->w.w_lom = d_wlom;
   e->w.b_lom = biases[g.nconv][0];
-  e->owned = {d_w16, d_w32, d_bias, d_wlom};
+  e->owned = {d_w16, d_w16x2, d_w32, d_bias, d_wlom};
 
   // workspace (all buffers zero-initialised: pad rows / guards must stay zero forever)
   Workspace& ws = e->ws;
@@ -309,6 +341,9 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   if (dev_alloc(&ws.act0_h, 2 * ra * 8)) return 1;
   if (dev_alloc(&ws.act_h[0], 4 * ra * 8)) return 1;
   if (dev_alloc(&ws.act_h[1], 4 * ra * 8)) return 1;
+  if (dev_alloc(&ws.act0_l, 2 * ra * 8)) return 1;
+  if (dev_alloc(&ws.act_l[0], 4 * ra * 8)) return 1;
+  if (dev_alloc(&ws.act_l[1], 4 * ra * 8)) return 1;
   if (dev_alloc(&ws.act0_f, ra)) return 1;
   if (dev_alloc(&ws.act_f[0], 8 * ra)) return 1;
   if (dev_alloc(&ws.act_f[1], 8 * ra)) return 1;
@@ -321,7 +356,7 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   if (dev_alloc(&ws.prof, 32)) return 1;
   if (dev_alloc(&e->d_action, 1)) return 1;
   if (dev_alloc(&e->d_dummy_state, 1)) return 1;
-  for (void* p : std::vector<void*>{ws.act0_h, ws.act_h[0], ws.act_h[1], ws.act0_f, ws.act_f[0], ws.act_f[1],
+  for (void* p : std::vector<void*>{ws.act0_h, ws.act_h[0], ws.act_h[1], ws.act0_l, ws.act_l[0], ws.act_l[1], ws.act0_f, ws.act_f[0], ws.act_f[1],
                                     ws.res, ws.seed_raw, ws.logits, ws.bar, ws.count, ws.abort_flag, ws.prof,
                                     e->d_action, e->d_dummy_state})
     e->owned.push_back(p);
@@ -330,16 +365,12 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
 }
 
 void ffn_engine_destroy(FfnEngine* e) {
-  if (!e) return;
-  cudaSetDevice(e->device);
-  cudaDeviceSynchronize();
-  for (void* p : e->owned) cudaFree(p);
-  cudaFree(e->d_in_seed);
-  cudaFree(e->d_in_image);
-  cudaFree(e->d_out);
-  cudaEventDestroy(e->ev0);
-  cudaEventDestroy(e->ev1);
-  delete e;
+  if (!e || e->closing) return;
+  if (e->live_canvases > 0) {   // canvases outlive the engine: defer the release to the last of them
+    e->closing = true;
+    return;
+  }
+  engine_free(e);
 }
 
 int ffn_engine_set_grid(FfnEngine* e, int num_ctas) {
@@ -354,7 +385,8 @@ int ffn_engine_set_grid(FfnEngine* e, int num_ctas) {
 
 int ffn_engine_set_compute_mode(FfnEngine* e, int mode) {
   if (!e) return fail("null engine");
-  if (mode != FFN_COMPUTE_FP16_TC && mode != FFN_COMPUTE_FP32) return fail("unknown compute mode");
+  if (mode != FFN_COMPUTE_FP16_TC && mode != FFN_COMPUTE_FP32 && mode != FFN_COMPUTE_FP16X2_TC)
+    return fail("unknown compute mode");
   e->compute_mode = mode;
   return 0;
 }
@@ -479,13 +511,15 @@ int ffn_canvas_create(FfnEngine* e, const void* image, int image_dtype, const in
   }
   if (push_state(c.get())) return 1;
   CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
+  e->live_canvases++;
   *out = c.release();
   return 0;
 }
 
 void ffn_canvas_destroy(FfnCanvas* c) {
   if (!c) return;
-  cudaSetDevice(c->eng->device);
+  FfnEngine* e = c->eng;
+  cudaSetDevice(e->device);
   cudaFree(c->d_image);
   cudaFree(c->cv.seed);
   cudaFree(c->cv.seg);
@@ -499,6 +533,7 @@ void ffn_canvas_destroy(FfnCanvas* c) {
   cudaFree(c->d_mask);
   cudaFree(c->d_seed_mask);
   delete c;
+  if (--e->live_canvases == 0 && e->closing) engine_free(e);
 }
 
 int ffn_canvas_set_mask(FfnCanvas* c, int which, const uint8_t* mask) {

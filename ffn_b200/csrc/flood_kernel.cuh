@@ -196,12 +196,18 @@ __device__ __forceinline__ void stage_fov(Ctx& c, int pz, int py, int px, int ba
       fed = isnan(s) ? p.cv.opt.pad_value : s;
     }
     p.ws.seed_raw[r] = predict ? fed : s;
-    if (p.compute_mode == FFN_COMPUTE_FP16_TC) {
+    if (p.compute_mode != FFN_COMPUTE_FP32) {
       const __half2 h01 = __floats2half2_rn(img, fed);
       uint4 v;
       v.x = *reinterpret_cast<const uint32_t*>(&h01);
       v.y = v.z = v.w = 0u;
       *reinterpret_cast<uint4*>(p.ws.act0_h + ((size_t)g.guard + r) * 8) = v;
+      if (p.compute_mode == FFN_COMPUTE_FP16X2_TC) {   // lo parts: x - fp16(x), exact in fp32
+        const float2 hf = __half22float2(h01);
+        const __half2 l01 = __floats2half2_rn(img - hf.x, fed - hf.y);
+        v.x = *reinterpret_cast<const uint32_t*>(&l01);
+        *reinterpret_cast<uint4*>(p.ws.act0_l + ((size_t)g.guard + r) * 8) = v;
+      }
     } else {
       p.ws.act0_f[(size_t)g.guard + r] = make_float4(img, fed, 0.f, 0.f);
     }
@@ -346,16 +352,18 @@ __device__ __forceinline__ void quad_sync(int quad) {   // the four epilogue war
 // down, done with warp shuffles (+ a 2 KB shared-memory exchange at the three warp boundaries).
 enum EpiKind : int { EPI_A = 0, EPI_B_FIRST = 1, EPI_B = 2, EPI_LAST = 3 };
 
-template <int KIND>
+template <int KIND, bool X2 = false>
 __device__ __forceinline__ int tc_epilogue(Ctx& c, int layer, int ntiles) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
+  constexpr float kUnscale = 1.0f / (float)(1 << kSplitShift);   // X2: accumulators carry w * 2^kSplitShift
   constexpr bool kReadRes = KIND == EPI_B || KIND == EPI_LAST;
   constexpr bool kWriteRes = KIND == EPI_B_FIRST || KIND == EPI_B;
   const int half = c.warp >> 2, wq = c.warp & 3;
   const float4* bias4 = reinterpret_cast<const float4*>(c.s_bias + layer * 32 + half * 16);   // re-read per tile: 16 registers less
   const size_t chunk_stride = (size_t)g.rows_alloc * 8;
   __half* out_base = p.ws.act_h[layer & 1] + (size_t)(half * 2) * chunk_stride + (size_t)g.guard * 8;
+  __half* out_lo_base = X2 ? p.ws.act_l[layer & 1] + (size_t)(half * 2) * chunk_stride + (size_t)g.guard * 8 : nullptr;
   int hit = 0;
   for (int j = 0; j < ntiles; ++j) {
     const int slot = c.epi_cnt % kAccSlots;
@@ -430,7 +438,8 @@ __device__ __forceinline__ int tc_epilogue(Ctx& c, int layer, int ntiles) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int k = 4 * i + e;
-        v[k] = fmaf(up[k], m_up, fmaf(dn[k], m_dn, __uint_as_float(b[k]))) + bias[e];
+        const float acc = fmaf(up[k], m_up, fmaf(dn[k], m_dn, __uint_as_float(b[k])));
+        v[k] = X2 ? fmaf(acc, kUnscale, bias[e]) : acc + bias[e];
         if (kReadRes) v[k] += __uint_as_float(rr[k]);
       }
     }
@@ -452,6 +461,17 @@ __device__ __forceinline__ int tc_epilogue(Ctx& c, int layer, int ntiles) {
           o.z = sm100::cvt_relu_f16x2(v[8 * q + 4], v[8 * q + 5]);
           o.w = sm100::cvt_relu_f16x2(v[8 * q + 6], v[8 * q + 7]);
           *reinterpret_cast<uint4*>(dst + q * chunk_stride) = o;
+          if (X2) {   // lo parts of relu(v): relu(v) - fp16(relu(v)) is exact in fp32
+            const uint32_t hi[4] = {o.x, o.y, o.z, o.w};
+            uint32_t lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[e]));
+              const __half2 l = __floats2half2_rn(fmaxf(v[8 * q + 2 * e], 0.f) - hf.x, fmaxf(v[8 * q + 2 * e + 1], 0.f) - hf.y);
+              lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            *reinterpret_cast<uint4*>(out_lo_base + (size_t)r * 8 + q * chunk_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
         }
       }
     } else {
@@ -588,6 +608,116 @@ __device__ __forceinline__ void tc_layer(Ctx& c, int layer) {
   if (c.tid == 0) prof_add(c, 11, prof_now(c) - t_layer);
 }
 
+// Near-fp32 tensor-core layer (FFN_COMPUTE_FP16X2_TC): activations and weights are both split into fp16
+// hi + lo parts and every (tap-row, k-pair) becomes THREE UMMAs into the same fp32 accumulator,
+//   a * w  ~=  a_hi * w_hi + a_lo * w_hi + a_hi * w_lo        (the dropped a_lo * w_lo term is ~2^-22 relative),
+// which gives ~22 significant bits per product.  Same roles and barriers as tc_layer; shared memory is
+// used differently: activation stage 0 holds the hi parts and stage 1 the lo parts of ONE tile, weight
+// buffer 0 holds w_hi and buffer 1 w_lo of THIS layer (so there is no cross-layer weight prefetch and no
+// tile double-buffering: this is the label-exact parity mode, not the throughput mode).
+__device__ __forceinline__ void tc_layer_x2(Ctx& c, int layer) {
+  const KParams& p = *c.p;
+  const Geom& g = p.g;
+  const int nch = layer == 0 ? 2 : 4;
+  const __half* in_hi = layer == 0 ? p.ws.act0_h : p.ws.act_h[(layer - 1) & 1];
+  const __half* in_lo = layer == 0 ? p.ws.act0_l : p.ws.act_l[(layer - 1) & 1];
+  unsigned char* act_smem = c.smem + 2 * 27 * 4 * 512;
+  const int seg_rows = kTileOut + 2 * g.halo;
+  const int stage_bytes = 3 * 4 * seg_rows * 16;
+  const int ntiles = c.t_end - c.t_begin;
+  const bool last = layer == g.nconv - 1;
+  int hit = 0;
+  bit_set(c, 8, true);
+  if (c.warp == kLoadWarp) {
+    sm100::fence_proxy_async_global();
+    if (sm100::elect_one()) {
+      // both halves of this layer's weights; every UMMA of the previous layer has completed (its
+      // epilogue waited for the accumulators), so the buffers are free
+      const uint32_t wbytes = (uint32_t)(27 * nch * 512);
+      const __half* src = p.w.w16x2 + 2 * w16_layer_offset_halfs(layer);
+      sm100::mbar_expect_tx(&c.mb_w[0], 2 * wbytes);
+      sm100::bulk_g2s(c.smem, src, wbytes, &c.mb_w[0]);
+      sm100::bulk_g2s(c.smem + 27 * 4 * 512, src + wbytes / 2, wbytes, &c.mb_w[0]);
+    }
+    __syncwarp();
+    for (int j = 0; j < ntiles; ++j) {
+      if (j > 0) mbar_wait(c, &c.mb_empty[0], (c.load_cnt & 1u) ^ 1u);
+      const int r0 = (c.t_begin + j) * kTileOut;
+      if (sm100::elect_one()) {
+        sm100::mbar_expect_tx(&c.mb_full[0], (uint32_t)(2 * 3 * nch * seg_rows * 16));
+        for (int part = 0; part < 2; ++part) {
+          const __half* in = part ? in_lo : in_hi;
+          unsigned char* dst = act_smem + (size_t)part * stage_bytes;
+          for (int dzi = 0; dzi < 3; ++dzi)
+            for (int ch = 0; ch < nch; ++ch)
+              sm100::bulk_g2s(dst + (size_t)(dzi * nch + ch) * seg_rows * 16,
+                              in + ((size_t)ch * g.rows_alloc + g.guard + r0 + (dzi - 1) * g.pp - g.halo) * 8,
+                              (uint32_t)seg_rows * 16, &c.mb_full[0]);
+        }
+      }
+      __syncwarp();
+      ++c.load_cnt;
+    }
+  } else if (c.warp == kMmaWarp) {
+    mbar_wait(c, &c.mb_w[0], bit_get(c, 0));
+    const uint32_t idesc = sm100::umma_idesc_f16(kTileM, kStackN);
+    const uint64_t hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+    const uint32_t bw_hi = ((sm100::smem_u32(c.smem) >> 4) & 0x3FFFu) | ((12u * 128u >> 4) << 16);
+    const uint32_t bw_lo = ((sm100::smem_u32(c.smem + 27 * 4 * 512) >> 4) & 0x3FFFu) | ((12u * 128u >> 4) << 16);
+    const uint32_t aa_hi = ((sm100::smem_u32(act_smem) >> 4) & 0x3FFFu) | ((uint32_t)seg_rows << 16);
+    const uint32_t aa_lo = ((sm100::smem_u32(act_smem + stage_bytes) >> 4) & 0x3FFFu) | ((uint32_t)seg_rows << 16);
+    for (int j = 0; j < ntiles; ++j) {
+      const int slot = c.mma_cnt % kAccSlots;
+      mbar_wait(c, &c.mb_full[0], c.mma_cnt & 1u);
+      if (j >= kAccSlots) mbar_wait(c, &c.mb_tempty[slot], ((c.mma_cnt / kAccSlots) & 1u) ^ 1u);
+      sm100::tc_fence_after();
+      const uint32_t d = c.tmem_base + (uint32_t)(slot * kStackN);
+      if (sm100::elect_one()) {
+        // The tensor core truncates when it aligns an MMA's sum to the accumulator, so the error of every
+        // accumulation scales with the accumulator's magnitude: the small cross terms (a_lo*w_hi, a_hi*w_lo,
+        // ~2^-11 of the result) go in FIRST, while the accumulator is small, the 9*nch/2 main MMAs last.
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+          for (int row = 0; row < 9; ++row) {
+            const int tz = row / 3, ty = row % 3;
+            for (int jj = 0; jj < nch / 2; ++jj) {
+              const uint32_t aoff = (uint32_t)((tz * nch + 2 * jj) * seg_rows + ty * g.xp);
+              const uint32_t boff = (uint32_t)((row * nch + 2 * jj) * (12 * 128 / 16));
+              if (pass == 0) {
+                sm100::umma_f16(d, hi | (uint64_t)(aa_lo + aoff), hi | (uint64_t)(bw_hi + boff), idesc, (row | jj) != 0 ? 1u : 0u);
+                sm100::umma_f16(d, hi | (uint64_t)(aa_hi + aoff), hi | (uint64_t)(bw_lo + boff), idesc, 1u);
+              } else {
+                sm100::umma_f16(d, hi | (uint64_t)(aa_hi + aoff), hi | (uint64_t)(bw_hi + boff), idesc, 1u);
+              }
+            }
+          }
+        }
+        sm100::umma_commit(&c.mb_tfull[slot]);
+        sm100::umma_commit(&c.mb_empty[0]);
+      }
+      __syncwarp();
+      ++c.mma_cnt;
+    }
+  } else {
+    if (last) {
+      hit = tc_epilogue<EPI_LAST, true>(c, layer, ntiles);
+    } else if (!(layer & 1)) {
+      tc_epilogue<EPI_A, true>(c, layer, ntiles);
+    } else if (layer == 1) {
+      tc_epilogue<EPI_B_FIRST, true>(c, layer, ntiles);
+    } else {
+      tc_epilogue<EPI_B, true>(c, layer, ntiles);
+    }
+  }
+  bit_flip(c, 0);
+  bit_set(c, 8, false);
+  if (last) {
+    hit = __reduce_add_sync(0xffffffffu, hit);
+    if (c.lane == 0 && hit) atomicAdd(&c.s_misc[0], hit);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // fp32 layer ("precise" parity mode): one thread per FoV row, 32 accumulators, weights
 // broadcast from shared memory, activations through L1.
@@ -653,6 +783,8 @@ __device__ __forceinline__ void run_network(Ctx& c) {
   for (int layer = 0; layer < p.g.nconv; ++layer) {
     if (p.compute_mode == FFN_COMPUTE_FP16_TC) {
       tc_layer(c, layer);
+    } else if (p.compute_mode == FFN_COMPUTE_FP16X2_TC) {
+      tc_layer_x2(c, layer);
     } else {
       f32_layer(c, layer);
     }
@@ -1493,7 +1625,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   const long long t_kernel = prof_now(c);
   c.bits = 0;
   c.tmem_base = 0;
-  const bool tc = p.compute_mode == FFN_COMPUTE_FP16_TC;
+  const bool tc = p.compute_mode != FFN_COMPUTE_FP32;
 
   for (int i = c.tid; i < p.g.nconv * 32; i += kThreads) c.s_bias[i] = p.w.bias[i];
   if (c.tid < 32) c.s_bias[p.g.nconv * 32 + c.tid] = p.w.w_lom[c.tid];
@@ -1518,8 +1650,10 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
     __syncthreads();
     sm100::tc_fence_after();
     c.tmem_base = __shfl_sync(0xffffffffu, *c.s_tmem, 0);
-    if (c.warp == kLoadWarp && c.lane == 0) tc_issue_weight_load(c, 0);
-    bit_set(c, 8, true);
+    if (p.compute_mode == FFN_COMPUTE_FP16_TC) {   // the split mode loads both weight halves per layer
+      if (c.warp == kLoadWarp && c.lane == 0) tc_issue_weight_load(c, 0);
+      bit_set(c, 8, true);
+    }
   }
   __syncthreads();
 

@@ -28,7 +28,10 @@ typedef struct FfnCanvas FfnCanvas;
 /* Arithmetic of the 3x3x3 convolutions. */
 enum {
   FFN_COMPUTE_FP16_TC = 0, /* fp16 operands, fp32 accumulate on tcgen05 tensor cores; fp32 residual stream */
-  FFN_COMPUTE_FP32 = 1     /* fp32 FMA on CUDA cores ("precise" parity mode) */
+  FFN_COMPUTE_FP32 = 1,    /* fp32 FMA on CUDA cores ("precise" parity mode) */
+  FFN_COMPUTE_FP16X2_TC = 2 /* near-fp32 on the tensor cores: every operand split into fp16 hi + lo parts,
+                             * a*w = a_hi*w_hi + a_lo*w_hi + a_hi*w_lo as three tcgen05 MMAs into the same fp32
+                             * accumulator (weights pre-scaled by 2^10 so that w_lo stays normal) */
 };
 
 enum { FFN_IMAGE_U8 = 0, FFN_IMAGE_F32 = 1 };
@@ -114,6 +117,8 @@ const char* ffn_last_error(void);
  * weights_dhwio[2*depth]: conv_lom [1,1,1,32,1]; biases[i]: [32] (conv_lom: [1]). */
 int ffn_engine_create(int device, const FfnModelDesc* model, const float* const* weights_dhwio,
                       const float* const* biases, int compute_mode, FfnEngine** out);
+/* Canvases created from the engine may outlive this call: the engine is then released by the last
+ * ffn_canvas_destroy (until then those canvases stay fully usable). */
 void ffn_engine_destroy(FfnEngine* engine);
 int ffn_engine_set_compute_mode(FfnEngine* engine, int compute_mode);
 /* Number of SMs (CTAs of the cooperative grid) this engine's kernel occupies; 0 = all.  Several engines

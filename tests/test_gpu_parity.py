@@ -4,9 +4,16 @@ fixtures recorded from the reference's own Python modules.
 Tolerances (also stated in DESIGN.md):
   * FFN_COMPUTE_FP32     logits max-abs <= 1e-4 vs the fp32 oracle; trajectories / labels identical to the
                          reference golden run; qprob within +-1 LSB.
-  * FFN_COMPUTE_FP16_TC  logits max-abs <= 6e-2 (fp16 operand rounding, fp32 accumulate) vs the fp32
-                         oracle; flood-fill state BIT-EXACT vs the oracle loop driven by the same
-                         GPU network ("hybrid oracle"): every integer / index / decision is exact.
+  * FFN_COMPUTE_FP16X2_TC (fp16 hi+lo split operands on the tensor cores) logits max-abs <= 1e-4 vs the
+                         fp32 oracle; trajectories / labels identical to the reference golden run — the
+                         label-exact mode that runs on tcgen05.
+  * FFN_COMPUTE_FP16_TC  logits max-abs <= 4e-2 (fp16 operand rounding, fp32 accumulate; measured 3.1e-2) vs the
+                         fp32 oracle and <= 1.5e-2 (measured 7.8e-3) vs the oracle with fp16-rounded conv
+                         operands; flood-fill state BIT-EXACT vs the oracle
+                         loop driven by the same GPU network ("hybrid oracle"): every integer / index /
+                         decision is exact.  Against the pure fp32 reference golden the labels may differ
+                         where a decision margin is below the logit error: label IoU after canonical
+                         relabelling >= 0.97 on the golden volume (reported, see test_fp16_labels_vs_fp32_reference).
 """
 
 import json
@@ -33,7 +40,8 @@ def engines(weights):
   from ffn_b200 import _lib, engine as eng
   w, b = weights
   out = {'fp32': eng.Engine(w, b, FOV, DELTAS, compute_mode=_lib.COMPUTE_FP32),
-         'tc': eng.Engine(w, b, FOV, DELTAS, compute_mode=_lib.COMPUTE_FP16_TC)}
+         'tc': eng.Engine(w, b, FOV, DELTAS, compute_mode=_lib.COMPUTE_FP16_TC),
+         'x2': eng.Engine(w, b, FOV, DELTAS, compute_mode=_lib.COMPUTE_FP16X2_TC)}
   yield out
   for e in out.values():
     e.close()
@@ -56,14 +64,16 @@ def test_umma_descriptor_known_answer():
   assert out[3] > 1.0, 'swapped LBO/SBO must NOT reproduce the product'
 
 
-@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('tc', 6e-2)])
+@pytest.mark.parametrize('mode,tol', [('fp32', 1e-4), ('x2', 1e-4), ('tc', 4e-2)])
 def test_predict_matches_oracle(engines, golden_dir, mode, tol):
   pat = np.load(os.path.join(golden_dir, 'net_patches.npz'))
   e = engines[mode]
   got = e.predict(pat['seed'], pat['image'])
   assert np.isfinite(got).all()
-  assert np.abs(got - pat['logits_fp32']).max() <= tol
-  assert np.abs(got - pat['logits_fp64']).max() <= tol
+  e32, e64 = float(np.abs(got - pat['logits_fp32']).max()), float(np.abs(got - pat['logits_fp64']).max())
+  print('%s: max |logit - oracle| = %.3g (fp32 oracle), %.3g (fp64 oracle), median %.3g' % (
+      mode, e32, e64, float(np.median(np.abs(got - pat['logits_fp64'])))))
+  assert e32 <= tol and e64 <= tol
   one = e.predict(pat['seed'][3], pat['image'][3])
   np.testing.assert_array_equal(one, got[3])                          # batch == single, deterministic
   np.testing.assert_array_equal(e.predict(pat['seed'][3], pat['image'][3]), one)
@@ -122,10 +132,52 @@ def _check_segment_all(cv, origins, overlaps, ctr, g, exact_qprob):
     assert seg[z, y, x] == sid                                       # every origin carries its own id
 
 
-def test_fp32_segment_all_matches_reference_golden(engines, g64):
-  """Whole-canvas run == the reference's Canvas.segment_all on the same volume / seeds / weights."""
+def test_fp16_logits_vs_fp16_operand_oracle(engines, weights, golden_dir):
+  """The fp16 tensor-core path against the oracle with the SAME operand rounding (conv inputs and
+  weights rounded to fp16, fp32 accumulate).  What is left is accumulation order — which still flips
+  individual fp16 roundings of the next layer's operands (1 ulp = 5e-4 relative), so two correct fp16-operand
+  implementations differ by a fraction of the rounding noise itself: measured 7.8e-3 here against 3.1e-2
+  versus the fp32 oracle (B200, round 2).  A kernel error (wrong tap, wrong halo) is O(1)."""
+  from oracle.network import ConvStackOracle
+  w, b = weights
+  pat = np.load(os.path.join(golden_dir, 'net_patches.npz'))
+  got = engines['tc'].predict(pat['seed'], pat['image'])
+  want16 = ConvStackOracle(w, b, operand_round='fp16')(pat['seed'], pat['image'])
+  err16 = float(np.abs(got - want16).max())
+  err32 = float(np.abs(got - pat['logits_fp32']).max())
+  print('fp16 TC: max |logit - fp16-operand oracle| = %.3g, vs fp32 oracle = %.3g' % (err16, err32))
+  assert err16 <= 1.5e-2, err16
+  assert err32 <= 4e-2, err32
+
+
+def test_fp16_labels_vs_fp32_reference(engines, g64):
+  """The fast fp16 mode against the PURE fp32 reference golden (not the hybrid oracle): fp16 operand
+  rounding can move knife-edge decisions, so equality is not the claim — the label overlap is."""
+  from ffn_b200 import _lib, engine as eng
+  cv = eng.DeviceCanvas(engines['tc'], g64['volume'], eng.make_options(), 128.0, 33.0)
+  origins, _, ctr = cv.segment_all(g64['seeds'])
+  seg = cv.read(_lib.ARRAY_SEGMENTATION)
+  cv.close()
+  a = ff.canonical_relabel(np.maximum(seg, 0))
+  b = ff.canonical_relabel(np.maximum(g64['segmentation'], 0))
+  fg = (a > 0) | (b > 0)
+  iou = float(((a == b) & fg).sum()) / float(fg.sum())
+  mism = int((a != b).sum())
+  steps_ref = int(json.loads(str(g64['counters']))['inference-calls'])
+  print('fp16 TC vs fp32 reference golden: label IoU %.4f, %d mismatching voxels (%.2f%%), steps %d vs %d, '
+        'segments %d vs %d' % (iou, mism, 100.0 * mism / a.size, ctr.inference_calls, steps_ref, len(origins),
+                               g64['origins'].shape[0]))
+  assert iou >= 0.97, iou
+  assert len(origins) == g64['origins'].shape[0]
+  assert abs(ctr.inference_calls - steps_ref) <= 0.05 * steps_ref
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'x2'])
+def test_fp32_segment_all_matches_reference_golden(engines, g64, mode):
+  """Whole-canvas run == the reference's Canvas.segment_all on the same volume / seeds / weights, in the
+  fp32 CUDA-core mode AND in the split-fp16 tensor-core mode (label-exact on tcgen05)."""
   from ffn_b200 import engine as eng
-  cv = eng.DeviceCanvas(engines['fp32'], g64['volume'], eng.make_options(), 128.0, 33.0)
+  cv = eng.DeviceCanvas(engines[mode], g64['volume'], eng.make_options(), 128.0, 33.0)
   origins, overlaps, ctr = cv.segment_all(g64['seeds'])
   _check_segment_all(cv, origins, overlaps, ctr, g64, exact_qprob=False)
   # idempotence: a second pass over the same seeds finds nothing new to segment
@@ -255,7 +307,7 @@ def test_anisotropic_model_vs_oracle(weights):
   fov, deltas = (17, 33, 33), (4, 8, 8)
   vol = voronoi_phantom((40, 72, 72), seed=4, sigma=(0.5, 1.0, 1.0), voxel_size_zyx=(2.0, 1.0, 1.0))
   oracle_net = ConvStackOracle(w9, b9)
-  for mode, tol in ((_lib.COMPUTE_FP32, 1e-4), (_lib.COMPUTE_FP16_TC, 6e-2)):
+  for mode, tol in ((_lib.COMPUTE_FP32, 1e-4), (_lib.COMPUTE_FP16X2_TC, 1e-4), (_lib.COMPUTE_FP16_TC, 4e-2)):
     e = eng.Engine(w9, b9, fov, deltas, compute_mode=mode)
     rng = np.random.RandomState(1)
     img = _image(vol)[4:21, 8:41, 10:43]

@@ -28,12 +28,12 @@ MASK_MOVEMENT = 0
 MASK_SEED = 1
 
 EXPORTS = [
-    'ffn_last_error', 'ffn_engine_create', 'ffn_engine_destroy', 'ffn_engine_set_compute_mode', 'ffn_engine_set_grid',
+    'ffn_last_error', 'ffn_engine_create', 'ffn_engine_destroy', 'ffn_engine_set_compute_mode', 'ffn_engine_set_chains', 'ffn_engine_set_grid',
     'ffn_engine_info', 'ffn_engine_profile', 'ffn_predict', 'ffn_canvas_create', 'ffn_canvas_destroy',
     'ffn_canvas_set_mask', 'ffn_canvas_segment_at', 'ffn_canvas_segment_all',
     'ffn_canvas_update_at', 'ffn_canvas_init_seed', 'ffn_canvas_read', 'ffn_canvas_write',
     'ffn_canvas_policy_state_size', 'ffn_canvas_policy_state_get', 'ffn_canvas_policy_state_set',
-    'ffn_canvas_set_resume', 'ffn_canvas_trace', 'ffn_canvas_seed_peaks', 'ffn_canvas_set_max_id', 'ffn_canvas_get_counters', 'ffn_canvas_device_ptr',
+    'ffn_canvas_set_resume', 'ffn_canvas_trace', 'ffn_canvas_seed_peaks', 'ffn_canvas_set_max_id', 'ffn_canvas_get_counters', 'ffn_canvas_spec_stats', 'ffn_canvas_device_ptr',
     'ffn_canvas_add_id_offset', 'ffn_selftest_umma',
 ]
 
@@ -104,6 +104,7 @@ def load() -> C.CDLL:
   lib.ffn_engine_destroy.restype = None
   lib.ffn_engine_set_compute_mode.argtypes = [p, C.c_int]
   lib.ffn_engine_set_grid.argtypes = [p, C.c_int]
+  lib.ffn_engine_set_chains.argtypes = [p, C.c_int]
   lib.ffn_engine_info.argtypes = [p, C.POINTER(C.c_int64)]
   lib.ffn_engine_profile.argtypes = [p, C.POINTER(C.c_int64), C.c_int]
   lib.ffn_predict.argtypes = [p, p, p, C.c_int, p]
@@ -127,6 +128,7 @@ def load() -> C.CDLL:
   lib.ffn_canvas_seed_peaks.argtypes = [p, C.POINTER(C.c_float), p, p, C.c_int64, C.POINTER(C.c_int64)]
   lib.ffn_canvas_set_max_id.argtypes = [p, C.c_int64]
   lib.ffn_canvas_get_counters.argtypes = [p, C.POINTER(Counters)]
+  lib.ffn_canvas_spec_stats.argtypes = [p, C.POINTER(C.c_int64)]
   lib.ffn_canvas_device_ptr.argtypes = [p, C.c_int, C.POINTER(p), C.POINTER(C.c_int64)]
   lib.ffn_canvas_add_id_offset.argtypes = [p, C.c_int32]
   lib.ffn_selftest_umma.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int]

@@ -178,6 +178,14 @@ struct Sched {
   long long spec_runs, spec_discarded, spec_steps_discarded;
   unsigned round;             // rounds completed (all launches)
   int all_done;
+  // Canvas.seed after segment_all holds the LAST object segment_at ran on (inference.py:443-450 clears it only when
+  // the next one starts).  `last_chain` is the chain whose seed array holds that object; when that chain is about
+  // to start an object ahead of its turn (which may later be discarded), its box is first moved to the snapshot
+  // array, so the last in-turn object is never lost.
+  int last_chain;             // -1: none
+  int last_in_snap;
+  int snap_lo[3], snap_hi[3];         // box of the snapshot array holding data (hi exclusive)
+  int snap_old_lo[3], snap_old_hi[3]; // previous snapshot box, cleared by the move pass of this round
   FfnCounters ctr;            // committed counters (== the reference's)
 };
 
@@ -188,7 +196,7 @@ struct Ctl {
 };
 
 enum Mode : int { MODE_PREDICT = 0, MODE_UPDATE_AT = 1, MODE_SEGMENT = 2 };
-enum Action : int { ACT_EXIT = 0, ACT_STEP, ACT_CLEAR, ACT_COUNT, ACT_WRITE, ACT_IDLE };
+enum Action : int { ACT_EXIT = 0, ACT_STEP, ACT_CLEAR, ACT_COUNT, ACT_WRITE, ACT_IDLE, ACT_CLEAR_MOVE };
 
 struct Job {
   int mode;
@@ -224,6 +232,7 @@ struct KParams {
   Sched* sched;
   Ctl* ctl;
   unsigned* round_flag;   // rounds published by the leader (release / acquire)
+  float* snap;            // snapshot seed array (see Sched::last_chain); null with one chain
   Job job;
   int compute_mode;
   int act_smem_bytes;   // 3 * 4 * seg_rows_max * 16

@@ -60,8 +60,12 @@ struct FfnEngine {
   ffn::Geom g{};
   ffn::Weights w{};
   ffn::Workspace ws{};
-  int* d_action = nullptr;
-  ffn::CanvasState* d_dummy_state = nullptr;
+  ffn::ChainDev cws[ffn::kMaxChains]{};   // per-chain step workspace (canvas-side pointers stay null here)
+  int max_chains = ffn::kMaxChains;       // chains the multi-seed / batched paths may use (ffn_engine_set_chains)
+  ffn::Ctl* d_ctl = nullptr;
+  unsigned* d_round_flag = nullptr;
+  ffn::CanvasState* d_dummy_state = nullptr;   // [kMaxChains]
+  ffn::Sched* d_dummy_sched = nullptr;
   // predict staging
   float* d_in_seed = nullptr;
   float* d_in_image = nullptr;
@@ -81,8 +85,15 @@ struct FfnEngine {
 struct FfnCanvas {
   FfnEngine* eng = nullptr;
   ffn::CanvasDev cv{};
-  ffn::CanvasState* d_state = nullptr;
-  ffn::CanvasState h_state{};
+  ffn::ChainDev ch[ffn::kMaxChains]{};    // canvas-side buffers of the chains; [0] is the canvas's own seed array
+  int nchains_alloc = 1;
+  float* d_snap = nullptr;                // snapshot seed array (Sched::last_chain), allocated with the extra chains
+  ffn::CanvasState* d_state = nullptr;    // [kMaxChains]
+  ffn::CanvasState h_state{};             // chain 0
+  ffn::Sched* d_sched = nullptr;
+  ffn::Sched h_sched{};
+  size_t q_cap = 0, traj_cap = 0;
+  long long last_spec[4] = {0, 0, 0, 0};   // last segment_all: early runs started / discarded / their steps / steps executed
   void* d_image = nullptr;
   uint8_t* d_mask = nullptr;
   uint8_t* d_seed_mask = nullptr;
@@ -138,21 +149,43 @@ Geom make_geom(const FfnModelDesc& m) {
   return g;
 }
 
-// Launches the persistent kernel once and waits for it.
-int launch(FfnEngine* e, const CanvasDev& cv, CanvasState* d_state, const Job& job) {
+// How many chains a launch may use: the fp32 residual stream of every (chain, tile) lives in TMEM.
+int chain_limit(const FfnEngine* e) {
+  const int tiles = (e->g.nt + e->grid - 1) / e->grid;
+  return std::max(1, std::min({e->max_chains, (int)kMaxChains, kMaxTilesPerCta / std::max(tiles, 1)}));
+}
+
+// Launches the persistent kernel once and waits for it.  `c` may be null (predict).
+int launch(FfnEngine* e, FfnCanvas* c, int nchains, const Job& job) {
   KParams p{};
   p.g = e->g;
   p.w = e->w;
   p.ws = e->ws;
   if (!e->profiling) p.ws.prof = nullptr;
-  p.cv = cv;
-  p.st = d_state ? d_state : e->d_dummy_state;
+  if (c) p.cv = c->cv;
+  p.nchains = nchains;
+  for (int k = 0; k < kMaxChains; ++k) {
+    p.ch[k] = e->cws[k];
+    if (c && k < c->nchains_alloc) {
+      p.ch[k].seed = c->ch[k].seed;
+      p.ch[k].q_score = c->ch[k].q_score;
+      p.ch[k].q_pos = c->ch[k].q_pos;
+      p.ch[k].lattice = c->ch[k].lattice;
+      p.ch[k].traj = c->ch[k].traj;
+    }
+    p.ch[k].st = c ? c->d_state + k : e->d_dummy_state + k;
+  }
+  p.sched = c ? c->d_sched : e->d_dummy_sched;
+  p.ctl = e->d_ctl;
+  p.round_flag = e->d_round_flag;
+  p.snap = c ? c->d_snap : nullptr;
   p.job = job;
-  p.job.action = e->d_action;
   p.compute_mode = e->compute_mode;
   CUDA_OK(cudaMemsetAsync(e->ws.bar, 0, sizeof(unsigned), cudaStreamPerThread));
   CUDA_OK(cudaMemsetAsync(e->ws.abort_flag, 0, sizeof(int), cudaStreamPerThread));
-  CUDA_OK(cudaMemsetAsync(e->d_action, 0, sizeof(int), cudaStreamPerThread));
+  CUDA_OK(cudaMemsetAsync(e->d_ctl, 0, sizeof(Ctl), cudaStreamPerThread));
+  CUDA_OK(cudaMemsetAsync(e->d_round_flag, 0, sizeof(unsigned), cudaStreamPerThread));
+  for (int k = 0; k < kMaxChains; ++k) CUDA_OK(cudaMemsetAsync(e->cws[k].bar, 0, sizeof(unsigned), cudaStreamPerThread));
   void* args[] = {&p};
   CUDA_OK(cudaEventRecord(e->ev0, cudaStreamPerThread));
   CUDA_OK(cudaLaunchCooperativeKernel(e->profiling ? reinterpret_cast<const void*>(profiled::ffn_flood_kernel)
@@ -168,16 +201,57 @@ int launch(FfnEngine* e, const CanvasDev& cv, CanvasState* d_state, const Job& j
   CUDA_OK(cudaMemcpy(&abort_flag, e->ws.abort_flag, sizeof(int), cudaMemcpyDeviceToHost));
   if (abort_flag != 0)
     return fail("device-side wait timed out (abort code " + std::to_string(abort_flag) +
-                "): 1 = grid barrier, 2 = mbarrier");
+                "): 1 = grid barrier, 2 = mbarrier, 3 = chain barrier, 4 = round flag");
   return 0;
 }
 
-int pull_state(FfnCanvas* c) {
+int pull_state(FfnCanvas* c) {   // chain 0: the canvas's own flood-fill state
   CUDA_OK(cudaMemcpy(&c->h_state, c->d_state, sizeof(CanvasState), cudaMemcpyDeviceToHost));
   return 0;
 }
 int push_state(FfnCanvas* c) {
   CUDA_OK(cudaMemcpy(c->d_state, &c->h_state, sizeof(CanvasState), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// Queue / done lattice / trajectory log of one chain (the seed array of chain 0 is the canvas's own).
+int alloc_chain(FfnCanvas* c, int k) {
+  ChainDev& ch = c->ch[k];
+  if (k > 0) {
+    if (dev_alloc(&ch.seed, c->nvox, false)) return 1;
+    fill_f32_kernel<<<c->eng->sm_count * 8, 256, 0, cudaStreamPerThread>>>(ch.seed, c->nvox, NAN);
+    CUDA_OK(cudaGetLastError());
+  }
+  if (dev_alloc(&ch.lattice, c->lattice_cells)) return 1;
+  if (dev_alloc(&ch.q_score, c->q_cap, false)) return 1;
+  if (dev_alloc(&ch.q_pos, c->q_cap * 3, false)) return 1;
+  if (dev_alloc(&ch.traj, c->traj_cap * 3, false)) return 1;
+  return 0;
+}
+
+// Private seed arrays etc. for chains 1 .. n-1 and the snapshot array, on first use.
+int ensure_chains(FfnCanvas* c, int n) {
+  for (int k = c->nchains_alloc; k < n; ++k) {
+    if (alloc_chain(c, k)) return 1;
+    c->nchains_alloc = k + 1;
+  }
+  if (n > 1 && !c->d_snap) {
+    if (dev_alloc(&c->d_snap, c->nvox, false)) return 1;
+    fill_f32_kernel<<<c->eng->sm_count * 8, 256, 0, cudaStreamPerThread>>>(c->d_snap, c->nvox, NAN);
+    CUDA_OK(cudaGetLastError());
+    for (int q = 0; q < 3; ++q) c->h_sched.snap_lo[q] = c->h_sched.snap_hi[q] = 0;
+  }
+  CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
+  return 0;
+}
+
+int fill_box(FfnCanvas* c, float* arr, const int lo[3], const int hi[3]) {
+  const int l[3] = {std::max(lo[0], 0), std::max(lo[1], 0), std::max(lo[2], 0)};
+  const int n[3] = {std::min(hi[0], c->cv.sz) - l[0], std::min(hi[1], c->cv.sy) - l[1], std::min(hi[2], c->cv.sx) - l[2]};
+  if (n[0] <= 0 || n[1] <= 0 || n[2] <= 0) return 0;
+  fill_box_f32_kernel<<<c->eng->sm_count * 4, 256, 0, cudaStreamPerThread>>>(arr, c->cv.sy, c->cv.sx, l[0], l[1], l[2], n[0],
+                                                                          n[1], n[2], NAN);
+  CUDA_OK(cudaGetLastError());
   return 0;
 }
 
@@ -224,7 +298,7 @@ int box_copy(FfnCanvas* c, int which, const int32_t lo[3], const int32_t sz[3], 
   size_t esz = 0;
   char* base = nullptr;
   switch (which) {
-    case FFN_ARRAY_SEED: esz = 4; base = reinterpret_cast<char*>(cv.seed); break;
+    case FFN_ARRAY_SEED: esz = 4; base = reinterpret_cast<char*>(c->ch[0].seed); break;
     case FFN_ARRAY_SEGMENTATION: esz = 4; base = reinterpret_cast<char*>(cv.seg); break;
     case FFN_ARRAY_QPROB:
       if (!cv.qprob) return fail("canvas was created without probability maps");
@@ -338,9 +412,6 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   // workspace (all buffers zero-initialised: pad rows / guards must stay zero forever)
   Workspace& ws = e->ws;
   const size_t ra = (size_t)g.rows_alloc;
-  if (dev_alloc(&ws.act0_h, 2 * ra * 8)) return 1;
-  if (dev_alloc(&ws.act_h[0], 4 * ra * 8)) return 1;
-  if (dev_alloc(&ws.act_h[1], 4 * ra * 8)) return 1;
   if (dev_alloc(&ws.act0_l, 2 * ra * 8)) return 1;
   if (dev_alloc(&ws.act_l[0], 4 * ra * 8)) return 1;
   if (dev_alloc(&ws.act_l[1], 4 * ra * 8)) return 1;
@@ -348,18 +419,31 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   if (dev_alloc(&ws.act_f[0], 8 * ra)) return 1;
   if (dev_alloc(&ws.act_f[1], 8 * ra)) return 1;
   if (dev_alloc(&ws.res, 8 * ra)) return 1;
-  if (dev_alloc(&ws.seed_raw, (size_t)g.nt * kTileM)) return 1;
-  if (dev_alloc(&ws.logits, (size_t)g.nt * kTileM)) return 1;
   if (dev_alloc(&ws.bar, 1)) return 1;
-  if (dev_alloc(&ws.count, 2)) return 1;
   if (dev_alloc(&ws.abort_flag, 1)) return 1;
   if (dev_alloc(&ws.prof, 32)) return 1;
-  if (dev_alloc(&e->d_action, 1)) return 1;
-  if (dev_alloc(&e->d_dummy_state, 1)) return 1;
-  for (void* p : std::vector<void*>{ws.act0_h, ws.act_h[0], ws.act_h[1], ws.act0_l, ws.act_l[0], ws.act_l[1], ws.act0_f, ws.act_f[0], ws.act_f[1],
-                                    ws.res, ws.seed_raw, ws.logits, ws.bar, ws.count, ws.abort_flag, ws.prof,
-                                    e->d_action, e->d_dummy_state})
+  for (void* p : std::vector<void*>{ws.act0_l, ws.act_l[0], ws.act_l[1], ws.act0_f, ws.act_f[0], ws.act_f[1], ws.res,
+                                    ws.bar, ws.abort_flag, ws.prof})
     e->owned.push_back(p);
+  for (int k = 0; k < kMaxChains; ++k) {   // per-chain step workspace: fp16 operands, raw seed, logits, counters, barrier
+    ChainDev& cw = e->cws[k];
+    if (dev_alloc(&cw.act0_h, 2 * ra * 8)) return 1;
+    if (dev_alloc(&cw.act_h[0], 4 * ra * 8)) return 1;
+    if (dev_alloc(&cw.act_h[1], 4 * ra * 8)) return 1;
+    if (dev_alloc(&cw.seed_raw[0], (size_t)g.nt * kTileM)) return 1;
+    if (dev_alloc(&cw.seed_raw[1], (size_t)g.nt * kTileM)) return 1;
+    if (dev_alloc(&cw.logits, (size_t)g.nt * kTileM)) return 1;
+    if (dev_alloc(&cw.count, 4)) return 1;
+    if (dev_alloc(&cw.bar, 1)) return 1;
+    for (void* p : std::vector<void*>{cw.act0_h, cw.act_h[0], cw.act_h[1], cw.seed_raw[0], cw.seed_raw[1], cw.logits,
+                                      cw.count, cw.bar})
+      e->owned.push_back(p);
+  }
+  if (dev_alloc(&e->d_ctl, 1)) return 1;
+  if (dev_alloc(&e->d_round_flag, 1)) return 1;
+  if (dev_alloc(&e->d_dummy_state, kMaxChains)) return 1;
+  if (dev_alloc(&e->d_dummy_sched, 1)) return 1;
+  for (void* p : std::vector<void*>{e->d_ctl, e->d_round_flag, e->d_dummy_state, e->d_dummy_sched}) e->owned.push_back(p);
   *out = e.release();
   return 0;
 }
@@ -380,6 +464,14 @@ int ffn_engine_set_grid(FfnEngine* e, int num_ctas) {
   if ((e->g.nt + num_ctas - 1) / num_ctas > kMaxTilesPerCta)
     return fail("grid too small: at most " + std::to_string(kMaxTilesPerCta) + " tiles per CTA (TMEM residual)");
   e->grid = num_ctas;
+  return 0;
+}
+
+int ffn_engine_set_chains(FfnEngine* e, int max_chains) {
+  if (!e) return fail("null engine");
+  if (max_chains <= 0) max_chains = kMaxChains;
+  if (max_chains > kMaxChains) return fail("at most " + std::to_string(kMaxChains) + " chains");
+  e->max_chains = max_chains;
   return 0;
 }
 
@@ -440,8 +532,9 @@ int ffn_predict(FfnEngine* e, const float* seed, const float* image, int batch, 
   job.in_image = e->d_in_image;
   job.out_logits = e->d_out;
   job.batch = batch;
-  CanvasDev cv{};
-  if (launch(e, cv, nullptr, job)) return 1;
+  // the patches of a batch are independent: up to chain_limit() of them share one round of the pipeline
+  const int nch = e->compute_mode == FFN_COMPUTE_FP16_TC ? std::min(chain_limit(e), batch) : 1;
+  if (launch(e, nullptr, nch, job)) return 1;
   CUDA_OK(cudaMemcpy(logits_out, e->d_out, n * sizeof(float), cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -478,12 +571,12 @@ int ffn_canvas_create(FfnEngine* e, const void* image, int image_dtype, const in
   CUDA_OK(cudaMalloc(&c->d_image, ibytes));
   CUDA_OK(cudaMemcpy(c->d_image, image, ibytes, cudaMemcpyHostToDevice));
   cv.image = c->d_image;
-  if (dev_alloc(&cv.seed, c->nvox, false)) return 1;
+  if (dev_alloc(&c->ch[0].seed, c->nvox, false)) return 1;
   if (dev_alloc(&cv.seg, c->nvox)) return 1;
   if (keep_probability_maps) {
     if (dev_alloc(&cv.qprob, c->nvox)) return 1;
   }
-  fill_f32_kernel<<<e->sm_count * 8, 256, 0, cudaStreamPerThread>>>(cv.seed, c->nvox, NAN);
+  fill_f32_kernel<<<e->sm_count * 8, 256, 0, cudaStreamPerThread>>>(c->ch[0].seed, c->nvox, NAN);
   CUDA_OK(cudaGetLastError());
   // movement policy storage
   const int del[3] = {std::max(g.dz, 1), std::max(g.dy, 1), std::max(g.dx, 1)};
@@ -497,18 +590,19 @@ int ffn_canvas_create(FfnEngine* e, const void* image, int image_dtype, const in
     qcells *= (size_t)(n + 2);
   }
   c->lattice_cells = cells;
-  if (dev_alloc(&cv.lattice, cells)) return 1;
-  const size_t qcap = std::min<size_t>(6 * qcells + 16, (size_t)1 << 30);
-  cv.q_cap = (int)qcap;
-  if (dev_alloc(&cv.q_score, qcap, false)) return 1;
-  if (dev_alloc(&cv.q_pos, qcap * 3, false)) return 1;
-  if (dev_alloc(&c->d_state, 1)) return 1;
+  c->q_cap = std::min<size_t>(6 * qcells + 16, (size_t)1 << 30);
+  c->traj_cap = std::min<size_t>(qcells + 16, (size_t)1 << 28);   // one FoV step per lattice cell at most
+  cv.q_cap = (int)c->q_cap;
+  cv.traj_cap = (int)c->traj_cap;
+  if (alloc_chain(c.get(), 0)) return 1;
+  if (dev_alloc(&c->d_state, kMaxChains)) return 1;
+  if (dev_alloc(&c->d_sched, 1)) return 1;
   if (dev_alloc(&c->d_pred, (size_t)g.V, false)) return 1;
   std::memset(&c->h_state, 0, sizeof(CanvasState));
-  for (int k = 0; k < 3; ++k) {   // nothing dirty yet
-    c->h_state.dirty_lo[k] = 0;
-    c->h_state.dirty_hi[k] = 0;
-  }
+  std::memset(&c->h_sched, 0, sizeof(Sched));
+  c->h_sched.owner = -1;
+  c->h_sched.last_chain = -1;
+  c->h_state.seed_index = -1;
   if (push_state(c.get())) return 1;
   CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
   e->live_canvases++;
@@ -521,14 +615,19 @@ void ffn_canvas_destroy(FfnCanvas* c) {
   FfnEngine* e = c->eng;
   cudaSetDevice(e->device);
   cudaFree(c->d_image);
-  cudaFree(c->cv.seed);
+  for (int k = 0; k < kMaxChains; ++k) {
+    cudaFree(c->ch[k].seed);
+    cudaFree(c->ch[k].lattice);
+    cudaFree(c->ch[k].q_score);
+    cudaFree(c->ch[k].q_pos);
+    cudaFree(c->ch[k].traj);
+  }
+  cudaFree(c->d_snap);
   cudaFree(c->cv.seg);
   cudaFree(c->cv.qprob);
-  cudaFree(c->cv.lattice);
-  cudaFree(c->cv.q_score);
-  cudaFree(c->cv.q_pos);
   cudaFree(c->cv.trace);
   cudaFree(c->d_state);
+  cudaFree(c->d_sched);
   cudaFree(c->d_pred);
   cudaFree(c->d_mask);
   cudaFree(c->d_seed_mask);
@@ -561,16 +660,8 @@ int ffn_canvas_init_seed(FfnCanvas* c, const int32_t pos[3]) {
   if (pull_state(c)) return 1;
   CanvasState& st = c->h_state;
   // clear only what can be non-NaN (== NumpyArray.clear), then place the seed
-  for (int z = std::max(st.dirty_lo[0], 0); z < std::min(st.dirty_hi[0], c->cv.sz); ++z)
-    for (int y = std::max(st.dirty_lo[1], 0); y < std::min(st.dirty_hi[1], c->cv.sy); ++y) {
-      const int x0 = std::max(st.dirty_lo[2], 0), x1 = std::min(st.dirty_hi[2], c->cv.sx);
-      if (x1 > x0) {
-        fill_f32_kernel<<<1, 128, 0, cudaStreamPerThread>>>(c->cv.seed + ((size_t)z * c->cv.sy + y) * c->cv.sx + x0,
-                                                       (size_t)(x1 - x0), NAN);
-      }
-    }
-  CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaMemcpyAsync(c->cv.seed + ((size_t)pos[0] * c->cv.sy + pos[1]) * c->cv.sx + pos[2],
+  if (fill_box(c, c->ch[0].seed, st.dirty_lo, st.dirty_hi)) return 1;
+  CUDA_OK(cudaMemcpyAsync(c->ch[0].seed + ((size_t)pos[0] * c->cv.sy + pos[1]) * c->cv.sx + pos[2],
                           &c->cv.opt.init_activation, sizeof(float), cudaMemcpyHostToDevice, cudaStreamPerThread));
   CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
   for (int k = 0; k < 3; ++k) {
@@ -595,8 +686,9 @@ int ffn_canvas_segment_at(FfnCanvas* c, const int32_t start[3], int reset, int64
   const long long weak0 = st.ctr.seed_got_too_weak;
   if (reset) {
     for (int k = 0; k < 3; ++k) st.start[k] = start[k];
-    st.reset_seed = 1;
+    st.reset_seed = (reset & 2) ? 0 : 1;   // 2: Canvas.reset_seed_per_segment == False (inference.py:486-490)
     st.phase = PH_START_SEGMENT;
+    st.popped = 0;
   } else {
     if (st.phase != PH_POP) return fail("no object in flight to resume");
   }
@@ -609,7 +701,7 @@ int ffn_canvas_segment_at(FfnCanvas* c, const int32_t start[3], int reset, int64
     long long chunk = 1 << 15;
     if (max_steps > 0) chunk = std::min<long long>(chunk, max_steps - done);
     job.step_budget = st.ctr.inference_calls + chunk;
-    if (launch(e, c->cv, c->d_state, job)) return 1;
+    if (launch(e, c, 1, job)) return 1;
     secs += e->last_kernel_seconds;
     if (pull_state(c)) return 1;
     if (st.phase == PH_SEGMENT_DONE) break;
@@ -623,7 +715,7 @@ int ffn_canvas_segment_at(FfnCanvas* c, const int32_t start[3], int reset, int64
     out->max_pos[k] = st.max_pos[k];
   }
   out->seed_got_too_weak = (int)(st.ctr.seed_got_too_weak - weak0);
-  out->queue_len = st.q_tail - st.q_head;
+  out->queue_len = st.q_tail - st.q_head + (st.popped && st.pop_run ? 1 : 0);
   out->finished = st.phase == PH_SEGMENT_DONE;
   out->reserved = 0;
   st.ctr.device_seconds += secs;
@@ -638,35 +730,71 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   if (set_device(e)) return 1;
   if (pull_state(c)) return 1;
   CanvasState& st = c->h_state;
+  Sched& sc = c->h_sched;
+  // Chains: several objects in flight, committed in seed order (see Sched).  The parity modes and the event
+  // trace (Canvas.history) run one object at a time.
+  int K = 1;
+  if (e->compute_mode == FFN_COMPUTE_FP16_TC && !c->cv.trace) K = chain_limit(e);
+  if (ensure_chains(c, K)) return 1;
   int* d_seeds = nullptr;
   FfnOrigin* d_orig = nullptr;
   FfnOverlap* d_ovl = nullptr;
   int *d_cnt = nullptr, *d_touched = nullptr;
-  const int ovl_ids = (int)std::min<int64_t>((int64_t)st.max_id + n_seeds + 2, (int64_t)1 << 30);
+  unsigned char* d_status = nullptr;
+  const int ovl_ids = (int)std::min<int64_t>((int64_t)sc.max_id + n_seeds + 2, (int64_t)1 << 30);
   auto cleanup = [&]() {
     cudaFree(d_seeds);
     cudaFree(d_orig);
     cudaFree(d_ovl);
     cudaFree(d_cnt);
     cudaFree(d_touched);
+    cudaFree(d_status);
   };
   if (dev_alloc(&d_seeds, (size_t)n_seeds * 3, false) || dev_alloc(&d_orig, (size_t)origins_cap, false) ||
       dev_alloc(&d_ovl, (size_t)overlaps_cap, false) || dev_alloc(&d_cnt, (size_t)ovl_ids) ||
-      dev_alloc(&d_touched, (size_t)ovl_ids)) {
+      dev_alloc(&d_touched, (size_t)ovl_ids) || dev_alloc(&d_status, (size_t)n_seeds)) {
     cleanup();
     return 1;
   }
-  if (n_seeds) CUDA_OK(cudaMemcpy(d_seeds, seeds, (size_t)n_seeds * 3 * sizeof(int), cudaMemcpyHostToDevice));
-  st.seg_all = 1;
-  st.seed_idx = 0;
-  st.n_origins = st.n_overlaps = 0;
-  st.overflow = 0;
-  st.phase = c->resume_pending ? PH_POP : PH_NEXT_SEED;   // PH_POP: finish the restored in-flight object first
-  c->resume_pending = false;
-  const FfnCounters before = st.ctr;
-  if (push_state(c)) {
+  if (n_seeds && cudaMemcpy(d_seeds, seeds, (size_t)n_seeds * 3 * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
     cleanup();
-    return 1;
+    return fail("seed list copy failed");
+  }
+  // ---- scheduler and chain states
+  const bool resume = c->resume_pending;   // finish the restored in-flight object first (inference.py:538-550)
+  c->resume_pending = false;
+  sc.commit_idx = 0;
+  sc.owner = resume ? 0 : -1;
+  sc.nchains = K;
+  sc.overflow = 0;
+  sc.n_origins = sc.n_overlaps = 0;
+  sc.steps_executed = 0;
+  sc.all_done = 0;
+  sc.ctr = st.ctr;             // cumulative counters of the canvas; the chains count per object from here on
+  const bool has_data = st.dirty_hi[0] > st.dirty_lo[0];
+  sc.last_chain = has_data ? 0 : -1;   // what Canvas.seed shows right now
+  sc.last_in_snap = 0;
+  std::vector<CanvasState> hs(kMaxChains);
+  if (cudaMemcpy(hs.data(), c->d_state, sizeof(CanvasState) * kMaxChains, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cleanup();
+    return fail("state copy failed");
+  }
+  hs[0] = st;
+  for (int k = 0; k < kMaxChains; ++k) {
+    CanvasState& h = hs[k];
+    h.seg_all = 1;
+    h.seed_index = -1;
+    h.spec = 0;
+    h.popped = 0;
+    h.overflow = 0;
+    h.ctr = FfnCounters{};
+    h.phase = (k == 0 && resume) ? PH_POP : PH_FREE;
+    if (!(k == 0 && resume)) h.have_cur = 0;
+  }
+  if (cudaMemcpy(c->d_state, hs.data(), sizeof(CanvasState) * kMaxChains, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(c->d_sched, &sc, sizeof(Sched), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cleanup();
+    return fail("state upload failed");
   }
   Job job{};
   job.mode = MODE_SEGMENT;
@@ -679,46 +807,87 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   job.ovl_count = d_cnt;
   job.ovl_touched = d_touched;
   job.ovl_ids = ovl_ids;
+  job.seed_status = d_status;
   double secs = 0;
   long long launches = 0;
+  int stuck = 0;
+  int rc = 0;
   for (;;) {
-    job.step_budget = st.ctr.inference_calls + (1 << 15);
-    if (launch(e, c->cv, c->d_state, job)) {
+    const long long before_steps = sc.steps_executed, before_idx = sc.commit_idx;
+    const unsigned before_round = sc.round;
+    job.step_budget = sc.steps_executed + (1 << 15);
+    if (launch(e, c, K, job)) {
       cleanup();
       return 1;
     }
     secs += e->last_kernel_seconds;
     ++launches;
-    if (pull_state(c)) {
+    if (cudaMemcpy(&sc, c->d_sched, sizeof(Sched), cudaMemcpyDeviceToHost) != cudaSuccess) {
       cleanup();
-      return 1;
+      return fail("scheduler state copy failed");
     }
-    if (st.phase == PH_ALL_DONE) break;
-    if (st.phase != PH_POP) {
-      cleanup();
-      return fail("unexpected device phase " + std::to_string(st.phase));
+    if (sc.all_done) break;
+    stuck = (sc.steps_executed == before_steps && sc.commit_idx == before_idx && sc.round <= before_round + 1) ? stuck + 1 : 0;
+    if (stuck >= 3) {
+      rc = fail("segment_all made no progress (device scheduler stuck at seed " + std::to_string(sc.commit_idx) + ")");
+      break;
     }
   }
-  *n_origins = st.n_origins;
-  *n_overlaps = st.n_overlaps;
-  int rc = 0;
-  if (st.overflow & 1) rc = fail("movement queue capacity exceeded");
-  if (!rc && origins_out && st.n_origins)
-    if (cudaMemcpy(origins_out, d_orig, (size_t)std::min<long long>(st.n_origins, origins_cap) * sizeof(FfnOrigin),
+  if (!rc && pull_state(c)) rc = 1;
+  // ---- Canvas.seed shows the last object segment_at ran on: bring it into the canvas's own array
+  if (!rc && (sc.last_in_snap || sc.last_chain > 0)) {
+    const float* src = sc.last_in_snap ? c->d_snap : c->ch[sc.last_chain].seed;
+    int lo[3], hi[3];
+    CanvasState last{};
+    if (!sc.last_in_snap &&
+        cudaMemcpy(&last, c->d_state + sc.last_chain, sizeof(CanvasState), cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = fail("state copy failed");
+    for (int q = 0; q < 3; ++q) {
+      lo[q] = std::max(sc.last_in_snap ? sc.snap_lo[q] : last.dirty_lo[q], 0);
+      hi[q] = std::min(sc.last_in_snap ? sc.snap_hi[q] : last.dirty_hi[q], q == 0 ? c->cv.sz : q == 1 ? c->cv.sy : c->cv.sx);
+    }
+    if (!rc && fill_box(c, c->ch[0].seed, st.dirty_lo, st.dirty_hi)) rc = 1;
+    if (!rc && hi[0] > lo[0] && hi[1] > lo[1] && hi[2] > lo[2]) {
+      copy_box_f32_kernel<<<e->sm_count * 4, 256, 0, cudaStreamPerThread>>>(c->ch[0].seed, src, c->cv.sy, c->cv.sx, lo[0], lo[1],
+                                                                         lo[2], hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
+      if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(cudaStreamPerThread) != cudaSuccess)
+        rc = fail("seed box copy failed");
+    }
+    for (int q = 0; q < 3; ++q) {
+      st.dirty_lo[q] = lo[q];
+      st.dirty_hi[q] = hi[q];
+    }
+  } else if (!rc && sc.last_chain < 0) {
+    // no object ran in turn: Canvas.seed is what it was (nothing); early runs on chain 0 leave no trace
+    if (fill_box(c, c->ch[0].seed, st.dirty_lo, st.dirty_hi)) rc = 1;
+    for (int q = 0; q < 3; ++q) st.dirty_lo[q] = st.dirty_hi[q] = 0;
+    cudaStreamSynchronize(cudaStreamPerThread);
+  }
+  *n_origins = sc.n_origins;
+  *n_overlaps = sc.n_overlaps;
+  if (!rc && (sc.overflow & 1)) rc = fail("movement queue capacity exceeded");
+  if (!rc && (sc.overflow & 8)) rc = fail("trajectory log capacity exceeded");
+  if (!rc && origins_out && sc.n_origins)
+    if (cudaMemcpy(origins_out, d_orig, (size_t)std::min<long long>(sc.n_origins, origins_cap) * sizeof(FfnOrigin),
                    cudaMemcpyDeviceToHost) != cudaSuccess)
       rc = fail("origins copy failed");
-  if (!rc && overlaps_out && st.n_overlaps)
-    if (cudaMemcpy(overlaps_out, d_ovl, (size_t)std::min<long long>(st.n_overlaps, overlaps_cap) * sizeof(FfnOverlap),
+  if (!rc && overlaps_out && sc.n_overlaps)
+    if (cudaMemcpy(overlaps_out, d_ovl, (size_t)std::min<long long>(sc.n_overlaps, overlaps_cap) * sizeof(FfnOverlap),
                    cudaMemcpyDeviceToHost) != cudaSuccess)
       rc = fail("overlaps copy failed");
   cleanup();
+  st.ctr = sc.ctr;
+  st.ctr.max_id = sc.max_id;
   st.ctr.device_seconds += secs;
   st.ctr.kernel_launches += launches;
   st.phase = PH_IDLE;
-  if (counters_out) {
-    *counters_out = st.ctr;
-    (void)before;
-  }
+  st.seg_all = 0;
+  st.have_cur = 0;
+  c->last_spec[0] = sc.spec_runs;
+  c->last_spec[1] = sc.spec_discarded;
+  c->last_spec[2] = sc.spec_steps_discarded;
+  c->last_spec[3] = sc.steps_executed;
+  if (counters_out) *counters_out = st.ctr;
   if (push_state(c)) return 1;
   return rc;
 }
@@ -740,7 +909,7 @@ int ffn_canvas_update_at(FfnCanvas* c, const int32_t pos[3], float* pred_out) {
   Job job{};
   job.mode = MODE_UPDATE_AT;
   job.pred_out = c->d_pred;
-  if (launch(e, c->cv, c->d_state, job)) return 1;
+  if (launch(e, c, 1, job)) return 1;
   if (pull_state(c)) return 1;
   st.phase = saved_phase;
   st.ctr.device_seconds += e->last_kernel_seconds;
@@ -795,9 +964,10 @@ int ffn_canvas_policy_state_size(FfnCanvas* c, int64_t* queue_len, int64_t* done
   if (!c || !queue_len || !done_len) return fail("null argument");
   if (set_device(c->eng)) return 1;
   if (pull_state(c)) return 1;
-  *queue_len = c->h_state.q_tail - c->h_state.q_head;
+  // a position popped for the next step but not yet executed (paused launch) is still part of the queue
+  *queue_len = c->h_state.q_tail - c->h_state.q_head + ((c->h_state.popped && c->h_state.pop_run) ? 1 : 0);
   std::vector<unsigned> lat(c->lattice_cells);
-  CUDA_OK(cudaMemcpy(lat.data(), c->cv.lattice, lat.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(lat.data(), c->ch[0].lattice, lat.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
   int64_t n = 0;
   if (c->h_state.epoch)
     for (unsigned v : lat) n += v == c->h_state.epoch;
@@ -810,12 +980,13 @@ int ffn_canvas_policy_state_get(FfnCanvas* c, double* queue_szyx, int32_t* done_
   if (set_device(c->eng)) return 1;
   if (pull_state(c)) return 1;
   const CanvasState& st = c->h_state;
-  const int n = st.q_tail - st.q_head;
+  const int head = st.q_head - ((st.popped && st.pop_run) ? 1 : 0);   // see ffn_canvas_policy_state_size
+  const int n = st.q_tail - head;
   if (n > 0 && queue_szyx) {
     std::vector<float> sc(n);
     std::vector<int> ps((size_t)n * 3);
-    CUDA_OK(cudaMemcpy(sc.data(), c->cv.q_score + st.q_head, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
-    CUDA_OK(cudaMemcpy(ps.data(), c->cv.q_pos + (size_t)st.q_head * 3, (size_t)n * 3 * sizeof(int),
+    CUDA_OK(cudaMemcpy(sc.data(), c->ch[0].q_score + head, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(ps.data(), c->ch[0].q_pos + (size_t)head * 3, (size_t)n * 3 * sizeof(int),
                        cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) {
       queue_szyx[4 * i] = sc[i];
@@ -824,7 +995,7 @@ int ffn_canvas_policy_state_get(FfnCanvas* c, double* queue_szyx, int32_t* done_
   }
   if (done_zyx && st.epoch) {
     std::vector<unsigned> lat(c->lattice_cells);
-    CUDA_OK(cudaMemcpy(lat.data(), c->cv.lattice, lat.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(lat.data(), c->ch[0].lattice, lat.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
     size_t o = 0;
     const int* d = c->cv.lat_dim;
     for (size_t i = 0; i < lat.size(); ++i)
@@ -857,19 +1028,20 @@ int ffn_canvas_policy_state_set(FfnCanvas* c, const double* queue_szyx, int64_t 
       sc[i] = (float)queue_szyx[4 * i];
       for (int k = 0; k < 3; ++k) ps[3 * i + k] = (int)queue_szyx[4 * i + 1 + k];
     }
-    CUDA_OK(cudaMemcpy(c->cv.q_score, sc.data(), sc.size() * sizeof(float), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(c->cv.q_pos, ps.data(), ps.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->ch[0].q_score, sc.data(), sc.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->ch[0].q_pos, ps.data(), ps.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
   const int* d = c->cv.lat_dim;
   for (int64_t i = 0; i < done_len; ++i) {
     const int qz = done_zyx[3 * i] + c->cv.lat_off[0], qy = done_zyx[3 * i + 1] + c->cv.lat_off[1],
               qx = done_zyx[3 * i + 2] + c->cv.lat_off[2];
     if (qz < 0 || qy < 0 || qx < 0 || qz >= d[0] || qy >= d[1] || qx >= d[2]) return fail("done-set entry outside lattice");
-    CUDA_OK(cudaMemcpy(c->cv.lattice + ((size_t)qz * d[1] + qy) * d[2] + qx, &st.epoch, sizeof(unsigned),
+    CUDA_OK(cudaMemcpy(c->ch[0].lattice + ((size_t)qz * d[1] + qy) * d[2] + qx, &st.epoch, sizeof(unsigned),
                        cudaMemcpyHostToDevice));
   }
   st.phase = PH_POP;
   st.have_cur = 0;
+  st.popped = 0;
   return push_state(c);
 }
 
@@ -885,6 +1057,7 @@ int ffn_canvas_set_resume(FfnCanvas* c, int64_t iters, const int32_t min_pos[3],
   }
   st.phase = PH_POP;
   st.have_cur = 0;
+  st.popped = 0;
   st.seg_t0 = 0;
   c->resume_pending = true;
   return push_state(c);
@@ -978,7 +1151,7 @@ int ffn_canvas_set_max_id(FfnCanvas* c, int64_t max_id) {
   if (!c) return fail("null canvas");
   if (set_device(c->eng)) return 1;
   if (pull_state(c)) return 1;
-  c->h_state.max_id = (int)max_id;
+  c->h_sched.max_id = (int)max_id;
   c->h_state.ctr.max_id = max_id;
   return push_state(c);
 }
@@ -988,14 +1161,20 @@ int ffn_canvas_get_counters(FfnCanvas* c, FfnCounters* out) {
   if (set_device(c->eng)) return 1;
   if (pull_state(c)) return 1;
   *out = c->h_state.ctr;
-  out->max_id = c->h_state.max_id;
+  out->max_id = c->h_sched.max_id;
+  return 0;
+}
+
+int ffn_canvas_spec_stats(FfnCanvas* c, int64_t out[4]) {
+  if (!c || !out) return fail("null argument");
+  for (int i = 0; i < 4; ++i) out[i] = c->last_spec[i];
   return 0;
 }
 
 int ffn_canvas_device_ptr(FfnCanvas* c, int which, void** ptr, int64_t* bytes) {
   if (!c || !ptr || !bytes) return fail("null argument");
   switch (which) {
-    case FFN_ARRAY_SEED: *ptr = c->cv.seed; *bytes = (int64_t)c->nvox * 4; return 0;
+    case FFN_ARRAY_SEED: *ptr = c->ch[0].seed; *bytes = (int64_t)c->nvox * 4; return 0;
     case FFN_ARRAY_SEGMENTATION: *ptr = c->cv.seg; *bytes = (int64_t)c->nvox * 4; return 0;
     case FFN_ARRAY_QPROB:
       if (!c->cv.qprob) return fail("canvas was created without probability maps");

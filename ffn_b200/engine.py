@@ -89,6 +89,10 @@ class Engine:
     """SM budget of this engine's persistent kernel (0 = whole GPU); see ffn_engine_set_grid."""
     _lib.check(self._lib.ffn_engine_set_grid(self._h, int(num_ctas)))
 
+  def set_chains(self, max_chains: int):
+    """Objects / patches in flight at once in the persistent kernel (1..3, 0 = default); see ffn_engine_set_chains."""
+    _lib.check(self._lib.ffn_engine_set_chains(self._h, int(max_chains)))
+
   def set_compute_mode(self, mode: int):
     _lib.check(self._lib.ffn_engine_set_compute_mode(self._h, int(mode)))
     self.compute_mode = int(mode)
@@ -101,7 +105,7 @@ class Engine:
 
   PROFILE_SLOTS = ('barrier_wait', 'act_tma_wait', 'weight_wait', 'umma_issue', 'epi_wait_mma', 'epi_body',
                    'stage', 'paste', 'leader', 'steps', 'kernel', 'conv_layers', 'leader_policy', 'leader_pops',
-                   'leader_fence', 'layer_end_sync')
+                   'chain_barrier_wait', 'unused')
 
   def enable_profiling(self, on: bool = True):
     _lib.check(self._lib.ffn_engine_profile(self._h, None, 1 if on else 0))
@@ -226,6 +230,12 @@ class DeviceCanvas:
     c = _lib.Counters()
     _lib.check(self._lib.ffn_canvas_get_counters(self._h, C.byref(c)))
     return c
+
+  def spec_stats(self) -> dict:
+    """Early-run bookkeeping of the last segment_all (see ffn_canvas_spec_stats)."""
+    buf = (C.c_int64 * 4)()
+    _lib.check(self._lib.ffn_canvas_spec_stats(self._h, buf))
+    return dict(zip(('early_runs', 'early_runs_discarded', 'steps_discarded', 'steps_executed'), [int(v) for v in buf]))
 
   def set_resume(self, iters: int, min_pos, max_pos):
     _lib.check(self._lib.ffn_canvas_set_resume(self._h, int(iters), _lib.i3(min_pos), _lib.i3(max_pos)))

@@ -121,6 +121,12 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
  * ffn_canvas_destroy (until then those canvases stay fully usable). */
 void ffn_engine_destroy(FfnEngine* engine);
 int ffn_engine_set_compute_mode(FfnEngine* engine, int compute_mode);
+/* Flood-fill chains time-multiplexed over the SMs by ONE persistent kernel (1..3; 0 = default 3): objects of a
+ * canvas in flight at once in ffn_canvas_segment_all (committed in seed order — the results are those of the
+ * sequential reference loop, inference.py:538-683, for any value), and patches of a batch sharing a round in
+ * ffn_predict (the reference batches FoVs into one session.run, executor.py:266-340).  1 = strictly one
+ * object / patch at a time. */
+int ffn_engine_set_chains(FfnEngine* engine, int max_chains);
 /* Number of SMs (CTAs of the cooperative grid) this engine's kernel occupies; 0 = all.  Several engines
  * with disjoint SM budgets (e.g. 3 x 49) driven from different host threads run their persistent kernels
  * CONCURRENTLY on one GPU: the B200 form of the reference's batching across canvases
@@ -209,6 +215,10 @@ int ffn_canvas_seed_peaks(FfnCanvas* canvas, const float voxel_size_zyx[3], cons
 /* Canvas._max_id / counters carried across calls (checkpoint restore, init segmentation). */
 int ffn_canvas_set_max_id(FfnCanvas* canvas, int64_t max_id);
 int ffn_canvas_get_counters(FfnCanvas* canvas, FfnCounters* out);
+/* Bookkeeping of the last ffn_canvas_segment_all: out[0] objects started ahead of their turn, out[1] of
+ * those discarded (re-run in turn or rejected by the in-order gating), out[2] FoV steps of the discarded runs,
+ * out[3] FoV steps executed in total (FfnCounters.inference_calls counts only what the reference counts). */
+int ffn_canvas_spec_stats(FfnCanvas* canvas, int64_t out[4]);
 
 /* Multi-GPU merge helpers: raw device pointers for NCCL, and the HBM-bound
  * relabel kernel that adds a rank's ID offset to every label > 0. */

@@ -214,6 +214,71 @@ def test_device_loop_bit_exact_vs_hybrid_oracle(engines, g64, mode):
   cv.close()
 
 
+def _run_segment_all(e, vol, seeds, chains, **opts):
+  from ffn_b200 import _lib, engine as eng
+  e.set_chains(chains)
+  cv = eng.DeviceCanvas(e, vol, eng.make_options(**opts), 128.0, 33.0)
+  origins, overlaps, ctr = cv.segment_all(seeds)
+  out = dict(seg=cv.read(_lib.ARRAY_SEGMENTATION), seed=cv.read(_lib.ARRAY_SEED), qprob=cv.read(_lib.ARRAY_QPROB),
+             origins=[(o.id, tuple(o.start_zyx), o.iters) for o in origins],
+             overlaps=sorted((o.id, o.other_id, o.count) for o in overlaps),
+             ctr={n: getattr(ctr, n) for n, _ in ctr._fields_ if n not in ('device_seconds', 'kernel_launches')},
+             spec=cv.spec_stats())
+  cv.close()
+  e.set_chains(0)
+  return out
+
+
+@pytest.mark.parametrize('case', ['golden64', 'phantom'])
+def test_chains_commit_in_seed_order(engines, g64, case):
+  """Several objects in flight (chains, started ahead of their turn in private seed arrays) must give the
+  results of the strictly sequential loop: labels, ids, origins (incl. per-object iters), overlaps, every
+  counter, the probability map and Canvas.seed — bit for bit, because labels are committed in seed order and
+  an early run that could have seen a different `segmentation > 0` answer is redone in turn."""
+  from ffn_b200.synthetic import voronoi_phantom
+  e = engines['tc']
+  if case == 'golden64':
+    vol, seeds, opts = g64['volume'], g64['seeds'], {}
+  else:
+    vol = voronoi_phantom((96, 112, 128), seed=7, cell_volume=40000.0)
+    seeds = ff.grid_seeds(vol.shape, step=12, offsets=(0, 6))
+    opts = dict(min_segment_size=3000)
+  one = _run_segment_all(e, vol, seeds, 1, **opts)
+  assert one['spec']['early_runs'] == 0 and one['spec']['steps_executed'] == one['ctr']['inference_calls']
+  for chains in (2, 3):
+    many = _run_segment_all(e, vol, seeds, chains, **opts)
+    print('%s, %d chains: %d early runs, %d discarded (%d steps), %d steps executed for %d counted' % (
+        case, chains, many['spec']['early_runs'], many['spec']['early_runs_discarded'], many['spec']['steps_discarded'],
+        many['spec']['steps_executed'], many['ctr']['inference_calls']))
+    np.testing.assert_array_equal(many['seg'], one['seg'])
+    np.testing.assert_array_equal(many['qprob'], one['qprob'])
+    np.testing.assert_array_equal(many['seed'], one['seed'])
+    assert many['origins'] == one['origins']
+    assert many['overlaps'] == one['overlaps']
+    assert many['ctr'] == one['ctr']
+    assert many['spec']['steps_executed'] == many['ctr']['inference_calls'] + many['spec']['steps_discarded']
+  assert len(one['origins']) >= 3
+
+
+def test_batched_predict_shares_rounds(engines, golden_dir):
+  """ffn_predict(batch): patches run three per round through one pipeline (executor.py:266-340 batches FoVs into
+  one session.run); every patch's logits are bit-identical to its single-patch call, for any chain count."""
+  pat = np.load(os.path.join(golden_dir, 'net_patches.npz'))
+  e = engines['tc']
+  seeds = np.concatenate([pat['seed'], pat['seed'][::-1], pat['seed'][:3]])
+  imgs = np.concatenate([pat['image'], pat['image'][::-1], pat['image'][:3]])
+  got = e.predict(seeds, imgs)                     # 13 patches: 4 full rounds + one of a single patch
+  e.set_chains(1)
+  ref = e.predict(seeds, imgs)
+  e.set_chains(2)
+  two = e.predict(seeds, imgs)
+  e.set_chains(0)
+  np.testing.assert_array_equal(got, ref)
+  np.testing.assert_array_equal(two, ref)
+  for i in (0, 4, 12):
+    np.testing.assert_array_equal(e.predict(seeds[i], imgs[i]), ref[i])
+
+
 def test_masks_and_rejections_vs_hybrid_oracle(engines):
   """Movement mask, seed mask, min_boundary_dist, small-object rejection (-1 markers)."""
   from ffn_b200 import _lib, engine as eng

@@ -1,14 +1,31 @@
-"""FoV-steps/s benchmark of the B200 flood-fill engine (contract: see DESIGN.md "Measurement").
+"""FoV-steps/s and segmented-voxels/s benchmark of the B200 flood-fill engine (contract: DESIGN.md "Measurement").
 
-  python bench.py --gpus 1 --steps 256 --warmup 8            # our arm
-  python bench.py --impl reference --steps 16 --warmup 3    # reference arm (CPU restatement)
+  python bench.py --gpus 1 --steps K --warmup W            # our arm, N = 1
+  python bench.py --impl reference --steps K --warmup W    # reference arm (CPU restatement, rank 0 only)
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload at every N: BASELINE.json configs[1] per GPU — single-seed flood fills (one object after
-another until K steps are done) on a synthetic 256^3 Voronoi-membrane volume (seed 1 + rank),
-ConvStack3DFFNModel depth 12, fov 33^3, deltas 8, FIB-25 weights, fp16-operand tcgen05 mode.
-A "step" is ONE FoV step (network + merge + paste + movement policy) of the persistent kernel.
-Ranks work on independent volumes (no data-path collective): scaling is weak.
+Workloads (BASELINE.json):
+
+  N = 1   configs[0] — the configuration the metric is quoted on: the README run
+          `run_inference.py configs/inference_training_sample2.pbtxt` on a 250^3 bounding box, i.e.
+          Canvas.segment_all with PolicyPeaks seeds and the pbtxt's inference options, ConvStack3DFFNModel depth 12,
+          fov 33^3, deltas 8, FIB-25 weights, on the synthetic stand-in for training_sample2 (Voronoi phantom,
+          seed 0).  ONE timed pass = the whole canvas (~25.6 k FoV steps, ~585 objects): a flood
+          fill has no meaningful K-step prefix (seed policy, object commits and the last objects are part of
+          the metric), so --steps only caps the seed list when it is small (profiler runs: --steps < 1000 means
+          "first K seeds") and is otherwise ignored; `steps` in the output line is the number of FoV steps done.
+          `value` = FoV steps / wall clock of segment_all (device PolicyPeaks included) with the volume resident
+          in HBM; `e2e` = the same metric through Runner.run (volume file -> pinned H2D -> segment_all -> D2H ->
+          seg-*.npz / .prob written), which is what a user of run_inference.py gets.
+  N > 1   configs[3] — a 1024^3 volume as 8 slabs of 512^3 (2x2x2), slabs_of_rank(8, rank, N) per GPU, every slab an
+          independent canvas (the reference's subvolume semantics, doc/manual.md:107-127), then the merge inside the
+          timed region: all_gather of the id counts, id offsets on the device, NCCL gather of the label AND
+          probability slabs to rank 0.  Strong scaling over the same 8 slabs for N = 2, 4, 8.  (At N = 1 the driver's
+          line is configs[0]; both are FoV steps/s of the same kernel on canvases of the same statistics.)
+
+A "FoV step" is one network evaluation + merge + paste + movement-policy update of the persistent kernel
+(= the reference's 'inference-calls' counter); steps of objects that were started ahead of their turn and
+then discarded are NOT counted (they are reported as `steps_executed`).
 """
 
 import argparse
@@ -16,6 +33,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -27,8 +45,11 @@ sys.path.insert(0, REPO)
 FOV = (33, 33, 33)
 DELTAS = (8, 8, 8)
 DEPTH = 12
-VOLUME = (256, 256, 256)
 WEIGHTS = os.path.join(REPO, 'tests', 'golden', 'fib25_convstack.npz')
+WORKLOAD_N1 = ('configs[0]: Runner.run / Canvas.segment_all with PolicyPeaks on a synthetic 250^3 volume (seed 0), '
+               'ConvStack3DFFNModel depth 12 fov 33^3 deltas 8, FIB-25 weights, options of inference_training_sample2.pbtxt')
+WORKLOAD_MULTI = ('configs[3]: synthetic 1024^3 as 8 slabs of 512^3 (seeds 300..307), slabs_of_rank(8, rank, N), '
+                  'Canvas.segment_all with PolicyPeaks per slab, NCCL merge of labels + probability maps on rank 0')
 
 
 def flops_per_step():
@@ -47,34 +68,18 @@ def load_weights():
   return (ws, bs), 'random-init'
 
 
-def make_volume(seed):
+def make_volume(shape, seed):
   from ffn_b200.synthetic import voronoi_phantom
-  cache = os.path.join(REPO, 'gpurun_out', '.bench_vol_%d_%d.npy' % (VOLUME[0], seed))
+  cache = os.path.join(REPO, 'gpurun_out', '.bench_vol_%d_%d.npy' % (shape[0], seed))
   if os.path.exists(cache):
     return np.load(cache)
-  vol = voronoi_phantom(VOLUME, seed)
+  vol = voronoi_phantom(shape, seed)
   try:
     os.makedirs(os.path.dirname(cache), exist_ok=True)
     np.save(cache, vol)
   except OSError:
     pass
   return vol
-
-
-def seed_points(vol, count):
-  """Deterministic object centres: interior bright voxels on a coarse lattice."""
-  from ffn_b200.synthetic import interior_seed
-  pts = []
-  lo, hi, step = 40, VOLUME[0] - 40, 44
-  for z in range(lo, hi, step):
-    for y in range(lo, hi, step):
-      for x in range(lo, hi, step):
-        p = interior_seed(vol, (z, y, x))
-        if all(16 <= c < s - 17 for c, s in zip(p, VOLUME)):
-          pts.append(p)
-        if len(pts) >= count:
-          return pts
-  return pts
 
 
 class ClockSampler:
@@ -125,23 +130,29 @@ class ClockSampler:
 
 
 def ncu_dram_traffic():
-  """DRAM bytes (read + write) of one flood-kernel launch from the committed `ncu --set full` capture
-  (profiles/r01_ncu_full_flood_kernel_steps16.txt: one launch = 16 FoV steps), or None."""
-  path = os.path.join(REPO, 'profiles', 'r01_ncu_full_flood_kernel_steps16.txt')
+  """DRAM bytes (read + write) per launch of the flood kernel from the newest committed `ncu --set full`
+  summary under profiles/ (file name carries the FoV steps of the captured launch), or None."""
+  import glob
+  import re
   scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-  total, seen = 0.0, 0
-  try:
-    with open(path) as f:
-      for line in f:
-        for key in ('dram__bytes_read.sum [', 'dram__bytes_write.sum ['):
-          if line.startswith(key):
-            unit = line[len(key):line.index(']')]
-            total += float(line.split('=')[1]) * scale[unit]
-            seen += 1
-  except (OSError, ValueError, KeyError):
-    return None
-  return {'bytes_per_launch': total, 'steps_per_launch': 16, 'bytes_per_step': total / 16,
-          'source': 'profiles/r01_ncu_full_flood_kernel_steps16.txt'} if seen == 2 else None
+  for path in sorted(glob.glob(os.path.join(REPO, 'profiles', 'r*_ncu_full_flood_kernel_steps*.txt')), reverse=True):
+    m = re.search(r'steps(\d+)', os.path.basename(path))
+    total, seen = 0.0, 0
+    try:
+      with open(path) as f:
+        for line in f:
+          for key in ('dram__bytes_read.sum [', 'dram__bytes_write.sum ['):
+            if line.startswith(key):
+              unit = line[len(key):line.index(']')]
+              total += float(line.split('=')[1]) * scale[unit]
+              seen += 1
+    except (OSError, ValueError, KeyError):
+      continue
+    if seen == 2 and m:
+      n = int(m.group(1))
+      return {'bytes_per_launch': total, 'steps_per_launch': n, 'bytes_per_step': total / n,
+              'source': os.path.relpath(path, REPO)}
+  return None
 
 
 def measured_peaks():
@@ -149,8 +160,8 @@ def measured_peaks():
   if os.path.exists(path):
     with open(path) as f:
       d = json.load(f)
-    return d.get('bf16_tflops', 1590.0), d.get('bf16_tflops_sustained', 1400.0), 'measured'
-  return 1590.0, 1400.0, 'fallback'
+    return d.get('bf16_tflops', 1590.0), d.get('bf16_tflops_sustained', 1400.0), 'measured (MEASURED_PEAKS.json)'
+  return 1590.0, 1400.0, 'fallback (B200_PROFILING.md)'
 
 
 def best_cpu_threads():
@@ -179,123 +190,361 @@ def best_cpu_threads():
   return best
 
 
-def run_cpu_steps(vol, points, n_steps, threads=None):
-  """Times n_steps FoV steps of the CPU restatement (oracle/) on this host; returns (steps, seconds)."""
+def run_cpu_sample(vol, n_steps, threads):
+  """The reference's path restated on the CPU (oracle/): PolicyPeaks seeds + Canvas.segment_all on the same
+  volume, stopped after n_steps FoV steps.  Returns (steps, voxels labelled so far, seconds of the flood fill,
+  seconds of the seed policy)."""
   import torch
   from oracle import flood_fill as ff
+  from oracle import seed_peaks
   from oracle.network import ConvStackOracle
-  if threads:
-    torch.set_num_threads(threads)
+  torch.set_num_threads(threads)
   (w, b), _ = load_weights()
   net = ConvStackOracle(w, b)
   image = (vol.astype(np.float32) - np.float32(128.0)) / np.float32(33.0)
-  done = 0
   t0 = time.time()
-  for p in points:
-    if done >= n_steps:
-      break
-    cv = ff.Canvas(net, image, FOV, DELTAS, ff.Options())
-    budget = n_steps - done
+  seeds = seed_peaks.policy_peaks(image, margin_zyx=(16, 16, 16))
+  t_seed = time.time() - t0
+  cv = ff.Canvas(net, image, FOV, DELTAS, ff.Options())
 
-    class _Stop(Exception):
-      pass
-    orig = cv.update_at
+  class _Stop(Exception):
+    pass
+  orig = cv.update_at
 
-    def limited(pos, _orig=orig, _cv=cv):
-      if len(_cv.trace) >= budget:
-        raise _Stop()
-      return _orig(pos)
-    cv.update_at = limited
-    try:
-      cv.segment_at(p)
-    except _Stop:
-      pass
-    done += len(cv.trace)
-  return done, time.time() - t0
+  def limited(pos):
+    if len(cv.trace) >= n_steps:
+      raise _Stop()
+    return orig(pos)
+  cv.update_at = limited
+  t0 = time.time()
+  try:
+    cv.segment_all(seeds)
+  except _Stop:
+    pass
+  secs = time.time() - t0
+  return len(cv.trace), int((cv.segmentation > 0).sum()), secs, t_seed
 
 
-def throughput_mode(chains, steps):
-  import threading
-  from ffn_b200 import engine as eng
-  (w, b), _ = load_weights()
-  sms = None
-  engines = []
-  for _ in range(chains):
-    e = eng.Engine(w, b, FOV, DELTAS)
-    sms = sms or e.info()['grid']
-    e.set_grid(sms // chains)
-    engines.append(e)
-  out = [None] * chains
-  gate = threading.Barrier(chains)
+def device_seeds(cv, margin=(16, 16, 16)):
+  """PolicyPeaks on the device + the border filter of BaseSeedPolicy.__next__ (seed.py:81-88)."""
+  from ffn_b200.inference import seed as seed_mod
+  noise = seed_mod._tie_break_noise(tuple(cv.shape))   # RandomState(42).rand(*shape), seed.py:133-139
+  coords = cv.seed_peaks((1, 1, 1), noise)
+  m = np.asarray(margin)[None]
+  keep = np.all((coords - m >= 0) & (coords + m < np.asarray(cv.shape)[None]), axis=1)
+  return np.ascontiguousarray(coords[keep], dtype=np.int32), noise.nbytes
 
-  def worker(i):
-    vol = make_volume(1 + i)
-    pts = seed_points(vol, 64)
-    cv = eng.DeviceCanvas(engines[i], vol, eng.make_options(), 128.0, 33.0)
-    done, k = 0, 0
-    while done < 8:
-      done += int(cv.segment_at(pts[k % len(pts)], max_steps=8 - done).iters)
-      k += 1
-    c0 = cv.counters()
-    gate.wait()
-    t0 = time.perf_counter()
-    done = ncalls = 0
-    while done < steps:
-      done += int(cv.segment_at(pts[k % len(pts)], max_steps=steps - done).iters)
-      k += 1
-      ncalls += 1
-    out[i] = (done, time.perf_counter() - t0, cv.counters().device_seconds - c0.device_seconds, ncalls)
-    cv.close()
-  threads = [threading.Thread(target=worker, args=(i,)) for i in range(chains)]
-  for t in threads:
-    t.start()
-  for t in threads:
-    t.join()
-  for e in engines:
-    e.close()
-  total = sum(o[0] for o in out)
-  wall = max(o[1] for o in out)
-  return {'chains': chains, 'sms_per_chain': sms // chains, 'value': total / wall, 'unit': 'FoV steps/s (aggregate, wall clock)',
-          'per_chain_steps_per_s_device': [o[0] / o[2] for o in out], 'per_chain_wall_s': [o[1] for o in out],
-          'per_chain_calls': [o[3] for o in out],
-          'roofline_frac': total / wall * flops_per_step() / 1e12 / measured_peaks()[0]}
+
+def request_for(vol_path, out_dir):
+  from google.protobuf import text_format
+  from ffn.inference import inference_pb2
+  req = inference_pb2.InferenceRequest()
+  # configs/inference_training_sample2.pbtxt with the volume / checkpoint paths of this box
+  text_format.Parse('''image { hdf5: "%s:raw" } image_mean: 128 image_stddev: 33 checkpoint_interval: 1800
+    seed_policy: "PolicyPeaks" model_checkpoint_path: "%s" model_name: "convstack_3d.ConvStack3DFFNModel"
+    model_args: "{\\"depth\\": 12, \\"fov_size\\": [33, 33, 33], \\"deltas\\": [8, 8, 8]}"
+    segmentation_output_dir: "%s"
+    inference_options { init_activation: 0.95 pad_value: 0.05 move_threshold: 0.9 min_boundary_dist { x: 1 y: 1 z: 1}
+                        segment_threshold: 0.6 min_segment_size: 1000 }''' % (vol_path, WEIGHTS, out_dir), req)
+  return req
 
 
 def reference_arm(args, rank):
-  """The reference's own CPU implementation of the path: TensorFlow cannot be installed offline, so
-  this times the CPU restatement in oracle/ (kind 'port') with all host threads on a bounded
-  sample of the same workload."""
+  """The reference's own CPU implementation of the path: TensorFlow cannot be installed offline, so this times
+  the CPU restatement in oracle/ (kind 'port') with the host threads torch's conv3d can use, on a bounded
+  sample of the same workload: the first FoV steps of the same segment_all on the same volume and seeds."""
   if rank != 0:
     return
-  import torch
+  n1 = args.gpus == 1
+  vol = make_volume((250, 250, 250), 0) if n1 else make_volume((512, 512, 512), 300)
+  if not n1:
+    vol = vol[:256, :256, :256]     # bounded sample: a corner of slab 0 (the CPU seed policy alone is minutes on 512^3)
   threads = best_cpu_threads()
-  vol = make_volume(1)
-  pts = seed_points(vol, 64)
-  run_cpu_steps(vol, pts, max(args.warmup, 1), threads)
-  steps, secs = run_cpu_steps(vol, pts, args.steps, threads)
+  budget = args.steps if 0 < args.steps < 1000 else 24     # a bounded sample: ~1 s of CPU per FoV step on 8 cores
+  steps, vox, secs, t_seed = run_cpu_sample(vol, budget, threads)
   value = steps / secs
   line = {
       'impl': 'reference', 'metric': 'fov_steps_per_sec', 'value': value, 'unit': 'FoV steps/s',
-      'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / steps,
-      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': 'configs[1]: single-seed flood-fill, depth 12 fov 33^3 deltas 8, synthetic 256^3',
-                 'note': 'CPU restatement of the reference path (TensorFlow not installable offline)'},
+      'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / max(steps, 1),
+      'higher_is_better': True, 'scaling': 'weak' if n1 else 'strong', 'vs_baseline': None, 'dtype': 'f32',
+      'data': 'synthetic',
+      'config': {'workload': WORKLOAD_N1 if n1 else WORKLOAD_MULTI,
+                 'note': 'CPU restatement of the reference path (TensorFlow not installable offline); '
+                         'published P100 run of the reference: 65.5 FoV steps/s, 35.2 k voxels/s (README)'},
       'cpu_baseline': {'value': value, 'unit': 'FoV steps/s', 'cores': threads, 'kind': 'port',
-                       'sample': '%d FoV steps of the same flood fill' % steps},
+                       'sample': 'first %d FoV steps of the same segment_all%s; CPU PolicyPeaks took %.1f s (not in value)' % (
+                           steps, '' if n1 else ' on a 256^3 corner of slab 0', t_seed),
+                       'voxels_per_sec': vox / secs},
       'e2e': {'value': value, 'unit': 'FoV steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
   }
   print(json.dumps(line), flush=True)
 
 
+def extras_n1(engine, eng, _lib, args):
+  """Secondary numbers: the single-seed latency case (configs[1]) and the batched conv stack alone."""
+  from ffn_b200.synthetic import interior_seed
+  out = {}
+  vol1 = make_volume((256, 256, 256), 1)
+  cv = eng.DeviceCanvas(engine, vol1, eng.make_options(), 128.0, 33.0)
+  start = interior_seed(vol1, (128, 128, 128))
+  cv.segment_at(start)
+  c0 = cv.counters(); st = cv.segment_at(start); c1 = cv.counters()
+  dev = c1.device_seconds - c0.device_seconds
+  out['configs1_single_seed_256'] = {'steps': int(st.iters), 'steps_per_s': st.iters / dev, 'us_per_step': 1e6 * dev / st.iters,
+                                     'note': 'one object = a strictly sequential chain of FoV steps: latency-bound'}
+  cv.close()
+  rng = np.random.RandomState(0)
+  batch = 48
+  seed = np.where(rng.rand(batch, *FOV) < 0.3, rng.randn(batch, *FOV) * 2, -2.9444).astype(np.float32)
+  img = rng.randn(batch, *FOV).astype(np.float32)
+  engine.predict(seed, img)
+  engine.predict(seed, img)
+  ns = engine.info()['last_kernel_ns']
+  rate = batch / (ns * 1e-9)
+  out['predict_batch48'] = {'patches_per_s': rate, 'kernel_us': ns / 1e3,
+                            'roofline_frac': rate * flops_per_step() / 1e12 / measured_peaks()[0],
+                            'note': 'ffn_predict(batch=48): the conv stack alone, three patches per round'}
+  return out
+
+
+def run_n1(args, rank, local_rank):
+  import torch
+  from ffn_b200 import _lib
+  from ffn_b200 import engine as eng
+  (w, b), wdesc = load_weights()
+  mode = {'fp16': _lib.COMPUTE_FP16_TC, 'fp32': _lib.COMPUTE_FP32, 'x2': _lib.COMPUTE_FP16X2_TC}[args.compute]
+  engine = eng.Engine(w, b, FOV, DELTAS, device=local_rank, compute_mode=mode)
+  if args.chains:
+    engine.set_chains(args.chains)
+  shape = (250, 250, 250)
+  vol = make_volume(shape, 0)
+  pinned = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
+  pinned.numpy()[...] = vol
+  opts = eng.make_options()
+  seed_cap = args.steps if 0 < args.steps < 1000 else 0
+
+  # ---- warm-up: W short flood fills on a scratch canvas (allocator, instruction cache, weights in L2)
+  warm = eng.DeviceCanvas(engine, pinned.numpy(), opts, 128.0, 33.0)
+  wseeds, _ = device_seeds(warm)
+  warm.segment_all(wseeds[:max(8 * max(args.warmup, 3), 24)])
+  warm.close()
+
+  # ---- device-resident leg: the volume is in HBM before the timed region starts
+  canvas = eng.DeviceCanvas(engine, pinned.numpy(), opts, 128.0, 33.0, keep_probability_maps=True)
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  torch.cuda.synchronize()
+  launches0 = engine.info()['launches']
+  t0 = time.perf_counter()
+  seeds, _ = device_seeds(canvas)
+  t_seed = time.perf_counter() - t0
+  if seed_cap:
+    seeds = seeds[:seed_cap]
+  origins, _, ctr = canvas.segment_all(seeds, overlaps_cap=max(64 * len(seeds), 1 << 16))
+  torch.cuda.synchronize()
+  wall = time.perf_counter() - t0
+  clocks = sampler.stop()
+  launches = engine.info()['launches'] - launches0 + 10        # + the ten seed-policy kernels
+  spec = canvas.spec_stats()
+  steps = int(ctr.inference_calls)
+  dev_seconds = float(ctr.device_seconds)
+  canvas.close()
+
+  # ---- end-to-end leg: what run_inference.py does — Runner.start + Runner.run on a volume file
+  from ffn.inference import runner as runner_mod
+  tmp = tempfile.mkdtemp(prefix='ffn_bench_')
+  vol_path = os.path.join(tmp, 'vol.npy')
+  np.save(vol_path, vol)
+  runner = runner_mod.Runner(device=local_rank, compute_mode=mode)
+  runner.start(request_for(vol_path, os.path.join(tmp, 'out')))
+  if args.chains:
+    runner.executor.engine.set_chains(args.chains)
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  rc = runner.run((0, 0, 0), shape)
+  e2e_seconds = time.perf_counter() - t0
+  cnt = {k: c.value for k, c in rc.counters}
+  e2e_steps = int(cnt.get('inference-calls', 0))
+  e2e_vox = int(cnt.get('voxels-segmented', 0))
+  runner.stop_executor()
+  del rc
+
+  value = steps / wall
+  burst, sustained, src = measured_peaks()
+  kernel_rate = steps / dev_seconds                                  # counted steps over the flood kernel's own time
+  achieved = kernel_rate * flops_per_step() / 1e12
+  executed = spec['steps_executed'] / dev_seconds * flops_per_step() / 1e12
+  line = {
+      'metric': 'fov_steps_per_sec', 'value': value, 'unit': 'FoV steps/s', 'n_gpus': 1,
+      'steps': steps, 'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * wall / max(steps, 1),
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+      'dtype': {'fp16': 'f16', 'fp32': 'f32', 'x2': 'f16x2 (hi+lo split, ~f32)'}[args.compute], 'data': 'synthetic',
+      'config': {
+          'workload': WORKLOAD_N1,
+          'weights': wdesc, 'accumulate': 'f32', 'timed_pass': 'one whole segment_all (device PolicyPeaks + flood fill + commits); '
+          '--steps is ignored unless < 1000 (then: first K seeds)',
+          'l2': 'canvas state (image u8 + 4 seed f32 arrays + segmentation i32 + qprob u8 = 330 MB) exceeds L2; '
+                'the ~36 MB activation working set of three chains is L2-resident by design',
+          'published_reference_p100': {'fov_steps_per_sec': 65.5, 'voxels_per_sec': 35216},
+      },
+      'voxels_per_sec': float(ctr.voxels_segmented) / wall,
+      'segments': int(ctr.segments), 'objects_run': int(ctr.segment_at_calls), 'seeds': int(len(seeds)),
+      'seed_policy_seconds': t_seed,
+      'device_only': {'value': kernel_rate, 'unit': 'FoV steps/s', 'seconds': dev_seconds,
+                      'note': 'CUDA events around the flood-kernel launches only'},
+      'chains': {'max': args.chains or 3, **spec},
+      'gpu_launches': int(launches),
+      'clocks': clocks,
+      'e2e': {'value': e2e_steps / e2e_seconds, 'unit': 'FoV steps/s', 'voxels_per_sec': e2e_vox / e2e_seconds,
+              'seconds': e2e_seconds,
+              'h2d_bytes_per_step': int((vol.nbytes + 8 * vol.size) / max(e2e_steps, 1)),
+              'd2h_bytes_per_step': int((4 * vol.size + vol.size) / max(e2e_steps, 1)),
+              'path': 'Runner.run: volume file -> H2D (uint8 volume + float64 PolicyPeaks tie-break noise) -> '
+                      'segment_all -> D2H (int32 labels + uint8 probabilities) -> seg-*.npz + .prob written'},
+      'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': burst, 'unit': 'TFLOP/s',
+                   'frac': achieved / burst, 'frac_of_sustained': achieved / sustained, 'peak_source': src,
+                   'flops_per_step': flops_per_step(), 'executed_frac': executed / burst,
+                   'note': 'achieved = counted FoV steps x FLOP/step / flood-kernel seconds (CUDA events around its '
+                           'launches); executed_frac also counts the steps of discarded early runs',
+                   'traffic': ncu_dram_traffic()},
+  }
+  if not args.skip_extras and args.compute == 'fp16':
+    try:
+      line.update(extras_n1(engine, eng, _lib, args))
+    except Exception as e:  # pylint: disable=broad-except
+      line['extras_error'] = repr(e)
+  if not args.skip_extras:
+    try:
+      threads = best_cpu_threads()
+      csteps, cvox, csecs, ct_seed = run_cpu_sample(vol, args.cpu_baseline_steps, threads)
+      line['cpu_baseline'] = {'value': csteps / csecs, 'unit': 'FoV steps/s', 'cores': threads, 'kind': 'port',
+                              'sample': 'first %d FoV steps of the same segment_all; CPU PolicyPeaks took %.1f s (not in value)' % (
+                                  csteps, ct_seed),
+                              'voxels_per_sec': cvox / csecs}
+    except Exception as e:  # pylint: disable=broad-except
+      line['cpu_baseline'] = {'error': repr(e)}
+  print(json.dumps(line), flush=True)
+  engine.close()
+
+
+def run_multi(args, rank, local_rank, world):
+  import torch
+  import torch.distributed as dist
+  from ffn_b200 import _lib, distributed as D
+  from ffn_b200 import engine as eng
+  (w, b), wdesc = load_weights()
+  engine = eng.Engine(w, b, FOV, DELTAS, device=local_rank)
+  if args.chains:
+    engine.set_chains(args.chains)
+  n_slabs, slab = 8, (512, 512, 512)
+  if args.slab:
+    slab = (args.slab,) * 3
+  mine = D.slabs_of_rank(n_slabs, rank, world)
+  vols = []
+  for k in mine:                                           # untimed: synthetic data generation
+    v = make_volume(slab, 300 + k)
+    p = torch.empty(slab, dtype=torch.uint8, pin_memory=True)
+    p.numpy()[...] = v
+    vols.append(p)
+  opts = eng.make_options()
+  dev = torch.device('cuda', local_rank)
+
+  def barrier():
+    dist.barrier()
+    torch.cuda.synchronize()
+
+  warm = eng.DeviceCanvas(engine, vols[0].numpy()[:160, :160, :160].copy(), opts, 128.0, 33.0)
+  wseeds, _ = device_seeds(warm)
+  warm.segment_all(wseeds[:max(8 * max(args.warmup, 3), 24)])
+  warm.close()
+
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  barrier()
+  t0 = time.perf_counter()
+  canvases, steps, vox, dev_s, executed, h2d = [], 0, 0, 0.0, 0, 0
+  launches0 = engine.info()['launches']
+  for p in vols:                                           # each slab: upload, device PolicyPeaks, segment_all
+    cv = eng.DeviceCanvas(engine, p.numpy(), opts, 128.0, 33.0, keep_probability_maps=True)
+    seeds, nbytes = device_seeds(cv)
+    h2d += p.numpy().nbytes + nbytes
+    _, _, ctr = cv.segment_all(seeds, overlaps_cap=max(64 * len(seeds), 1 << 16))
+    steps += int(ctr.inference_calls)
+    vox += int(ctr.voxels_segmented)
+    dev_s += float(ctr.device_seconds)
+    executed += cv.spec_stats()['steps_executed']
+    canvases.append((cv, int(ctr.max_id)))
+  torch.cuda.synchronize()
+  t_work = time.perf_counter() - t0
+  # ---- the one exchange step: ids made globally unique, label + probability slabs gathered on rank 0
+  tm = time.perf_counter()
+  labs = [D.canvas_tensor(cv, _lib.ARRAY_SEGMENTATION, slab, '<i4', dev) for cv, _ in canvases]     # alias engine memory
+  probs = [D.canvas_tensor(cv, _lib.ARRAY_QPROB, slab, '|u1', dev) for cv, _ in canvases]
+  gl, gp, _, total_ids = D.merge_slabs(labs, probs, [m for _, m in canvases], dst=0,
+                                       add_offset=lambda i, o: canvases[i][0].add_id_offset(o))    # HBM-bound relabel kernel
+  gathered_vox = 0
+  if rank == 0:
+    gathered_vox = int(sum(int((t > 0).sum()) for row in gl for t in row))
+    assert sum(t.numel() for row in gp for t in row) == n_slabs * slab[0] * slab[1] * slab[2]
+  del gl, gp
+  torch.cuda.synchronize()
+  t_merge = time.perf_counter() - tm
+  barrier()
+  total = time.perf_counter() - t0
+  clocks = sampler.stop()
+  launches = engine.info()['launches'] - launches0 + 10 * len(vols)
+
+  stats = torch.tensor([steps, vox, dev_s, t_work, t_merge, total, executed, launches, h2d], dtype=torch.float64, device=dev)
+  smax = stats.clone(); dist.all_reduce(smax, op=dist.ReduceOp.MAX)
+  smin = stats.clone(); dist.all_reduce(smin, op=dist.ReduceOp.MIN)
+  ssum = stats.clone(); dist.all_reduce(ssum, op=dist.ReduceOp.SUM)
+  if rank == 0:
+    wall = float(smax[5])
+    value = float(ssum[0]) / wall
+    burst, sustained, src = measured_peaks()
+    achieved = float(ssum[0]) / float(smax[2]) / world * flops_per_step() / 1e12     # per GPU, busiest rank's kernel time
+    line = {
+        'metric': 'fov_steps_per_sec', 'value': value, 'unit': 'FoV steps/s', 'n_gpus': world,
+        'steps': int(ssum[0]), 'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * wall / max(float(ssum[0]), 1.0),
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD_MULTI, 'weights': wdesc, 'accumulate': 'f32', 'slab': list(slab),
+                   'timed_pass': 'per rank: upload + device PolicyPeaks + segment_all of its slabs, then the NCCL merge; '
+                                 'barrier to barrier, max over ranks; --steps is ignored',
+                   'l2': 'every slab canvas (3.1 GB) exceeds L2'},
+        'voxels_per_sec': float(ssum[1]) / wall,
+        'merge_seconds': float(smax[4]), 'work_seconds_max': float(smax[3]), 'work_seconds_min': float(smin[3]),
+        'imbalance': float(smax[3]) / max(float(smin[3]), 1e-9),
+        'labelled_voxels_on_rank0_after_merge': gathered_vox, 'total_ids': int(total_ids),
+        'steps_executed': int(ssum[6]),
+        'gpu_launches': int(ssum[7]),
+        'clocks': clocks,
+        'e2e': {'value': value, 'unit': 'FoV steps/s', 'voxels_per_sec': float(ssum[1]) / wall,
+                'h2d_bytes_per_step': int(float(ssum[8]) / max(float(ssum[0]), 1.0)),
+                'd2h_bytes_per_step': 0,
+                'path': 'the timed region IS the end-to-end path: pinned uint8 slabs + PolicyPeaks noise H2D, '
+                        'segment_all, merged labels / probabilities left in rank 0 HBM (NCCL gather, no D2H)'},
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': burst, 'unit': 'TFLOP/s', 'frac': achieved / burst,
+                     'frac_of_sustained': achieved / sustained, 'peak_source': src, 'flops_per_step': flops_per_step(),
+                     'note': 'per GPU: counted steps x FLOP/step / (busiest rank flood-kernel seconds x N)',
+                     'traffic': ncu_dram_traffic()},
+    }
+    print(json.dumps(line), flush=True)
+  for cv, _ in canvases:
+    cv.close()
+  engine.close()
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=256)
-  ap.add_argument('--warmup', type=int, default=8)
+  ap.add_argument('--steps', type=int, default=0)
+  ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--compute', default='fp16', choices=['fp16', 'fp32', 'x2'])
+  ap.add_argument('--chains', type=int, default=0, help='objects in flight per GPU (1..3, 0 = default 3)')
+  ap.add_argument('--slab', type=int, default=0, help='N > 1: slab edge instead of 512 (tests)')
   ap.add_argument('--cpu-baseline-steps', type=int, default=24)
-  ap.add_argument('--skip-extras', action='store_true', help='no throughput_mode / cpu_baseline legs (profiler runs)')
+  ap.add_argument('--skip-extras', action='store_true', help='no single-seed / predict / cpu_baseline legs (profiler runs)')
   args = ap.parse_args()
   rank = int(os.environ.get('RANK', '0'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -312,130 +561,10 @@ def main():
   torch.cuda.set_device(local_rank)
   if world > 1:
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-
-  from ffn_b200 import _lib
-  from ffn_b200 import engine as eng
-  (w, b), wdesc = load_weights()
-  mode = {'fp16': _lib.COMPUTE_FP16_TC, 'fp32': _lib.COMPUTE_FP32, 'x2': _lib.COMPUTE_FP16X2_TC}[args.compute]
-  engine = eng.Engine(w, b, FOV, DELTAS, device=local_rank, compute_mode=mode)
-  vol = make_volume(1 + rank)
-  pts = seed_points(vol, 256)
-  # pinned host copy of the volume: the e2e leg uploads it inside its timed region
-  pinned = torch.empty(VOLUME, dtype=torch.uint8, pin_memory=True)
-  pinned.numpy()[...] = vol
-  vol_pinned = pinned.numpy()
-  opts = eng.make_options()
-
-  def barrier():
-    if world > 1:
-      dist.barrier()
-    torch.cuda.synchronize()
-
-  def run_steps(canvas, n, first_point):
-    """Runs exactly n FoV steps as consecutive single-seed flood fills; returns (#launches, next point)."""
-    launches0 = engine.info()['launches']
-    done, k = 0, first_point
-    while done < n:
-      st = canvas.segment_at(pts[k % len(pts)], reset=True, max_steps=n - done)
-      done += int(st.iters)
-      k += 1
-      if st.iters == 0 and k - first_point > 4 * len(pts):
-        raise RuntimeError('no seed point produces FoV steps')
-    return engine.info()['launches'] - launches0, k
-
-  # ---- device-resident leg: canvas lives in HBM before the timed region starts
-  canvas = eng.DeviceCanvas(engine, vol_pinned, opts, 128.0, 33.0, keep_probability_maps=True)
-  _, nxt = run_steps(canvas, max(args.warmup, 3), 0)
-  sampler = ClockSampler(local_rank)
-  sampler.start()
-  barrier()
-  c0 = canvas.counters()
-  launches, nxt = run_steps(canvas, args.steps, nxt)
-  barrier()
-  c1 = canvas.counters()
-  clocks = sampler.stop()
-  dev_seconds = c1.device_seconds - c0.device_seconds      # CUDA events around each launch, engine stream
-  steps_done = c1.inference_calls - c0.inference_calls
-
-  # ---- end-to-end leg: the user's call path with host buffers — canvas creation (H2D of the pinned
-  # uint8 volume), the same flood fills, D2H of the touched seed / segmentation box
-  warm = eng.DeviceCanvas(engine, vol_pinned, opts, 128.0, 33.0, keep_probability_maps=True)   # allocator warm-up
-  warm.close()
-  barrier()
-  t0 = time.perf_counter()
-  cv2 = eng.DeviceCanvas(engine, vol_pinned, opts, 128.0, 33.0, keep_probability_maps=True)
-  d2h = 0
-  done, k = 0, nxt
-  while done < args.steps:
-    st = cv2.segment_at(pts[k % len(pts)], reset=True, max_steps=args.steps - done)
-    done += int(st.iters)
-    k += 1
-    lo = [max(int(a) - 16, 0) for a in st.min_pos]
-    size = [min(int(b) + 17, s) - l for b, s, l in zip(st.max_pos, VOLUME, lo)]
-    out = cv2.read(_lib.ARRAY_SEED, lo, size)
-    d2h += out.nbytes
-  torch.cuda.synchronize()
-  e2e_seconds = time.perf_counter() - t0
-  cv2.close()
-
-  t = torch.tensor([dev_seconds, e2e_seconds, float(steps_done), float(done)], dtype=torch.float64, device='cuda')
-  if world > 1:
-    tmax = t.clone()
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    tsum = t.clone()
-    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    dev_seconds, e2e_seconds = float(tmax[0]), float(tmax[1])
-    total_steps, total_e2e_steps = float(tsum[2]), float(tsum[3])
-  else:
-    total_steps, total_e2e_steps = float(steps_done), float(done)
-
-  if rank == 0:
-    value = total_steps / dev_seconds
-    burst, sustained, src = measured_peaks()
-    achieved = value / world * flops_per_step() / 1e12          # TFLOP/s per GPU
-    line = {
-        'metric': 'fov_steps_per_sec', 'value': value, 'unit': 'FoV steps/s', 'n_gpus': world,
-        'steps': int(steps_done), 'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * dev_seconds / steps_done,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': {'fp16': 'f16', 'fp32': 'f32', 'x2': 'f16x2 (hi+lo split, ~f32)'}[args.compute], 'data': 'synthetic',
-        'config': {
-            'workload': 'configs[1]: single-seed flood-fill, depth 12 fov 33^3 deltas 8, synthetic 256^3 per GPU',
-            'weights': wdesc, 'volume_seed': '1 + rank', 'accumulate': 'f32',
-            'l2': 'canvas state (image u8 + seed f32 + segmentation i32 + qprob u8 = 168 MB) exceeds L2; '
-                  'the 12 MB per-step activation working set is L2-resident by design',
-            'published_p100_steps_per_sec': 84.7,
-        },
-        'gpu_launches': int(launches),
-        'clocks': clocks,
-        'e2e': {'value': total_e2e_steps / e2e_seconds, 'unit': 'FoV steps/s',
-                'h2d_bytes_per_step': int(vol.nbytes / max(done, 1)), 'd2h_bytes_per_step': int(d2h / max(done, 1)),
-                'path': 'ffn_canvas_create (pinned uint8 volume H2D) + ffn_canvas_segment_at + ffn_canvas_read'},
-        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': burst, 'unit': 'TFLOP/s',
-                     'frac': achieved / burst, 'frac_of_sustained': achieved / sustained, 'peak_source': src,
-                     'flops_per_step': flops_per_step(), 'traffic': ncu_dram_traffic()},
-    }
-    # ---- throughput mode (extra, N = 1 only): the reference batches FoVs of several canvases per executor
-    # (InferenceRequest.batch_size); here three engines with 49 SMs each flood-fill three independent 256^3
-    # volumes concurrently, one host thread per canvas.  Reported beside, never instead of, `value`.
-    if world == 1 and args.compute == 'fp16' and not args.skip_extras:
-      try:
-        line['throughput_mode'] = throughput_mode(3, args.steps)
-      except Exception as e:  # pylint: disable=broad-except
-        line['throughput_mode'] = {'error': repr(e)}
-    # ---- CPU baseline: the restated reference path on this box's host cores, bounded sample
-    try:
-      if world == 1 and not args.skip_extras:
-        threads = best_cpu_threads()
-        csteps, csecs = run_cpu_steps(vol, pts, args.cpu_baseline_steps, threads)
-        line['cpu_baseline'] = {'value': csteps / csecs, 'unit': 'FoV steps/s', 'cores': threads, 'kind': 'port',
-                                'sample': '%d FoV steps of the same flood fill' % csteps}
-    except Exception as e:  # pylint: disable=broad-except
-      line['cpu_baseline'] = {'error': repr(e)}
-    print(json.dumps(line), flush=True)
-  canvas.close()
-  engine.close()
-  if world > 1:
+    run_multi(args, rank, local_rank, world)
     dist.destroy_process_group()
+  else:
+    run_n1(args, rank, local_rank)
 
 
 if __name__ == '__main__':

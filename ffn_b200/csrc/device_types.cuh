@@ -147,6 +147,7 @@ struct CanvasState {
   int seg_all;                // 1: segment_all mode, 0: segment_at mode
   int weak;                   // last object ended by 'seed_got_too_weak'
   int popped, pop_run, pop_pos[3];   // leader scratch: queue already popped for this round (phase A)
+  int start_max_id, was_early;   // Sched::max_id when the object started; run ahead of its turn (scheduler experiments)
   // commit scratch
   int box_lo[3], box_hi[3];
   unsigned long long cnt_raw, cnt_actual;
@@ -220,6 +221,8 @@ struct Job {
   int* ovl_touched;    // [ovl_ids]
   int ovl_ids;
   unsigned char* seed_status;   // [n_seeds] 0: not started, 1: taken by a chain
+  long long round_cap;          // segment_all: rounds one launch may run (watchdog)
+  int debug;                    // scheduler experiments (FFN_B200_DEBUG): 1 = treat every early run as conflicting, 2 = no early runs
 };
 
 struct KParams {

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -201,7 +202,7 @@ int launch(FfnEngine* e, FfnCanvas* c, int nchains, const Job& job) {
   CUDA_OK(cudaMemcpy(&abort_flag, e->ws.abort_flag, sizeof(int), cudaMemcpyDeviceToHost));
   if (abort_flag != 0)
     return fail("device-side wait timed out (abort code " + std::to_string(abort_flag) +
-                "): 1 = grid barrier, 2 = mbarrier, 3 = chain barrier, 4 = round flag");
+                "): 1 = grid barrier, 2 = mbarrier, 3 = chain barrier, 4 = round flag, 5 = launch exceeded 60 s");
   return 0;
 }
 
@@ -808,6 +809,7 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   job.ovl_touched = d_touched;
   job.ovl_ids = ovl_ids;
   job.seed_status = d_status;
+  if (const char* dbg = std::getenv("FFN_B200_DEBUG")) job.debug = std::atoi(dbg);
   double secs = 0;
   long long launches = 0;
   int stuck = 0;
@@ -816,6 +818,7 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
     const long long before_steps = sc.steps_executed, before_idx = sc.commit_idx;
     const unsigned before_round = sc.round;
     job.step_budget = sc.steps_executed + (1 << 15);
+    job.round_cap = 2 * (1 << 15) + 8 * n_seeds + 4096;
     if (launch(e, c, K, job)) {
       cleanup();
       return 1;
@@ -827,9 +830,19 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
       return fail("scheduler state copy failed");
     }
     if (sc.all_done) break;
-    stuck = (sc.steps_executed == before_steps && sc.commit_idx == before_idx && sc.round <= before_round + 1) ? stuck + 1 : 0;
+    if (sc.overflow & 16) stuck = 3;   // the device watchdog tripped
+    (void)before_round;
+    if (stuck < 3) stuck = (sc.steps_executed == before_steps && sc.commit_idx == before_idx) ? stuck + 1 : 0;
     if (stuck >= 3) {
-      rc = fail("segment_all made no progress (device scheduler stuck at seed " + std::to_string(sc.commit_idx) + ")");
+      std::vector<CanvasState> dbg(kMaxChains);
+      cudaMemcpy(dbg.data(), c->d_state, sizeof(CanvasState) * kMaxChains, cudaMemcpyDeviceToHost);
+      std::string msg = "segment_all made no progress: device scheduler stalled at seed " + std::to_string(sc.commit_idx) +
+                        " of " + std::to_string(n_seeds) + ", owner " + std::to_string(sc.owner) + ", round " +
+                        std::to_string(sc.round) + "; chains (phase/seed/spec/iters/fin_round):";
+      for (int k = 0; k < K; ++k)
+        msg += " [" + std::to_string(dbg[k].phase) + "/" + std::to_string(dbg[k].seed_index) + "/" + std::to_string(dbg[k].spec) +
+               "/" + std::to_string(dbg[k].iters) + "/" + std::to_string(dbg[k].fin_round) + "]";
+      rc = fail(msg);
       break;
     }
   }

@@ -48,6 +48,7 @@ struct Ctx {
   unsigned bar_target;         // whole-grid barrier
   unsigned ev0, ev1, ev2;      // split-phase barrier events completed so far (this launch), per chain
   unsigned round;              // rounds completed in this launch (parity of seed_raw / count buffers)
+  unsigned long long t_start;  // globaltimer at kernel entry (watchdog)
   unsigned char* smem;
   float* s_bias;               // [(nconv)*32] biases, then w_lom[32], b_lom
   uint64_t* mb_w;              // [2]
@@ -1398,8 +1399,10 @@ __device__ __forceinline__ bool run_conflicts(const Ctx& c, int k, const CanvasS
   return __any_sync(0xffffffffu, bad);
 }
 
-__device__ __forceinline__ void start_object(CanvasState* st, long long idx, int spec, int sz, int sy, int sx) {
+__device__ __forceinline__ void start_object(CanvasState* st, const Sched* sc, long long idx, int spec, int sz, int sy, int sx) {
   st->seed_index = idx;
+  st->start_max_id = sc->max_id;
+  st->was_early = spec;
   st->spec = spec;
   st->start[0] = sz;
   st->start[1] = sy;
@@ -1445,7 +1448,7 @@ __device__ __forceinline__ void assign_seed(const Ctx& c, int k, CanvasState* st
       if (ok) {
         p.job.seed_status[i] = 1;
         sc->owner = k;
-        start_object(st, i, 0, sz, sy, sx);
+        start_object(st, sc, i, 0, sz, sy, sx);
       } else {
         sc->commit_idx = i + 1;
       }
@@ -1453,7 +1456,7 @@ __device__ __forceinline__ void assign_seed(const Ctx& c, int k, CanvasState* st
     __syncwarp();
     if (ok) return;
   }
-  if (sc->owner == k || p.nchains == 1) return;
+  if (sc->owner == k || p.nchains == 1 || (p.job.debug & 2)) return;
   // ---- look ahead
   constexpr int kWindow = 128;
   const long long base = sc->commit_idx + 1;
@@ -1502,7 +1505,7 @@ __device__ __forceinline__ void assign_seed(const Ctx& c, int k, CanvasState* st
       if (c.lane == 0) {
         p.job.seed_status[j0] = 1;
         sc->spec_runs++;
-        start_object(st, j0, 1, sz, sy, sx);
+        start_object(st, sc, j0, 1, sz, sy, sx);
       }
       __syncwarp();
       return;
@@ -1520,7 +1523,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sche
   const ChainDev& ch = p.ch[L.k];
   CanvasState* st = L.st;
   const unsigned full = 0xffffffffu;
-  for (int guard = 0; guard < (1 << 30); ++guard) {
+  for (int guard = 0; guard < (1 << 20); ++guard) {
     const int phase = st->phase;
     // ------------------------------------------------------------- terminal / idle phases
     if (phase == PH_IDLE || phase == PH_SEGMENT_DONE || phase == PH_ALL_DONE) return ACT_EXIT;
@@ -1566,7 +1569,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sche
         // in-turn object (what Canvas.seed shows after segment_all), move that box to the snapshot array instead
         // of just clearing it
         int act = ACT_CLEAR;
-        if (st->seg_all && st->spec && sc->last_chain == L.k && !sc->last_in_snap && p.snap) {
+        if (st->seg_all && st->spec && sc->last_chain == L.k && !sc->last_in_snap && p.snap && !(p.job.debug & 8)) {
           act = ACT_CLEAR_MOVE;
           if (c.lane == 0) {
             for (int q = 0; q < 3; ++q) {
@@ -1658,7 +1661,8 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sche
       if (st->spec) {
         int sz, sy, sx;
         const int ok = gate_seed(c, sc, st->seed_index, true, sz, sy, sx);   // the reference's gating, now, in order
-        const bool conflict = ok && run_conflicts(c, L.k, st);
+        const bool conflict = ok && (run_conflicts(c, L.k, st) || (p.job.debug & 1) ||
+                                     ((p.job.debug & 4) && sc->max_id != st->start_max_id));
         if (!ok || conflict) {
           if (c.lane == 0) {
             sc->spec_discarded++;
@@ -1668,7 +1672,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sche
             if (!ok) {
               finalize_seed(sc, st);                                  // rejected before it would have started
             } else {
-              start_object(st, st->seed_index, 0, sz, sy, sx);        // redo it in turn
+              start_object(st, sc, st->seed_index, 0, sz, sy, sx);    // redo it in turn
             }
           }
           __syncwarp();
@@ -1765,6 +1769,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sche
             o.start_zyx[2] = st->start[2];
             o.iters = st->iters;
             o.walltime_sec = (double)(sm100::globaltimer_ns() - st->seg_t0) * 1e-9;
+            if (p.job.debug & 16) o.walltime_sec = st->was_early * 1e6 + L.k * 1e5 + st->start_max_id;   // experiments
             p.job.origins[sc->n_origins] = o;
           } else {
             sc->overflow |= 4;
@@ -1808,6 +1813,9 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
   static_assert(kSchedWords <= 64, "scheduler copy uses threads 256..319");
   const unsigned par = (c.round & 1u) ^ 1u;   // parity the finished round was staged with
   const long long t_all = prof_now(c);
+  // Watchdog: one launch covers at most 2^15 FoV steps (a few seconds).  A launch that is still going after
+  // 60 s has stalled; raise the abort flag so that every CTA leaves at this round boundary and the host reports it.
+  if (c.tid == 0 && sm100::globaltimer_ns() - c.t_start > 60000000000ull) atomicExch(p.ws.abort_flag, 5);
   // Work on shared-memory copies: the serial code is full of read-after-write on these fields, and in
   // global memory every one of those is an L2 round trip.
   for (int i = c.tid; i < K * kStateWords; i += 256) {
@@ -1877,11 +1885,18 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
         }
         any = false;
       } else if (!any) {
-        // nobody has a collective action: keep going only if someone is waiting for a paste to land
+        // nobody has a collective action: keep going only if someone is waiting for a paste to land — for
+        // one round; a second one means the scheduler has stalled (reported by the host, never spun on)
         bool waiting = false;
-        for (int k = 0; k < K; ++k) waiting = waiting || chain_state(c, k)->phase == PH_FINISHED;
+        for (int k = 0; k < K; ++k)
+          waiting = waiting || (chain_state(c, k)->phase == PH_FINISHED && chain_state(c, k)->fin_round + 1 >= (int)sc->round);
         any = waiting;
       }
+    }
+    // watchdog: a launch that runs far more rounds than its step budget and seed count allow is reported, not spun on
+    if (p.job.mode == MODE_SEGMENT && s0->seg_all && c.round > (unsigned)p.job.round_cap) {
+      if (c.lane == 0) sc->overflow |= 16;
+      any = false;
     }
     if (c.lane == 0) {
       sc->round++;
@@ -1920,11 +1935,21 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
 // ------------------------------------------------------------------------------------------
 // Collective helpers over a canvas box (all CTAs)
 // ------------------------------------------------------------------------------------------
+// What the leader published this round (boxes, ids) is read through L2, like every other cross-CTA datum.
+__device__ __forceinline__ void load3(const int* src, int (&dst)[3]) {
+  dst[0] = __ldcg(src);
+  dst[1] = __ldcg(src + 1);
+  dst[2] = __ldcg(src + 2);
+}
+
 __device__ __forceinline__ void clear_dirty(Ctx& c, int k) {   // NumpyArray.clear restricted to the touched box
   const KParams& p = *c.p;
   const CanvasState* st = p.ch[k].st;
-  const int lo[3] = {max(st->dirty_lo[0], 0), max(st->dirty_lo[1], 0), max(st->dirty_lo[2], 0)};
-  const int hi[3] = {min(st->dirty_hi[0], p.cv.sz), min(st->dirty_hi[1], p.cv.sy), min(st->dirty_hi[2], p.cv.sx)};
+  int dlo[3], dhi[3];
+  load3(st->dirty_lo, dlo);
+  load3(st->dirty_hi, dhi);
+  const int lo[3] = {max(dlo[0], 0), max(dlo[1], 0), max(dlo[2], 0)};
+  const int hi[3] = {min(dhi[0], p.cv.sz), min(dhi[1], p.cv.sy), min(dhi[2], p.cv.sx)};
   const int nz = hi[0] - lo[0], ny = hi[1] - lo[1], nx = hi[2] - lo[2];
   if (nz <= 0 || ny <= 0 || nx <= 0) return;
   const long long lines = (long long)nz * ny;
@@ -1941,10 +1966,16 @@ __device__ __forceinline__ void clear_dirty(Ctx& c, int k) {   // NumpyArray.cle
 __device__ __forceinline__ void clear_move(Ctx& c, int k) {
   const KParams& p = *c.p;
   const Sched* sc = p.sched;
-  const int olo[3] = {sc->snap_old_lo[0], sc->snap_old_lo[1], sc->snap_old_lo[2]};
-  const int ohi[3] = {sc->snap_old_hi[0], sc->snap_old_hi[1], sc->snap_old_hi[2]};
-  const int lo[3] = {sc->snap_lo[0], sc->snap_lo[1], sc->snap_lo[2]};
-  const int hi[3] = {sc->snap_hi[0], sc->snap_hi[1], sc->snap_hi[2]};
+  const CanvasState* st = p.ch[k].st;
+  int olo[3], ohi[3], dlo[3], dhi[3];
+  load3(sc->snap_old_lo, olo);
+  load3(sc->snap_old_hi, ohi);
+  // the box to move is the chain's touched box, read exactly like clear_dirty does (the leader recorded the same
+  // numbers as the new snapshot box for the host)
+  load3(st->dirty_lo, dlo);
+  load3(st->dirty_hi, dhi);
+  const int lo[3] = {max(dlo[0], 0), max(dlo[1], 0), max(dlo[2], 0)};
+  const int hi[3] = {min(dhi[0], p.cv.sz), min(dhi[1], p.cv.sy), min(dhi[2], p.cv.sx)};
   const float nanv = CUDART_NAN_F;
   {
     const int nz = ohi[0] - olo[0], ny = ohi[1] - olo[1], nx = ohi[2] - olo[2];
@@ -1978,8 +2009,9 @@ __device__ __forceinline__ void clear_move(Ctx& c, int k) {
 __device__ __forceinline__ void commit_count(Ctx& c, int k) {   // inference.py:624-636
   const KParams& p = *c.p;
   CanvasState* st = p.ch[k].st;
-  const int* lo = st->box_lo;
-  const int* hi = st->box_hi;
+  int lo[3], hi[3];
+  load3(st->box_lo, lo);
+  load3(st->box_hi, hi);
   const int nz = hi[0] - lo[0], ny = hi[1] - lo[1], nx = hi[2] - lo[2];
   const long long lines = (long long)nz * ny;
   unsigned raw = 0, actual = 0;
@@ -2014,11 +2046,12 @@ __device__ __forceinline__ void commit_count(Ctx& c, int k) {   // inference.py:
 __device__ __forceinline__ void commit_write(Ctx& c, int k) {   // inference.py:653-658
   const KParams& p = *c.p;
   const CanvasState* st = p.ch[k].st;
-  const int* lo = st->box_lo;
-  const int* hi = st->box_hi;
+  int lo[3], hi[3];
+  load3(st->box_lo, lo);
+  load3(st->box_hi, hi);
   const int nz = hi[0] - lo[0], ny = hi[1] - lo[1], nx = hi[2] - lo[2];
   const long long lines = (long long)nz * ny;
-  const int sid = st->cur_sid;
+  const int sid = __ldcg(&st->cur_sid);
   for (long long l = (long long)c.cta * (kThreads / 32) + c.warp; l < lines; l += (long long)c.G * (kThreads / 32)) {
     const int z = lo[0] + (int)(l / ny), y = lo[1] + (int)(l % ny);
     const size_t base = cv_index(p.cv, z, y, lo[2]);
@@ -2069,6 +2102,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   c.bar_target = 0;
   c.ev0 = c.ev1 = c.ev2 = 0;
   c.round = 0;
+  c.t_start = sm100::globaltimer_ns();
   c.smem = smem_raw;
   const SmemLayout L = smem_layout(p.g);
   c.s_bias = reinterpret_cast<float*>(smem_raw + L.bias);

@@ -114,3 +114,47 @@ def merge_labels(local_labels, local_max_id: int, dst: int = 0, add_offset=None)
     gathered = [torch.empty_like(local_labels) for _ in range(world)]
   dist.gather(local_labels, gathered, dst=dst)
   return gathered, off, sum(max_ids)
+
+
+def merge_slabs(labels, probs, max_ids, dst: int = 0, add_offset=None):
+  """The exchange step of a sharded run: every rank holds the results of its slabs
+  (`labels[i]` int32, `probs[i]` uint8 or None, `max_ids[i]` = ids used by slab i); ids are made globally unique
+  in slab order (rank-major) and both arrays of every slab are gathered on `dst`.
+
+  Args:
+    labels / probs: lists of torch tensors (CUDA for NCCL, CPU for gloo); every rank holds the same number
+    max_ids: list of ints, one per local slab
+    add_offset: optional callable(i, offset) applying the offset to local slab i in place (the engine's relabel
+      kernel); default: a torch expression on labels[i]
+
+  Returns:
+    (gathered_labels, gathered_probs, offsets of the local slabs, total ids); the gathered lists are
+    [local slab index][rank] on dst and None elsewhere.
+  """
+  import torch
+  import torch.distributed as dist
+  rank, world = dist.get_rank(), dist.get_world_size()
+  dev = labels[0].device if labels and labels[0].is_cuda else None
+  per_rank = gather_max_ids(sum(int(m) for m in max_ids), device=dev)
+  off = exclusive_offsets(per_rank)[rank]
+  offsets = []
+  for i, m in enumerate(max_ids):
+    offsets.append(off)
+    if off:
+      if add_offset is not None:
+        add_offset(i, off)
+      else:
+        labels[i][labels[i] > 0] += off
+    off += int(m)
+  out_l, out_p = ([] if rank == dst else None), ([] if rank == dst else None)
+  for i in range(len(labels)):
+    gl = [torch.empty_like(labels[i]) for _ in range(world)] if rank == dst else None
+    dist.gather(labels[i], gl, dst=dst)
+    if rank == dst:
+      out_l.append(gl)
+    if probs is not None:
+      gp = [torch.empty_like(probs[i]) for _ in range(world)] if rank == dst else None
+      dist.gather(probs[i], gp, dst=dst)
+      if rank == dst:
+        out_p.append(gp)
+  return out_l, (out_p if probs is not None else None), offsets, sum(per_rank)

@@ -47,7 +47,7 @@ class Runner:
     self.canvases = {}
     self._device = device
     if compute_mode is None:
-      compute_mode = {'fp32': _lib.COMPUTE_FP32, 'fp16': _lib.COMPUTE_FP16_TC}[
+      compute_mode = {'fp32': _lib.COMPUTE_FP32, 'fp16': _lib.COMPUTE_FP16_TC, 'x2': _lib.COMPUTE_FP16X2_TC}[
           os.environ.get('FFN_B200_COMPUTE', 'fp16')]
     self._compute_mode = compute_mode
     self.init_seg_volume = None

@@ -48,3 +48,44 @@ def test_merge_labels_two_ranks(tmp_path):
   ids0 = set(np.unique(merged[0][merged[0] > 0]))
   ids1 = set(np.unique(merged[1][merged[1] > 0]))
   assert not ids0 & ids1
+
+
+def _worker_slabs(rank, world, port, out_dir):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  rng = np.random.RandomState(10 + rank)
+  max_ids = [2 + rank, 4]                       # two slabs per rank
+  labels = [torch.from_numpy(rng.randint(-1, m + 1, size=(3, 4, 5)).astype(np.int32)) for m in max_ids]
+  probs = [torch.from_numpy(rng.randint(0, 256, size=(3, 4, 5)).astype(np.uint8)) for _ in max_ids]
+  np.save(os.path.join(out_dir, 'lab_%d.npy' % rank), np.stack([t.numpy().copy() for t in labels]))
+  np.save(os.path.join(out_dir, 'prob_%d.npy' % rank), np.stack([t.numpy().copy() for t in probs]))
+  gl, gp, offsets, total = distributed.merge_slabs(labels, probs, max_ids, dst=0)
+  np.save(os.path.join(out_dir, 'off_%d.npy' % rank), np.array(offsets))
+  if rank == 0:
+    np.save(os.path.join(out_dir, 'gl.npy'), np.stack([np.stack([t.numpy() for t in row]) for row in gl]))
+    np.save(os.path.join(out_dir, 'gp.npy'), np.stack([np.stack([t.numpy() for t in row]) for row in gp]))
+    np.save(os.path.join(out_dir, 'total.npy'), np.array([total]))
+  dist.destroy_process_group()
+
+
+def test_merge_slabs_labels_and_probabilities_two_ranks(tmp_path):
+  """configs[3]'s exchange step on CPU: slabs of two ranks, ids unique in rank-major slab order, labels AND
+  probability maps gathered on rank 0 unchanged."""
+  port = _free_port()
+  mp.spawn(_worker_slabs, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  gl, gp = np.load(tmp_path / 'gl.npy'), np.load(tmp_path / 'gp.npy')        # [slab][rank]
+  assert int(np.load(tmp_path / 'total.npy')[0]) == (2 + 4) + (3 + 4)
+  assert np.load(tmp_path / 'off_0.npy').tolist() == [0, 2] and np.load(tmp_path / 'off_1.npy').tolist() == [6, 9]
+  seen = set()
+  for r in range(2):
+    lab, prob = np.load(tmp_path / ('lab_%d.npy' % r)), np.load(tmp_path / ('prob_%d.npy' % r))
+    offs = np.load(tmp_path / ('off_%d.npy' % r))
+    for i in range(2):
+      want = lab[i].copy()
+      want[lab[i] > 0] += offs[i]
+      np.testing.assert_array_equal(gl[i, r], want)
+      np.testing.assert_array_equal(gp[i, r], prob[i])
+      ids = set(np.unique(want[want > 0]).tolist())
+      assert not ids & seen
+      seen |= ids

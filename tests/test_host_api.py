@@ -386,5 +386,5 @@ def test_bench_reference_arm_contract():
 def test_bench_traffic_comes_from_committed_ncu_capture():
   import bench
   t = bench.ncu_dram_traffic()
-  assert t is not None and t['steps_per_launch'] == 16
+  assert t is not None and t['steps_per_launch'] >= 16
   assert 1e5 < t['bytes_per_step'] < 431244 * 2      # at most about the compulsory 431 KB/step (u8 image, L2 reuse)

@@ -180,3 +180,39 @@ def test_toy_anisotropic_flood_fill_bit_exact(golden_dir):
   canvas.segment_all(g['seeds'])
   _check_canvas(canvas, g, exact_seed=True)
   assert g['trace'].shape[0] > 100
+
+
+def test_seed_peaks_edt_restatement_equals_the_definition():
+  """oracle/seed_peaks.py restates edt.edt with scipy's exact EDT: pinned against the O(n^2) definition
+  (distance to the nearest background voxel in physical units), isotropic and anisotropic."""
+  from scipy import ndimage
+  from oracle import seed_peaks
+  rng = np.random.RandomState(0)
+  fg = rng.rand(9, 11, 13) > 0.25
+  for voxel in ((1.0, 1.0, 1.0), (2.0, 1.0, 1.0), (3.0, 1.5, 1.0)):
+    want = seed_peaks.brute_force_edt(fg, voxel)
+    got = ndimage.distance_transform_edt(fg, sampling=voxel)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+
+
+def test_seed_peaks_oracle_properties():
+  """Lexicographic order, border filter, exclusions, spacing > min_distance (Chebyshev) and determinism."""
+  from ffn_b200.synthetic import voronoi_phantom
+  from oracle import seed_peaks
+  vol = voronoi_phantom((48, 56, 64), seed=9, cell_volume=9000.0)
+  image = (vol.astype(np.float32) - np.float32(128)) / np.float32(33)
+  seg = np.zeros(vol.shape, np.int32)
+  seg[10:30, 10:30, 10:30] = 3
+  mask = np.zeros(vol.shape, bool)
+  mask[:, :6, :] = True
+  c = seed_peaks.policy_peaks(image, (1, 1, 1), segmentation=seg, mask=mask, margin_zyx=(4, 4, 4))
+  assert c.shape[0] > 10
+  assert [tuple(r) for r in c.tolist()] == sorted(tuple(r) for r in c.tolist())
+  assert np.all(c >= 4) and np.all(c + 4 < np.asarray(vol.shape)[None])
+  assert not any(seg[z, y, x] > 0 or mask[z, y, x] for z, y, x in c)
+  d = np.abs(c[:, None, :] - c[None, :, :]).max(axis=2)
+  np.fill_diagonal(d, 99)
+  assert d.min() > 3
+  np.testing.assert_array_equal(c, seed_peaks.policy_peaks(image, (1, 1, 1), segmentation=seg, mask=mask, margin_zyx=(4, 4, 4)))
+  full = seed_peaks.policy_peaks(image, (2, 1, 1))
+  assert full.shape[0] > 10 and not np.array_equal(full, seed_peaks.policy_peaks(image, (1, 1, 1)))

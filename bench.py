@@ -351,23 +351,26 @@ def run_n1(args, rank, local_rank):
   canvas.close()
 
   # ---- end-to-end leg: what run_inference.py does — Runner.start + Runner.run on a volume file
-  from ffn.inference import runner as runner_mod
-  tmp = tempfile.mkdtemp(prefix='ffn_bench_')
-  vol_path = os.path.join(tmp, 'vol.npy')
-  np.save(vol_path, vol)
-  runner = runner_mod.Runner(device=local_rank, compute_mode=mode)
-  runner.start(request_for(vol_path, os.path.join(tmp, 'out')))
-  if args.chains:
-    runner.executor.engine.set_chains(args.chains)
-  torch.cuda.synchronize()
-  t0 = time.perf_counter()
-  rc = runner.run((0, 0, 0), shape)
-  e2e_seconds = time.perf_counter() - t0
-  cnt = {k: c.value for k, c in rc.counters}
-  e2e_steps = int(cnt.get('inference-calls', 0))
-  e2e_vox = int(cnt.get('voxels-segmented', 0))
-  runner.stop_executor()
-  del rc
+  if args.skip_e2e:
+    e2e_seconds, e2e_steps, e2e_vox = wall, steps, int(ctr.voxels_segmented)
+  else:
+    from ffn.inference import runner as runner_mod
+    tmp = tempfile.mkdtemp(prefix='ffn_bench_')
+    vol_path = os.path.join(tmp, 'vol.npy')
+    np.save(vol_path, vol)
+    runner = runner_mod.Runner(device=local_rank, compute_mode=mode)
+    runner.start(request_for(vol_path, os.path.join(tmp, 'out')))
+    if args.chains:
+      runner.executor.engine.set_chains(args.chains)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rc = runner.run((0, 0, 0), shape)
+    e2e_seconds = time.perf_counter() - t0
+    cnt = {k: c.value for k, c in rc.counters}
+    e2e_steps = int(cnt.get('inference-calls', 0))
+    e2e_vox = int(cnt.get('voxels-segmented', 0))
+    runner.stop_executor()
+    del rc
 
   value = steps / wall
   burst, sustained, src = measured_peaks()
@@ -545,6 +548,7 @@ def main():
   ap.add_argument('--slab', type=int, default=0, help='N > 1: slab edge instead of 512 (tests)')
   ap.add_argument('--cpu-baseline-steps', type=int, default=24)
   ap.add_argument('--skip-extras', action='store_true', help='no single-seed / predict / cpu_baseline legs (profiler runs)')
+  ap.add_argument('--skip-e2e', action='store_true', help='no Runner.run leg (profiler runs; the line then repeats the device-resident value)')
   args = ap.parse_args()
   rank = int(os.environ.get('RANK', '0'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))

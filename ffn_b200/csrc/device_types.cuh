@@ -1,6 +1,7 @@
 // device_types.cuh — plain structs shared by the host engine and the persistent kernel.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -9,11 +10,13 @@
 
 namespace ffn {
 
-constexpr int kThreads = 320;     // warps 0-7: epilogue (2 channel halves x 4 TMEM lane quarters); warp 8: TMA producer; warp 9: UMMA issuer
+constexpr int kThreads = 352;     // warps 0-7: epilogue (2 channel halves x 4 TMEM lane quarters); warp 8: TMA producer; warp 9: UMMA issuer;
+                                  // warp 10: signals the chains' split-phase barriers (the release stays off the epilogue's path)
 constexpr int kLoadWarp = 8;
 constexpr int kMmaWarp = 9;
+constexpr int kSigWarp = 10;
 #ifndef FFN_ACT_STAGES
-#define FFN_ACT_STAGES 2
+#define FFN_ACT_STAGES 3
 #endif
 constexpr int kActStages = FFN_ACT_STAGES;     // shared-memory ring of per-tile activation operands
 constexpr int kAccSlots = 3;      // TMEM ring of per-tile accumulators
@@ -177,6 +180,7 @@ struct Sched {
   long long n_origins, n_overlaps;
   long long steps_executed;   // FoV steps run, incl. early runs that were discarded
   long long spec_runs, spec_discarded, spec_steps_discarded;
+  long long idle_free, idle_wait;   // chain-rounds spent without an object / waiting for the turn to commit
   unsigned round;             // rounds completed (all launches)
   int all_done;
   // Canvas.seed after segment_all holds the LAST object segment_at ran on (inference.py:443-450 clears it only when
@@ -235,6 +239,11 @@ struct KParams {
   Sched* sched;
   Ctl* ctl;
   unsigned* round_flag;   // rounds published by the leader (release / acquire)
+  // Tensor maps over the fp16 operand buffers of every chain ([0] layer-0 input, [1] / [2] the ping-pong pair):
+  // 4-D view (8 halfs, rows, 3 z-planes at pitch pp, k-chunks) so that ONE cp.async.bulk.tensor brings a whole
+  // tile's operands — 126 + 2*halo rows of the three z-planes, every k-chunk — into a shared-memory stage.
+  CUtensorMap tmap[kMaxChains][3];
+  int use_tmap;           // 0: the driver could not encode the maps -> 1-D bulk copies (same shared-memory layout)
   float* snap;            // snapshot seed array (see Sched::last_chain); null with one chain
   Job job;
   int compute_mode;
@@ -258,7 +267,7 @@ __host__ __device__ inline SmemLayout smem_layout(const Geom& g) {
   const int act_bytes = kActStages * 3 * 4 * seg_rows * 16;
   s.bias = s.act + act_bytes;
   s.bars = s.bias + (kMaxConv + 1) * 32 * 4 + 16;
-  s.total = s.bars + 4096 + 2560;   // barriers/misc | prof | epilogue exchange + conv_lom dots | leader's chain-state / scheduler copies
+  s.total = s.bars + 4096 + kMaxChains * 384 + 320;   // barriers/misc | prof | epilogue exchange + conv_lom dots | leader's chain-state / scheduler copies
   return s;
 }
 

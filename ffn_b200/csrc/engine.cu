@@ -62,6 +62,8 @@ struct FfnEngine {
   ffn::Weights w{};
   ffn::Workspace ws{};
   ffn::ChainDev cws[ffn::kMaxChains]{};   // per-chain step workspace (canvas-side pointers stay null here)
+  CUtensorMap tmap[ffn::kMaxChains][3]{};
+  int use_tmap = 0;
   int max_chains = ffn::kMaxChains;       // chains the multi-seed / batched paths may use (ffn_engine_set_chains)
   ffn::Ctl* d_ctl = nullptr;
   unsigned* d_round_flag = nullptr;
@@ -94,7 +96,7 @@ struct FfnCanvas {
   ffn::Sched* d_sched = nullptr;
   ffn::Sched h_sched{};
   size_t q_cap = 0, traj_cap = 0;
-  long long last_spec[4] = {0, 0, 0, 0};   // last segment_all: early runs started / discarded / their steps / steps executed
+  long long last_spec[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // last segment_all: early runs started / discarded / their steps / steps executed
   void* d_image = nullptr;
   uint8_t* d_mask = nullptr;
   uint8_t* d_seed_mask = nullptr;
@@ -144,6 +146,7 @@ Geom make_geom(const FfnModelDesc& m) {
   g.halo = g.xp + 1;
   g.guard = ((g.pp + g.halo + 7) / 8) * 8;
   g.rows_alloc = g.guard + g.nt * kTileM + g.guard;
+  g.rows_alloc = ((g.rows_alloc + g.pp - 1) / g.pp) * g.pp;   // k-chunk pitch = whole number of z-plane pitches (tensor-map strides)
   g.V = g.fz * g.fy * g.fx;
   g.inv_pp = 1.0f / (float)g.pp;
   g.inv_xp = 1.0f / (float)g.xp;
@@ -180,6 +183,8 @@ int launch(FfnEngine* e, FfnCanvas* c, int nchains, const Job& job) {
   p.ctl = e->d_ctl;
   p.round_flag = e->d_round_flag;
   p.snap = c ? c->d_snap : nullptr;
+  std::memcpy(p.tmap, e->tmap, sizeof(p.tmap));
+  p.use_tmap = e->use_tmap;
   p.job = job;
   p.compute_mode = e->compute_mode;
   CUDA_OK(cudaMemsetAsync(e->ws.bar, 0, sizeof(unsigned), cudaStreamPerThread));
@@ -439,6 +444,35 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
     for (void* p : std::vector<void*>{cw.act0_h, cw.act_h[0], cw.act_h[1], cw.seed_raw[0], cw.seed_raw[1], cw.logits,
                                       cw.count, cw.bar})
       e->owned.push_back(p);
+  }
+  // Tensor maps for the tile loads (driver entry point fetched at run time: no link-time dependency on libcuda).
+  {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    bool ok = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+              qres == cudaDriverEntryPointSuccess;
+    const int seg_rows = kTileOut + 2 * g.halo;
+    for (int k = 0; ok && k < kMaxChains; ++k)
+      for (int i = 0; ok && i < 3; ++i) {
+        const cuuint32_t nch = i == 0 ? 2 : 4;
+        void* base = i == 0 ? (void*)e->cws[k].act0_h : (void*)e->cws[k].act_h[i - 1];
+        const cuuint64_t dims[4] = {8, (cuuint64_t)(g.rows_alloc - 2 * g.pp), 3, nch};
+        const cuuint64_t strides[3] = {16, (cuuint64_t)g.pp * 16, (cuuint64_t)g.rows_alloc * 16};
+        const cuuint32_t box[4] = {8, (cuuint32_t)seg_rows, 3, nch};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        ok = reinterpret_cast<EncodeFn>(fn)(&e->tmap[k][i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      }
+    // Measured (B200, round 2): the tiled copy moves this layout as 16-byte rows (the k-chunk is the innermost
+    // extent) and needs 2.5x longer per tile than the twelve 3 KB 1-D bulk copies (UBLKCP, the same TMA engine):
+    // 13.1 k vs 16.8 k patches/s in ffn_predict(batch=48).  The bulk path is therefore the default;
+    // FFN_B200_TMAP=1 selects the tensor-map path.
+    const char* env = std::getenv("FFN_B200_TMAP");
+    e->use_tmap = (ok && env && std::atoi(env) != 0) ? 1 : 0;
   }
   if (dev_alloc(&e->d_ctl, 1)) return 1;
   if (dev_alloc(&e->d_round_flag, 1)) return 1;
@@ -770,6 +804,9 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   sc.overflow = 0;
   sc.n_origins = sc.n_overlaps = 0;
   sc.steps_executed = 0;
+  sc.spec_runs = sc.spec_discarded = sc.spec_steps_discarded = 0;
+  sc.idle_free = sc.idle_wait = 0;
+  const unsigned round0 = sc.round;
   sc.all_done = 0;
   sc.ctr = st.ctr;             // cumulative counters of the canvas; the chains count per object from here on
   const bool has_data = st.dirty_hi[0] > st.dirty_lo[0];
@@ -900,6 +937,10 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   c->last_spec[1] = sc.spec_discarded;
   c->last_spec[2] = sc.spec_steps_discarded;
   c->last_spec[3] = sc.steps_executed;
+  c->last_spec[4] = (long long)sc.round - (long long)round0;
+  c->last_spec[5] = sc.idle_free;
+  c->last_spec[6] = sc.idle_wait;
+  c->last_spec[7] = K;
   if (counters_out) *counters_out = st.ctr;
   if (push_state(c)) return 1;
   return rc;
@@ -1178,9 +1219,9 @@ int ffn_canvas_get_counters(FfnCanvas* c, FfnCounters* out) {
   return 0;
 }
 
-int ffn_canvas_spec_stats(FfnCanvas* c, int64_t out[4]) {
+int ffn_canvas_spec_stats(FfnCanvas* c, int64_t out[8]) {
   if (!c || !out) return fail("null argument");
-  for (int i = 0; i < 4; ++i) out[i] = c->last_spec[i];
+  for (int i = 0; i < 8; ++i) out[i] = c->last_spec[i];
   return 0;
 }
 

@@ -56,6 +56,7 @@ struct Ctx {
   uint64_t* mb_empty;          // [kActStages] UMMA -> TMA: the stage may be overwritten
   uint64_t* mb_tfull;          // [kAccSlots]  UMMA -> epilogue: accumulators complete
   uint64_t* mb_tempty;         // [kAccSlots]  epilogue -> UMMA: accumulators drained (8 arrivals)
+  uint64_t* mb_sig;            // [kMaxChains] epilogue -> signal warp: a chain's layer is stored (8 arrivals)
   unsigned load_cnt, mma_cnt, epi_cnt;   // per-role running tile counters (ring index + phase parity)
   uint32_t* s_tmem;            // TMEM base address
   int* s_misc;                 // [0..3) per-chain step-count accumulators, [4..7) disco flags, [8..) leader scratch
@@ -83,7 +84,7 @@ __device__ __forceinline__ void ev_add(Ctx& c, int k, unsigned n) {
   else c.ev2 += n;
 }
 __device__ __forceinline__ CanvasState* chain_state(const Ctx& c, int k) {
-  return reinterpret_cast<CanvasState*>(reinterpret_cast<unsigned char*>(c.s_state) + k * 512);
+  return reinterpret_cast<CanvasState*>(reinterpret_cast<unsigned char*>(c.s_state) + k * 384);
 }
 
 __device__ __forceinline__ bool aborted(const Ctx& c) {
@@ -163,14 +164,21 @@ __device__ __forceinline__ void grid_barrier(Ctx& c) {
   sm100::tc_fence_after();
 }
 
-// Split-phase barrier of one chain.  ARRIVE (the eight epilogue warps, after their global stores of one
-// layer of chain k): a named barrier among them, then one red.release.  WAIT (the TMA producer warp,
-// before it loads chain k's operands of the next layer): acquire-poll until `events` arrivals of every CTA
-// have been counted since the start of this chain's round.
+// Split-phase barrier of one chain.  ARRIVE: each of the eight epilogue warps, after its global stores of one
+// layer of chain k, arrives at the chain's shared-memory mbarrier and goes on with the next tile; the signal
+// warp waits for the eight arrivals and does the gpu-scope red.release (a release waits for the CTA's earlier
+// stores to be performed: ~1 k cycles that would otherwise sit on the epilogue's critical path three times per
+// layer).  WAIT (the TMA producer warp, before it loads chain k's operands of the next layer): acquire-poll
+// until `events` arrivals of every CTA have been counted since the start of this chain's round.
 __device__ __forceinline__ void chain_arrive_epi(Ctx& c, int k) {
   sm100::tc_fence_before();
-  asm volatile("bar.sync 5, 256;" ::: "memory");
-  if (c.tid == 0) sm100::red_release_add(c.p->ch[k].bar, 1u);
+  __syncwarp();
+  if (c.lane == 0) sm100::mbar_arrive(&c.mb_sig[k]);   // release.cta: this warp's stores -> the signal warp
+}
+__device__ __forceinline__ void chain_signal(Ctx& c, int k, uint32_t parity) {   // signal warp
+  mbar_wait(c, &c.mb_sig[k], parity);                     // acquire.cta: the eight epilogue warps' stores
+  if (c.lane == 0) sm100::red_release_add(c.p->ch[k].bar, 1u);   // cumulative: they become visible gpu-wide first
+  __syncwarp();
 }
 __device__ __forceinline__ void chain_wait(Ctx& c, int k, unsigned events) {
   if (c.lane == 0) {
@@ -369,7 +377,7 @@ __device__ __forceinline__ void tc_issue_tile(uint32_t d, uint32_t a_lo, uint32_
     const int tz = row / 3, ty = row % 3;
 #pragma unroll
     for (int j = 0; j < NCH / 2; ++j) {
-      const uint32_t aoff = (uint32_t)((tz * NCH + 2 * j) * seg_rows + ty * xp);
+      const uint32_t aoff = (uint32_t)((2 * j * 3 + tz) * seg_rows + ty * xp);   // stage layout [k-chunk][dz][row]
       const uint32_t boff = (uint32_t)((row * NCH + 2 * j) * (12 * 128 / 16));
       sm100::umma_f16(d, hi | (uint64_t)(a_lo + aoff), hi | (uint64_t)(b_lo + boff), idesc,
                       (row | j) != 0 ? 1u : 0u);
@@ -561,8 +569,9 @@ __device__ __forceinline__ void publish_counts(Ctx& c, int k, int hit) {
 // One round of the conv stacks of the chains in `mask`, as ONE warp-specialised pipeline over the work
 // items (layer, chain, tile) in that order:
 //   warp 8  TMA producer : waits for the chain's split-phase barrier (previous layer complete in every
-//                          CTA), then per tile 12 bulk copies (3 z-planes x k-chunks, 126 + 2*halo rows) into
-//                          a 2-stage shared-memory ring                 full[stage]  <-  empty[stage]
+//                          CTA), then per tile ONE tiled TMA through the buffer's tensor map (box: 8 halfs x
+//                          126 + 2*halo rows x 3 z-planes x k-chunks) into a 2-stage shared-memory ring
+//                                                                       full[stage]  <-  empty[stage]
 //   warp 9  UMMA issuer  : 18 UMMAs 128x96x16 per tile into a 3-slot TMEM ring; one commit frees the
 //                          smem stage, one publishes the slot           tfull[slot]  <-  tempty[slot]
 //   warps 0-7 epilogue   : every tile by all eight warps (2 channel halves x 4 TMEM lane quarters); after a
@@ -587,7 +596,14 @@ __device__ __forceinline__ void layers_pipelined(Ctx& c, unsigned mask) {
     // ------------------------------------------------------------------ TMA producer
     for (int layer = 0; layer < nconv; ++layer) {
       const int nch = layer == 0 ? 2 : 4;
-      bool first = true;
+      // The next layer's weights (next round's layer 0 after the last layer) are prefetched into the other
+      // buffer during this layer.  That buffer's previous user — layer - 1 — must have completed every UMMA,
+      // i.e. the tile issued just before this layer's first one (n0 - 1; commits are in order), and that is
+      // exactly what the `empty` wait of this layer's kActStages-th tile waits for (same stage).  A layer with
+      // fewer tiles waits for that phase explicitly at its end (it cannot have been overtaken: the stage's next
+      // user has not been loaded).
+      const unsigned n0 = c.load_cnt;   // first tile of this layer
+      bool weights_pending = true;
       for (int k = 0; k < kMaxChains; ++k) {
         if (!((mask >> k) & 1u)) continue;
         const ChainDev& ch = p.ch[k];
@@ -597,31 +613,35 @@ __device__ __forceinline__ void layers_pipelined(Ctx& c, unsigned mask) {
         for (int j = 0; j < ntiles; ++j) {
           const int s = c.load_cnt % kActStages;
           mbar_wait(c, &c.mb_empty[s], ((c.load_cnt / kActStages) & 1u) ^ 1u);
+          if (weights_pending && c.load_cnt - n0 == (unsigned)(kActStages - 1)) {
+            weights_pending = false;
+            if (sm100::elect_one()) tc_issue_weight_load(c, (layer + 1 == nconv) ? 0 : layer + 1);
+            __syncwarp();
+          }
           const int r0 = (c.t_begin + j) * kTileOut;
           unsigned char* dst = act_smem + (size_t)s * stage_bytes;
           if (sm100::elect_one()) {
             sm100::mbar_expect_tx(&c.mb_full[s], (uint32_t)(3 * nch * seg_rows * 16));
-            for (int dzi = 0; dzi < 3; ++dzi)
+            if (p.use_tmap) {
+              // one tiled TMA: box (8 halfs, seg_rows rows, 3 z-planes, nch k-chunks) -> stage layout [k-chunk][dz][row]
+              sm100::tma_load_4d(dst, &p.tmap[k][layer == 0 ? 0 : 1 + ((layer - 1) & 1)], 0, g.guard + r0 - g.halo - g.pp, 0, 0,
+                                 &c.mb_full[s]);
+            } else {
               for (int cc = 0; cc < nch; ++cc)
-                sm100::bulk_g2s(dst + (size_t)(dzi * nch + cc) * seg_rows * 16,
-                                in + ((size_t)cc * g.rows_alloc + g.guard + r0 + (dzi - 1) * g.pp - g.halo) * 8,
-                                (uint32_t)seg_rows * 16, &c.mb_full[s]);
+                for (int dzi = 0; dzi < 3; ++dzi)
+                  sm100::bulk_g2s(dst + (size_t)(cc * 3 + dzi) * seg_rows * 16,
+                                  in + ((size_t)cc * g.rows_alloc + g.guard + r0 + (dzi - 1) * g.pp - g.halo) * 8,
+                                  (uint32_t)seg_rows * 16, &c.mb_full[s]);
+            }
           }
           __syncwarp();
           ++c.load_cnt;
         }
-        if (first) {
-          // Prefetch the next layer's weights (next round's layer 0 after the last layer) into the other
-          // buffer, behind the first chain's operands.  Its previous user — layer - 1 — must have completed
-          // every UMMA: the `empty` wait of the NEXT tile (done here, early; waiting twice on a phase is
-          // harmless) covers the UMMAs up to tile load_cnt - kActStages, and at least one tile of this layer
-          // has been issued, so with two stages that includes the last tile of layer - 1 (commits are in order).
-          first = false;
-          static_assert(kActStages == 2, "the weight-buffer hand-over relies on a two-stage ring");
-          mbar_wait(c, &c.mb_empty[c.load_cnt % kActStages], ((c.load_cnt / kActStages) & 1u) ^ 1u);
-          if (sm100::elect_one()) tc_issue_weight_load(c, (layer + 1 == nconv) ? 0 : layer + 1);
-          __syncwarp();
-        }
+      }
+      if (weights_pending) {
+        if (n0 > 0) mbar_wait(c, &c.mb_empty[(n0 - 1u) % kActStages], ((n0 - 1u) / kActStages) & 1u);
+        if (sm100::elect_one()) tc_issue_weight_load(c, (layer + 1 == nconv) ? 0 : layer + 1);
+        __syncwarp();
       }
     }
   } else if (c.warp == kMmaWarp) {
@@ -643,7 +663,7 @@ __device__ __forceinline__ void layers_pipelined(Ctx& c, unsigned mask) {
           mbar_wait(c, &c.mb_tempty[slot], ((c.mma_cnt / kAccSlots) & 1u) ^ 1u);
           sm100::tc_fence_after();
           t0 = prof_now(c);
-          const uint32_t a_lo = ((sm100::smem_u32(act_smem + (size_t)s * stage_bytes) >> 4) & 0x3FFFu) | ((uint32_t)seg_rows << 16);
+          const uint32_t a_lo = ((sm100::smem_u32(act_smem + (size_t)s * stage_bytes) >> 4) & 0x3FFFu) | ((uint32_t)(3 * seg_rows) << 16);
           const uint32_t d = c.tmem_base + (uint32_t)(slot * kStackN);
           if (sm100::elect_one()) {
             if (layer == 0) {
@@ -660,6 +680,14 @@ __device__ __forceinline__ void layers_pipelined(Ctx& c, unsigned mask) {
         }
       }
     }
+  } else if (c.warp == kSigWarp) {
+    // ------------------------------------------------------------------ barrier signaller
+    for (int layer = 0; layer + 1 < nconv; ++layer)
+      for (int k = 0; k < kMaxChains; ++k) {
+        if (!((mask >> k) & 1u)) continue;
+        // phase of the chain's mbarrier: nconv - 1 (odd) arrivals per round the chain was active in
+        chain_signal(c, k, ((ev_get(c, k) / (unsigned)nconv) + (unsigned)layer) & 1u);
+      }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-7)
     for (int layer = 0; layer < nconv; ++layer) {
@@ -783,7 +811,7 @@ __device__ __forceinline__ void tc_layer_x2(Ctx& c, int layer) {
       __syncwarp();
       ++c.mma_cnt;
     }
-  } else {
+  } else if (c.warp < 8) {
     if (last) {
       hit = tc_epilogue<EPI_LAST, true>(c, 0, layer, ntiles);
     } else if (!(layer & 1)) {
@@ -1808,9 +1836,9 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
   Sched* sc = c.s_sched;
   constexpr int kStateWords = (int)(sizeof(CanvasState) / 8);
   constexpr int kSchedWords = (int)(sizeof(Sched) / 8);
-  static_assert(sizeof(CanvasState) <= 512 && sizeof(CanvasState) % 8 == 0, "state copy area");
-  static_assert(sizeof(Sched) <= 1024 && sizeof(Sched) % 8 == 0, "scheduler copy area");
-  static_assert(kSchedWords <= 64, "scheduler copy uses threads 256..319");
+  static_assert(sizeof(CanvasState) <= 384 && sizeof(CanvasState) % 8 == 0, "state copy area");
+  static_assert(sizeof(Sched) <= 320 && sizeof(Sched) % 8 == 0, "scheduler copy area");
+  static_assert(kSchedWords <= 64 && 256 + 64 <= kThreads - kMaxChains, "scheduler copy uses threads 256..319");
   const unsigned par = (c.round & 1u) ^ 1u;   // parity the finished round was staged with
   const long long t_all = prof_now(c);
   // Watchdog: one launch covers at most 2^15 FoV steps (a few seconds).  A launch that is still going after
@@ -1826,8 +1854,8 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
   }
   if (c.tid >= 256 && c.tid - 256 < kSchedWords)
     reinterpret_cast<unsigned long long*>(sc)[c.tid - 256] = __ldcg(reinterpret_cast<const unsigned long long*>(p.sched) + (c.tid - 256));
-  if (c.tid >= 320 - kMaxChains) {
-    const int k = c.tid - (320 - kMaxChains);
+  if (c.tid >= kThreads - kMaxChains) {
+    const int k = c.tid - (kThreads - kMaxChains);
     if (k < K) c.s_misc[4 + k] = (((stepped >> k) & 1u) && disco_active(p, k, par)) ? 1 : 0;
   }
   __syncthreads();
@@ -1869,6 +1897,10 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
         LChain L{k, chain_state(c, k), par, ((stepped >> k) & 1u) && c.s_misc[4 + k] != 0};
         acts[k] = chain_advance(c, L, sc, pause);
         if (acts[k] != ACT_EXIT && acts[k] != ACT_IDLE) any = true;
+        if (acts[k] == ACT_IDLE && c.lane == 0) {
+          if (L.st->phase == PH_FREE) sc->idle_free++;
+          else sc->idle_wait++;
+        }
       }
     }
     // segment_all: done when the line is empty and no chain holds an object; otherwise idle chains keep the
@@ -2111,15 +2143,16 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   c.mb_empty = c.mb_full + kActStages;
   c.mb_tfull = c.mb_empty + kActStages;
   c.mb_tempty = c.mb_tfull + kAccSlots;
-  c.s_tmem = reinterpret_cast<uint32_t*>(c.mb_tempty + kAccSlots);
+  c.mb_sig = c.mb_tempty + kAccSlots;
+  c.s_tmem = reinterpret_cast<uint32_t*>(c.mb_sig + kMaxChains);
   c.load_cnt = c.mma_cnt = c.epi_cnt = 0;
-  c.s_misc = reinterpret_cast<int*>(smem_raw + L.bars + 128);      // 8 + 3 * 32 ints
+  c.s_misc = reinterpret_cast<int*>(smem_raw + L.bars + 160);      // 8 + 3 * 32 ints
   c.s_round = reinterpret_cast<int*>(smem_raw + L.bars + 640);     // 2 * kMaxChains * 4 ints
   c.s_xchg = reinterpret_cast<float*>(smem_raw + L.bars + 1024);
   c.s_dot = c.s_xchg + 2 * 2 * 4 * 2 * 16;
   c.s_state = reinterpret_cast<CanvasState*>(smem_raw + L.bars + 4096);
-  c.s_sched = reinterpret_cast<Sched*>(smem_raw + L.bars + 4096 + kMaxChains * 512);
-  static_assert((2 + 2 * kActStages + 2 * kAccSlots) * 8 + 8 <= 128, "mbarrier area");
+  c.s_sched = reinterpret_cast<Sched*>(smem_raw + L.bars + 4096 + kMaxChains * 384);
+  static_assert((2 + 2 * kActStages + 2 * kAccSlots + kMaxChains) * 8 + 8 <= 160, "mbarrier area");
   c.prof = nullptr;
   if (FFN_PROFILE && p.ws.prof && (c.cta == 0 || c.cta == c.G - 1)) {
     c.prof = reinterpret_cast<long long*>(smem_raw + L.bars + 832);
@@ -2147,6 +2180,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
         sm100::mbar_init(&c.mb_tfull[i], 1);
         sm100::mbar_init(&c.mb_tempty[i], 8);   // one arrival per epilogue warp
       }
+      for (int i = 0; i < kMaxChains; ++i) sm100::mbar_init(&c.mb_sig[i], 8);
       sm100::fence_mbar_init();
     }
     __syncwarp();
@@ -2156,7 +2190,12 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
     sm100::tc_fence_after();
     c.tmem_base = __shfl_sync(0xffffffffu, *c.s_tmem, 0);
     if (p.compute_mode == FFN_COMPUTE_FP16_TC) {   // the split mode loads both weight halves per layer
-      if (c.warp == kLoadWarp && c.lane == 0) tc_issue_weight_load(c, 0);
+      if (c.warp == kLoadWarp && c.lane == 0) {
+        tc_issue_weight_load(c, 0);
+        if (p.use_tmap)
+          for (int k = 0; k < p.nchains; ++k)
+            for (int i = 0; i < 3; ++i) sm100::tma_prefetch_desc(&p.tmap[k][i]);
+      }
       bit_set(c, 8, true);
     }
   }

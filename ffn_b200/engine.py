@@ -233,9 +233,10 @@ class DeviceCanvas:
 
   def spec_stats(self) -> dict:
     """Early-run bookkeeping of the last segment_all (see ffn_canvas_spec_stats)."""
-    buf = (C.c_int64 * 4)()
+    buf = (C.c_int64 * 8)()
     _lib.check(self._lib.ffn_canvas_spec_stats(self._h, buf))
-    return dict(zip(('early_runs', 'early_runs_discarded', 'steps_discarded', 'steps_executed'), [int(v) for v in buf]))
+    return dict(zip(('early_runs', 'early_runs_discarded', 'steps_discarded', 'steps_executed', 'rounds',
+                     'chain_rounds_free', 'chain_rounds_waiting', 'chains'), [int(v) for v in buf]))
 
   def set_resume(self, iters: int, min_pos, max_pos):
     _lib.check(self._lib.ffn_canvas_set_resume(self._h, int(iters), _lib.i3(min_pos), _lib.i3(max_pos)))

@@ -217,8 +217,10 @@ int ffn_canvas_set_max_id(FfnCanvas* canvas, int64_t max_id);
 int ffn_canvas_get_counters(FfnCanvas* canvas, FfnCounters* out);
 /* Bookkeeping of the last ffn_canvas_segment_all: out[0] objects started ahead of their turn, out[1] of
  * those discarded (re-run in turn or rejected by the in-order gating), out[2] FoV steps of the discarded runs,
- * out[3] FoV steps executed in total (FfnCounters.inference_calls counts only what the reference counts). */
-int ffn_canvas_spec_stats(FfnCanvas* canvas, int64_t out[4]);
+ * out[3] FoV steps executed in total (FfnCounters.inference_calls counts only what the reference counts),
+ * out[4] rounds of the persistent kernel, out[5] / out[6] chain-rounds spent without an object / waiting for the
+ * turn to commit, out[7] chains used. */
+int ffn_canvas_spec_stats(FfnCanvas* canvas, int64_t out[8]);
 
 /* Multi-GPU merge helpers: raw device pointers for NCCL, and the HBM-bound
  * relabel kernel that adds a rank's ID offset to every label > 0. */

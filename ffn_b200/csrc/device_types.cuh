@@ -27,7 +27,9 @@ constexpr int kStackN = 96;       // UMMA N: the three dx taps of a (dz, dy) tap
 constexpr int kFeat = 32;         // feature maps of every hidden layer (UMMA N)
 constexpr int kGroupTiles = 3;    // accumulator slots in TMEM (the residual stream starts behind them)
 constexpr int kMaxConv = 32;      // 2 * depth limit
-constexpr int kMaxChains = 3;     // flood-fill chains (objects in flight) time-multiplexed over the SMs of one kernel
+constexpr int kMaxChains = 3;     // flood-fill chains (execution slots) time-multiplexed over the SMs of one kernel
+constexpr int kBufsPerChain = 4;  // object buffers per chain: finished objects that wait for their turn to commit are parked
+constexpr int kMaxBufs = kMaxChains * kBufsPerChain;
 constexpr int kSplitShift = 10;   // FFN_COMPUTE_FP16X2_TC: weights are split as w * 2^10 = hi + lo (keeps lo a normal fp16
                                   // number for |w| down to ~1e-4); the epilogue scales the accumulators back (exact)
 constexpr int kTmemCols = 512;    // accumulators (kGroupTiles * kStackN columns) + fp32 residual stream (32 per tile)
@@ -96,17 +98,21 @@ struct CanvasDev {
   int lat_dim[3], lat_off[3];
 };
 
-// One flood-fill chain: the private state of ONE object in flight (what the reference keeps in Canvas.seed and
-// the FaceMaxMovementPolicy object) plus the step workspace of its FoV.  Chain 0 owns the canvas's own seed
-// array; chains 1.. grow objects speculatively in private seed arrays (see Sched).
+// One OBJECT BUFFER: the private state of one object in flight — what the reference keeps in Canvas.seed and the
+// FaceMaxMovementPolicy object.  Buffer 0 owns the canvas's own seed array; the others hold objects grown ahead of
+// their turn (see Sched).  A chain (execution slot) works on one of its kBufsPerChain buffers at a time.
 struct CanvasState;
-struct ChainDev {
-  float* seed;                // seed canvas of this chain (NaN = unvisited)
+struct ObjDev {
+  float* seed;                // seed canvas of this object (NaN = unvisited)
   float* q_score;             // movement policy FIFO
   int* q_pos;                 // [cap][3]
   unsigned* lattice;          // epoch stamps over the quantised lattice (done set)
   int* traj;                  // [traj_cap][3] FoV positions of the object in flight (speculation check)
   CanvasState* st;
+};
+
+// One chain: the step workspace of its FoV.
+struct ChainDev {
   __half* act0_h;             // [2][rows_alloc][8] (chunk 1 stays zero)
   __half* act_h[2];           // [4][rows_alloc][8]
   float* seed_raw[2];         // [nt*128] seed FoV as read from the canvas (NaN preserved), by round parity
@@ -173,7 +179,15 @@ struct CanvasState {
 // sequential order, for any number of chains and any choice of early seeds.
 struct Sched {
   long long commit_idx;       // seeds [0, commit_idx) are final
-  int owner;                  // chain holding seed commit_idx (or the restored in-flight object); -1: none
+  // Every chain has kBufsPerChain object buffers (k * kBufsPerChain ...): `active` is the one it works on, the others
+  // are unusable (-1), empty (0), hold a finished object waiting for its turn (1) or a run that was suspended to let
+  // such an object commit (2).
+  long long bseed[kMaxBufs];          // seed index of the object in a buffer (-1: none)
+  int bkind[kMaxBufs];                // -1 unusable, 0 empty, 1 parked, 2 suspended, 3 active
+  int bround[kMaxBufs];               // round in which the buffer's object was parked / suspended
+  int active[kMaxChains];
+  int pad_active;
+  int owner;                  // BUFFER holding seed commit_idx (or the restored in-flight object); -1: none
   int nchains;
   int max_id;
   int overflow;               // 1: queue, 2: overlaps, 4: origins, 8: trajectory
@@ -187,7 +201,7 @@ struct Sched {
   // the next one starts).  `last_chain` is the chain whose seed array holds that object; when that chain is about
   // to start an object ahead of its turn (which may later be discarded), its box is first moved to the snapshot
   // array, so the last in-turn object is never lost.
-  int last_chain;             // -1: none
+  int last_chain;             // BUFFER whose seed array holds that object; -1: none
   int last_in_snap;
   int snap_lo[3], snap_hi[3];         // box of the snapshot array holding data (hi exclusive)
   int snap_old_lo[3], snap_old_hi[3]; // previous snapshot box, cleared by the move pass of this round
@@ -198,6 +212,7 @@ struct Sched {
 struct Ctl {
   int action[kMaxChains];
   int pos[kMaxChains][3];
+  int buf[kMaxChains];      // object buffer the chain works on this round
 };
 
 enum Mode : int { MODE_PREDICT = 0, MODE_UPDATE_AT = 1, MODE_SEGMENT = 2 };
@@ -236,6 +251,7 @@ struct KParams {
   CanvasDev cv;
   int nchains;
   ChainDev ch[kMaxChains];
+  ObjDev ob[kMaxBufs];
   Sched* sched;
   Ctl* ctl;
   unsigned* round_flag;   // rounds published by the leader (release / acquire)
@@ -267,7 +283,7 @@ __host__ __device__ inline SmemLayout smem_layout(const Geom& g) {
   const int act_bytes = kActStages * 3 * 4 * seg_rows * 16;
   s.bias = s.act + act_bytes;
   s.bars = s.bias + (kMaxConv + 1) * 32 * 4 + 16;
-  s.total = s.bars + 4096 + kMaxChains * 384 + 320;   // barriers/misc | prof | epilogue exchange + conv_lom dots | leader's chain-state / scheduler copies
+  s.total = s.bars + 4096 + kMaxChains * 384 + 512;   // barriers/misc | prof | epilogue exchange + conv_lom dots | leader's chain-state / scheduler copies
   return s;
 }
 

@@ -67,7 +67,7 @@ struct FfnEngine {
   int max_chains = ffn::kMaxChains;       // chains the multi-seed / batched paths may use (ffn_engine_set_chains)
   ffn::Ctl* d_ctl = nullptr;
   unsigned* d_round_flag = nullptr;
-  ffn::CanvasState* d_dummy_state = nullptr;   // [kMaxChains]
+  ffn::CanvasState* d_dummy_state = nullptr;   // [kMaxBufs]
   ffn::Sched* d_dummy_sched = nullptr;
   // predict staging
   float* d_in_seed = nullptr;
@@ -88,11 +88,11 @@ struct FfnEngine {
 struct FfnCanvas {
   FfnEngine* eng = nullptr;
   ffn::CanvasDev cv{};
-  ffn::ChainDev ch[ffn::kMaxChains]{};    // canvas-side buffers of the chains; [0] is the canvas's own seed array
-  int nchains_alloc = 1;
+  ffn::ObjDev ob[ffn::kMaxBufs]{};        // object buffers; [0] holds the canvas's own seed array
+  int nbufs_alloc = 1;
   float* d_snap = nullptr;                // snapshot seed array (Sched::last_chain), allocated with the extra chains
-  ffn::CanvasState* d_state = nullptr;    // [kMaxChains]
-  ffn::CanvasState h_state{};             // chain 0
+  ffn::CanvasState* d_state = nullptr;    // [kMaxBufs]
+  ffn::CanvasState h_state{};             // buffer 0
   ffn::Sched* d_sched = nullptr;
   ffn::Sched h_sched{};
   size_t q_cap = 0, traj_cap = 0;
@@ -168,16 +168,10 @@ int launch(FfnEngine* e, FfnCanvas* c, int nchains, const Job& job) {
   if (!e->profiling) p.ws.prof = nullptr;
   if (c) p.cv = c->cv;
   p.nchains = nchains;
-  for (int k = 0; k < kMaxChains; ++k) {
-    p.ch[k] = e->cws[k];
-    if (c && k < c->nchains_alloc) {
-      p.ch[k].seed = c->ch[k].seed;
-      p.ch[k].q_score = c->ch[k].q_score;
-      p.ch[k].q_pos = c->ch[k].q_pos;
-      p.ch[k].lattice = c->ch[k].lattice;
-      p.ch[k].traj = c->ch[k].traj;
-    }
-    p.ch[k].st = c ? c->d_state + k : e->d_dummy_state + k;
+  for (int k = 0; k < kMaxChains; ++k) p.ch[k] = e->cws[k];
+  for (int b = 0; b < kMaxBufs; ++b) {
+    if (c && b < c->nbufs_alloc) p.ob[b] = c->ob[b];
+    p.ob[b].st = c ? c->d_state + b : e->d_dummy_state + b;
   }
   p.sched = c ? c->d_sched : e->d_dummy_sched;
   p.ctl = e->d_ctl;
@@ -220,9 +214,9 @@ int push_state(FfnCanvas* c) {
   return 0;
 }
 
-// Queue / done lattice / trajectory log of one chain (the seed array of chain 0 is the canvas's own).
-int alloc_chain(FfnCanvas* c, int k) {
-  ChainDev& ch = c->ch[k];
+// Seed array, queue, done lattice and trajectory log of one object buffer (buffer 0's seed array is the canvas's own).
+int alloc_buf(FfnCanvas* c, int k) {
+  ObjDev& ch = c->ob[k];
   if (k > 0) {
     if (dev_alloc(&ch.seed, c->nvox, false)) return 1;
     fill_f32_kernel<<<c->eng->sm_count * 8, 256, 0, cudaStreamPerThread>>>(ch.seed, c->nvox, NAN);
@@ -235,11 +229,11 @@ int alloc_chain(FfnCanvas* c, int k) {
   return 0;
 }
 
-// Private seed arrays etc. for chains 1 .. n-1 and the snapshot array, on first use.
-int ensure_chains(FfnCanvas* c, int n) {
-  for (int k = c->nchains_alloc; k < n; ++k) {
-    if (alloc_chain(c, k)) return 1;
-    c->nchains_alloc = k + 1;
+// Object buffers 1 .. n-1 and the snapshot array, on first use.
+int ensure_bufs(FfnCanvas* c, int n) {
+  for (int k = c->nbufs_alloc; k < n; ++k) {
+    if (alloc_buf(c, k)) return 1;
+    c->nbufs_alloc = k + 1;
   }
   if (n > 1 && !c->d_snap) {
     if (dev_alloc(&c->d_snap, c->nvox, false)) return 1;
@@ -304,7 +298,7 @@ int box_copy(FfnCanvas* c, int which, const int32_t lo[3], const int32_t sz[3], 
   size_t esz = 0;
   char* base = nullptr;
   switch (which) {
-    case FFN_ARRAY_SEED: esz = 4; base = reinterpret_cast<char*>(c->ch[0].seed); break;
+    case FFN_ARRAY_SEED: esz = 4; base = reinterpret_cast<char*>(c->ob[0].seed); break;
     case FFN_ARRAY_SEGMENTATION: esz = 4; base = reinterpret_cast<char*>(cv.seg); break;
     case FFN_ARRAY_QPROB:
       if (!cv.qprob) return fail("canvas was created without probability maps");
@@ -476,7 +470,7 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   }
   if (dev_alloc(&e->d_ctl, 1)) return 1;
   if (dev_alloc(&e->d_round_flag, 1)) return 1;
-  if (dev_alloc(&e->d_dummy_state, kMaxChains)) return 1;
+  if (dev_alloc(&e->d_dummy_state, kMaxBufs)) return 1;
   if (dev_alloc(&e->d_dummy_sched, 1)) return 1;
   for (void* p : std::vector<void*>{e->d_ctl, e->d_round_flag, e->d_dummy_state, e->d_dummy_sched}) e->owned.push_back(p);
   *out = e.release();
@@ -606,12 +600,12 @@ int ffn_canvas_create(FfnEngine* e, const void* image, int image_dtype, const in
   CUDA_OK(cudaMalloc(&c->d_image, ibytes));
   CUDA_OK(cudaMemcpy(c->d_image, image, ibytes, cudaMemcpyHostToDevice));
   cv.image = c->d_image;
-  if (dev_alloc(&c->ch[0].seed, c->nvox, false)) return 1;
+  if (dev_alloc(&c->ob[0].seed, c->nvox, false)) return 1;
   if (dev_alloc(&cv.seg, c->nvox)) return 1;
   if (keep_probability_maps) {
     if (dev_alloc(&cv.qprob, c->nvox)) return 1;
   }
-  fill_f32_kernel<<<e->sm_count * 8, 256, 0, cudaStreamPerThread>>>(c->ch[0].seed, c->nvox, NAN);
+  fill_f32_kernel<<<e->sm_count * 8, 256, 0, cudaStreamPerThread>>>(c->ob[0].seed, c->nvox, NAN);
   CUDA_OK(cudaGetLastError());
   // movement policy storage
   const int del[3] = {std::max(g.dz, 1), std::max(g.dy, 1), std::max(g.dx, 1)};
@@ -629,14 +623,20 @@ int ffn_canvas_create(FfnEngine* e, const void* image, int image_dtype, const in
   c->traj_cap = std::min<size_t>(qcells + 16, (size_t)1 << 28);   // one FoV step per lattice cell at most
   cv.q_cap = (int)c->q_cap;
   cv.traj_cap = (int)c->traj_cap;
-  if (alloc_chain(c.get(), 0)) return 1;
-  if (dev_alloc(&c->d_state, kMaxChains)) return 1;
+  if (alloc_buf(c.get(), 0)) return 1;
+  if (dev_alloc(&c->d_state, kMaxBufs)) return 1;
   if (dev_alloc(&c->d_sched, 1)) return 1;
   if (dev_alloc(&c->d_pred, (size_t)g.V, false)) return 1;
   std::memset(&c->h_state, 0, sizeof(CanvasState));
   std::memset(&c->h_sched, 0, sizeof(Sched));
   c->h_sched.owner = -1;
   c->h_sched.last_chain = -1;
+  for (int k = 0; k < kMaxChains; ++k) c->h_sched.active[k] = kBufsPerChain * k;
+  for (int b = 0; b < kMaxBufs; ++b) {
+    c->h_sched.bseed[b] = -1;
+    c->h_sched.bkind[b] = b == 0 ? 3 : -1;
+  }
+  CUDA_OK(cudaMemcpy(c->d_sched, &c->h_sched, sizeof(Sched), cudaMemcpyHostToDevice));
   c->h_state.seed_index = -1;
   if (push_state(c.get())) return 1;
   CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
@@ -650,12 +650,12 @@ void ffn_canvas_destroy(FfnCanvas* c) {
   FfnEngine* e = c->eng;
   cudaSetDevice(e->device);
   cudaFree(c->d_image);
-  for (int k = 0; k < kMaxChains; ++k) {
-    cudaFree(c->ch[k].seed);
-    cudaFree(c->ch[k].lattice);
-    cudaFree(c->ch[k].q_score);
-    cudaFree(c->ch[k].q_pos);
-    cudaFree(c->ch[k].traj);
+  for (int k = 0; k < kMaxBufs; ++k) {
+    cudaFree(c->ob[k].seed);
+    cudaFree(c->ob[k].lattice);
+    cudaFree(c->ob[k].q_score);
+    cudaFree(c->ob[k].q_pos);
+    cudaFree(c->ob[k].traj);
   }
   cudaFree(c->d_snap);
   cudaFree(c->cv.seg);
@@ -695,8 +695,8 @@ int ffn_canvas_init_seed(FfnCanvas* c, const int32_t pos[3]) {
   if (pull_state(c)) return 1;
   CanvasState& st = c->h_state;
   // clear only what can be non-NaN (== NumpyArray.clear), then place the seed
-  if (fill_box(c, c->ch[0].seed, st.dirty_lo, st.dirty_hi)) return 1;
-  CUDA_OK(cudaMemcpyAsync(c->ch[0].seed + ((size_t)pos[0] * c->cv.sy + pos[1]) * c->cv.sx + pos[2],
+  if (fill_box(c, c->ob[0].seed, st.dirty_lo, st.dirty_hi)) return 1;
+  CUDA_OK(cudaMemcpyAsync(c->ob[0].seed + ((size_t)pos[0] * c->cv.sy + pos[1]) * c->cv.sx + pos[2],
                           &c->cv.opt.init_activation, sizeof(float), cudaMemcpyHostToDevice, cudaStreamPerThread));
   CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
   for (int k = 0; k < 3; ++k) {
@@ -770,7 +770,7 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   // trace (Canvas.history) run one object at a time.
   int K = 1;
   if (e->compute_mode == FFN_COMPUTE_FP16_TC && !c->cv.trace) K = chain_limit(e);
-  if (ensure_chains(c, K)) return 1;
+  if (ensure_bufs(c, K > 1 ? kBufsPerChain * K : 1)) return 1;
   int* d_seeds = nullptr;
   FfnOrigin* d_orig = nullptr;
   FfnOverlap* d_ovl = nullptr;
@@ -812,13 +812,19 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   const bool has_data = st.dirty_hi[0] > st.dirty_lo[0];
   sc.last_chain = has_data ? 0 : -1;   // what Canvas.seed shows right now
   sc.last_in_snap = 0;
-  std::vector<CanvasState> hs(kMaxChains);
-  if (cudaMemcpy(hs.data(), c->d_state, sizeof(CanvasState) * kMaxChains, cudaMemcpyDeviceToHost) != cudaSuccess) {
+  for (int k = 0; k < kMaxChains; ++k) sc.active[k] = kBufsPerChain * k;
+  for (int b = 0; b < kMaxBufs; ++b) {
+    sc.bseed[b] = -1;
+    sc.bround[b] = 0;
+    sc.bkind[b] = b >= c->nbufs_alloc || b >= K * kBufsPerChain ? -1 : (b % kBufsPerChain == 0 ? 3 : 0);
+  }
+  std::vector<CanvasState> hs(kMaxBufs);
+  if (cudaMemcpy(hs.data(), c->d_state, sizeof(CanvasState) * kMaxBufs, cudaMemcpyDeviceToHost) != cudaSuccess) {
     cleanup();
     return fail("state copy failed");
   }
   hs[0] = st;
-  for (int k = 0; k < kMaxChains; ++k) {
+  for (int k = 0; k < kMaxBufs; ++k) {
     CanvasState& h = hs[k];
     h.seg_all = 1;
     h.seed_index = -1;
@@ -829,7 +835,7 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
     h.phase = (k == 0 && resume) ? PH_POP : PH_FREE;
     if (!(k == 0 && resume)) h.have_cur = 0;
   }
-  if (cudaMemcpy(c->d_state, hs.data(), sizeof(CanvasState) * kMaxChains, cudaMemcpyHostToDevice) != cudaSuccess ||
+  if (cudaMemcpy(c->d_state, hs.data(), sizeof(CanvasState) * kMaxBufs, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(c->d_sched, &sc, sizeof(Sched), cudaMemcpyHostToDevice) != cudaSuccess) {
     cleanup();
     return fail("state upload failed");
@@ -871,12 +877,12 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
     (void)before_round;
     if (stuck < 3) stuck = (sc.steps_executed == before_steps && sc.commit_idx == before_idx) ? stuck + 1 : 0;
     if (stuck >= 3) {
-      std::vector<CanvasState> dbg(kMaxChains);
-      cudaMemcpy(dbg.data(), c->d_state, sizeof(CanvasState) * kMaxChains, cudaMemcpyDeviceToHost);
+      std::vector<CanvasState> dbg(kMaxBufs);
+      cudaMemcpy(dbg.data(), c->d_state, sizeof(CanvasState) * kMaxBufs, cudaMemcpyDeviceToHost);
       std::string msg = "segment_all made no progress: device scheduler stalled at seed " + std::to_string(sc.commit_idx) +
                         " of " + std::to_string(n_seeds) + ", owner " + std::to_string(sc.owner) + ", round " +
-                        std::to_string(sc.round) + "; chains (phase/seed/spec/iters/fin_round):";
-      for (int k = 0; k < K; ++k)
+                        std::to_string(sc.round) + "; buffers (phase/seed/spec/iters/fin_round):";
+      for (int k = 0; k < c->nbufs_alloc; ++k)
         msg += " [" + std::to_string(dbg[k].phase) + "/" + std::to_string(dbg[k].seed_index) + "/" + std::to_string(dbg[k].spec) +
                "/" + std::to_string(dbg[k].iters) + "/" + std::to_string(dbg[k].fin_round) + "]";
       rc = fail(msg);
@@ -886,7 +892,7 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   if (!rc && pull_state(c)) rc = 1;
   // ---- Canvas.seed shows the last object segment_at ran on: bring it into the canvas's own array
   if (!rc && (sc.last_in_snap || sc.last_chain > 0)) {
-    const float* src = sc.last_in_snap ? c->d_snap : c->ch[sc.last_chain].seed;
+    const float* src = sc.last_in_snap ? c->d_snap : c->ob[sc.last_chain].seed;
     int lo[3], hi[3];
     CanvasState last{};
     if (!sc.last_in_snap &&
@@ -896,9 +902,9 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
       lo[q] = std::max(sc.last_in_snap ? sc.snap_lo[q] : last.dirty_lo[q], 0);
       hi[q] = std::min(sc.last_in_snap ? sc.snap_hi[q] : last.dirty_hi[q], q == 0 ? c->cv.sz : q == 1 ? c->cv.sy : c->cv.sx);
     }
-    if (!rc && fill_box(c, c->ch[0].seed, st.dirty_lo, st.dirty_hi)) rc = 1;
+    if (!rc && fill_box(c, c->ob[0].seed, st.dirty_lo, st.dirty_hi)) rc = 1;
     if (!rc && hi[0] > lo[0] && hi[1] > lo[1] && hi[2] > lo[2]) {
-      copy_box_f32_kernel<<<e->sm_count * 4, 256, 0, cudaStreamPerThread>>>(c->ch[0].seed, src, c->cv.sy, c->cv.sx, lo[0], lo[1],
+      copy_box_f32_kernel<<<e->sm_count * 4, 256, 0, cudaStreamPerThread>>>(c->ob[0].seed, src, c->cv.sy, c->cv.sx, lo[0], lo[1],
                                                                          lo[2], hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
       if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(cudaStreamPerThread) != cudaSuccess)
         rc = fail("seed box copy failed");
@@ -909,7 +915,7 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
     }
   } else if (!rc && sc.last_chain < 0) {
     // no object ran in turn: Canvas.seed is what it was (nothing); early runs on chain 0 leave no trace
-    if (fill_box(c, c->ch[0].seed, st.dirty_lo, st.dirty_hi)) rc = 1;
+    if (fill_box(c, c->ob[0].seed, st.dirty_lo, st.dirty_hi)) rc = 1;
     for (int q = 0; q < 3; ++q) st.dirty_lo[q] = st.dirty_hi[q] = 0;
     cudaStreamSynchronize(cudaStreamPerThread);
   }
@@ -1021,7 +1027,7 @@ int ffn_canvas_policy_state_size(FfnCanvas* c, int64_t* queue_len, int64_t* done
   // a position popped for the next step but not yet executed (paused launch) is still part of the queue
   *queue_len = c->h_state.q_tail - c->h_state.q_head + ((c->h_state.popped && c->h_state.pop_run) ? 1 : 0);
   std::vector<unsigned> lat(c->lattice_cells);
-  CUDA_OK(cudaMemcpy(lat.data(), c->ch[0].lattice, lat.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(lat.data(), c->ob[0].lattice, lat.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
   int64_t n = 0;
   if (c->h_state.epoch)
     for (unsigned v : lat) n += v == c->h_state.epoch;
@@ -1039,8 +1045,8 @@ int ffn_canvas_policy_state_get(FfnCanvas* c, double* queue_szyx, int32_t* done_
   if (n > 0 && queue_szyx) {
     std::vector<float> sc(n);
     std::vector<int> ps((size_t)n * 3);
-    CUDA_OK(cudaMemcpy(sc.data(), c->ch[0].q_score + head, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
-    CUDA_OK(cudaMemcpy(ps.data(), c->ch[0].q_pos + (size_t)head * 3, (size_t)n * 3 * sizeof(int),
+    CUDA_OK(cudaMemcpy(sc.data(), c->ob[0].q_score + head, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(ps.data(), c->ob[0].q_pos + (size_t)head * 3, (size_t)n * 3 * sizeof(int),
                        cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) {
       queue_szyx[4 * i] = sc[i];
@@ -1049,7 +1055,7 @@ int ffn_canvas_policy_state_get(FfnCanvas* c, double* queue_szyx, int32_t* done_
   }
   if (done_zyx && st.epoch) {
     std::vector<unsigned> lat(c->lattice_cells);
-    CUDA_OK(cudaMemcpy(lat.data(), c->ch[0].lattice, lat.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(lat.data(), c->ob[0].lattice, lat.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
     size_t o = 0;
     const int* d = c->cv.lat_dim;
     for (size_t i = 0; i < lat.size(); ++i)
@@ -1082,15 +1088,15 @@ int ffn_canvas_policy_state_set(FfnCanvas* c, const double* queue_szyx, int64_t 
       sc[i] = (float)queue_szyx[4 * i];
       for (int k = 0; k < 3; ++k) ps[3 * i + k] = (int)queue_szyx[4 * i + 1 + k];
     }
-    CUDA_OK(cudaMemcpy(c->ch[0].q_score, sc.data(), sc.size() * sizeof(float), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(c->ch[0].q_pos, ps.data(), ps.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->ob[0].q_score, sc.data(), sc.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->ob[0].q_pos, ps.data(), ps.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
   const int* d = c->cv.lat_dim;
   for (int64_t i = 0; i < done_len; ++i) {
     const int qz = done_zyx[3 * i] + c->cv.lat_off[0], qy = done_zyx[3 * i + 1] + c->cv.lat_off[1],
               qx = done_zyx[3 * i + 2] + c->cv.lat_off[2];
     if (qz < 0 || qy < 0 || qx < 0 || qz >= d[0] || qy >= d[1] || qx >= d[2]) return fail("done-set entry outside lattice");
-    CUDA_OK(cudaMemcpy(c->ch[0].lattice + ((size_t)qz * d[1] + qy) * d[2] + qx, &st.epoch, sizeof(unsigned),
+    CUDA_OK(cudaMemcpy(c->ob[0].lattice + ((size_t)qz * d[1] + qy) * d[2] + qx, &st.epoch, sizeof(unsigned),
                        cudaMemcpyHostToDevice));
   }
   st.phase = PH_POP;
@@ -1228,7 +1234,7 @@ int ffn_canvas_spec_stats(FfnCanvas* c, int64_t out[8]) {
 int ffn_canvas_device_ptr(FfnCanvas* c, int which, void** ptr, int64_t* bytes) {
   if (!c || !ptr || !bytes) return fail("null argument");
   switch (which) {
-    case FFN_ARRAY_SEED: *ptr = c->ch[0].seed; *bytes = (int64_t)c->nvox * 4; return 0;
+    case FFN_ARRAY_SEED: *ptr = c->ob[0].seed; *bytes = (int64_t)c->nvox * 4; return 0;
     case FFN_ARRAY_SEGMENTATION: *ptr = c->cv.seg; *bytes = (int64_t)c->nvox * 4; return 0;
     case FFN_ARRAY_QPROB:
       if (!c->cv.qprob) return fail("canvas was created without probability maps");

@@ -60,7 +60,7 @@ struct Ctx {
   unsigned load_cnt, mma_cnt, epi_cnt;   // per-role running tile counters (ring index + phase parity)
   uint32_t* s_tmem;            // TMEM base address
   int* s_misc;                 // [0..3) per-chain step-count accumulators, [4..7) disco flags, [8..) leader scratch
-  int* s_round;                // [k][4] this round: action, z, y, x ; [kMaxChains + k][4] previous step: valid, z, y, x
+  int* s_round;                // [k][8] this round: action, z, y, x, buffer ; [kMaxChains + k][8] previous step: flags, z, y, x, buffer
   float* s_xchg;               // [2 tile parities][2 halves][4 warps][2][16] partial sums crossing warp boundaries
   float* s_dot;                // [2][128] conv_lom partial dot products of the upper channel half
   CanvasState* s_state;        // CTA 0: shared-memory working copies of the chain states (512-byte slots)
@@ -222,14 +222,14 @@ __device__ __forceinline__ float merged_row(const KParams& p, int k, unsigned pa
 // The previous step of the same chain may still be pasting into the canvas in other CTAs (paste and
 // stage of consecutive steps are separated by no grid barrier), so seed values inside the previous
 // FoV are taken from that step's merged logits in the workspace — exactly what the paste writes.
-__device__ __forceinline__ void stage_fov(Ctx& c, int k, int pz, int py, int px, int batch_idx) {
+__device__ __forceinline__ void stage_fov(Ctx& c, int k, int b, int pz, int py, int px, int batch_idx) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
   const ChainDev& ch = p.ch[k];
   const bool predict = p.job.mode == MODE_PREDICT;
   const unsigned par = c.round & 1u;
-  const int* prev = c.s_round + 4 * (kMaxChains + k);
-  const bool have_prev = !predict && prev[0] != 0;
+  const int* prev = c.s_round + 8 * (kMaxChains + k);
+  const bool have_prev = !predict && prev[0] != 0 && prev[4] == b;
   const bool prev_disco = have_prev && (prev[0] & 2) != 0;
   const int qz = prev[1] - g.mz, qy = prev[2] - g.my, qx = prev[3] - g.mx;   // previous FoV corner
   float* raw_out = ch.seed_raw[par];
@@ -255,7 +255,7 @@ __device__ __forceinline__ void stage_fov(Ctx& c, int k, int pz, int py, int px,
       if (have_prev && fz >= 0 && fz < g.fz && fy >= 0 && fy < g.fy && fx >= 0 && fx < g.fx) {
         s = merged_row(p, k, par ^ 1u, fz * g.pp + fy * g.xp + fx, prev_disco);
       } else {
-        s = __ldcg(ch.seed + i);
+        s = __ldcg(p.ob[b].seed + i);
       }
       fed = isnan(s) ? p.cv.opt.pad_value : s;
     }
@@ -908,7 +908,7 @@ __device__ __forceinline__ void layers_blocking(Ctx& c) {
 
 // Paste this CTA's rows of chain k's last step into the seed canvas (inference.py:439) / the prediction
 // output.  `par` = round parity the step was staged with.
-__device__ __forceinline__ void tail_paste(Ctx& c, int k, unsigned par, int pz, int py, int px, int batch_idx, bool disco) {
+__device__ __forceinline__ void tail_paste(Ctx& c, int k, int b, unsigned par, int pz, int py, int px, int batch_idx, bool disco) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
   const ChainDev& ch = p.ch[k];
@@ -923,7 +923,7 @@ __device__ __forceinline__ void tail_paste(Ctx& c, int k, unsigned par, int pz, 
     }
     const float m = merged_row(p, k, par, r, disco);
     const size_t i = ((size_t)(pz - g.mz + z) * p.cv.sy + (py - g.my + y)) * p.cv.sx + (px - g.mx + x);
-    ch.seed[i] = m;
+    p.ob[b].seed[i] = m;
     if (p.job.mode == MODE_UPDATE_AT && p.job.pred_out) p.job.pred_out[fi] = m;
   }
 }
@@ -952,7 +952,8 @@ __device__ __forceinline__ size_t lattice_index(const KParams& p, const CanvasSt
 
 // Leader-side view of one chain: k, its state copy, the parity its last step was staged with, its disco flag.
 struct LChain {
-  int k;
+  int k;                 // chain (workspace of the step)
+  int b;                 // object buffer (seed array, queue, done set, trajectory)
   CanvasState* st;
   unsigned par;
   bool disco;
@@ -968,7 +969,7 @@ __device__ __forceinline__ float seed_value(const KParams& p, const LChain& L, i
     if (fz >= 0 && fz < g.fz && fy >= 0 && fy < g.fy && fx >= 0 && fx < g.fx)
       return merged_row(p, L.k, L.par, fz * g.pp + fy * g.xp + fx, L.disco);
   }
-  return __ldcg(p.ch[L.k].seed + cv_index(p.cv, z, y, x));
+  return __ldcg(p.ob[L.b].seed + cv_index(p.cv, z, y, x));
 }
 
 // Optional event log for debugging / history export (one chain only; lane 0 of the leader warp).
@@ -993,10 +994,10 @@ __device__ __forceinline__ void push_move(const KParams& p, const LChain& L, flo
   }
   const int t = st->q_tail++;
   trace_event(p, st, EV_PUSH, z, y, x);
-  p.ch[L.k].q_score[t] = score;
-  p.ch[L.k].q_pos[3 * t + 0] = z;
-  p.ch[L.k].q_pos[3 * t + 1] = y;
-  p.ch[L.k].q_pos[3 * t + 2] = x;
+  p.ob[L.b].q_score[t] = score;
+  p.ob[L.b].q_pos[3 * t + 0] = z;
+  p.ob[L.b].q_pos[3 * t + 1] = y;
+  p.ob[L.b].q_pos[3 * t + 2] = x;
 }
 
 // Policy scratch of chain k in shared memory: score[6] floats, rel[6][3], ok[6].
@@ -1088,7 +1089,7 @@ __device__ __forceinline__ void face_argmax(const Ctx& c, const LChain& L, int f
 // indexed local arrays here: local memory lives behind the L1 that every acquire invalidates.)
 __device__ __forceinline__ void policy_finish(const Ctx& c, const LChain& L) {
   const KParams& p = *c.p;
-  const ChainDev& ch = p.ch[L.k];
+  const ObjDev& ob = p.ob[L.b];
   CanvasState* st = L.st;
   int* scr = policy_scratch(c, L.k);
   const float* s_score = reinterpret_cast<const float*>(scr);
@@ -1126,20 +1127,20 @@ __device__ __forceinline__ void policy_finish(const Ctx& c, const LChain& L) {
   const int room = max(p.cv.q_cap - tail, 0);
   if (keep && rank < room) {
     const int t = tail + rank;
-    ch.q_score[t] = sc;
-    ch.q_pos[3 * t + 0] = st->cur[0] + rz;
-    ch.q_pos[3 * t + 1] = st->cur[1] + ry;
-    ch.q_pos[3 * t + 2] = st->cur[2] + rx;
+    ob.q_score[t] = sc;
+    ob.q_pos[3 * t + 0] = st->cur[0] + rz;
+    ob.q_pos[3 * t + 1] = st->cur[1] + ry;
+    ob.q_pos[3 * t + 2] = st->cur[2] + rx;
   }
   __syncwarp();
   if (c.lane == 0) {
-    ch.lattice[lattice_index(p, st, st->cur[0], st->cur[1], st->cur[2])] = st->epoch;
+    ob.lattice[lattice_index(p, st, st->cur[0], st->cur[1], st->cur[2])] = st->epoch;
     if (n > room) st->overflow |= 1;
     const int wrote = min(n, room);
     if (p.cv.trace) {
       for (int i = 0; i < wrote; ++i)
-        trace_event(p, st, EV_PUSH, __ldcg(ch.q_pos + 3 * (tail + i)), __ldcg(ch.q_pos + 3 * (tail + i) + 1),
-                    __ldcg(ch.q_pos + 3 * (tail + i) + 2));
+        trace_event(p, st, EV_PUSH, __ldcg(ob.q_pos + 3 * (tail + i)), __ldcg(ob.q_pos + 3 * (tail + i) + 1),
+                    __ldcg(ob.q_pos + 3 * (tail + i) + 2));
     }
     st->q_tail = tail + wrote;
   }
@@ -1150,14 +1151,14 @@ __device__ __forceinline__ void policy_finish(const Ctx& c, const LChain& L) {
 // for queue entries; lane 0 only (used while the event trace records: per-candidate events in order).
 __device__ __forceinline__ bool pop_next(const KParams& p, const LChain& L, int& z, int& y, int& x) {
   const Geom& g = p.g;
-  const ChainDev& ch = p.ch[L.k];
+  const ObjDev& ob = p.ob[L.b];
   CanvasState* st = L.st;
   while (st->q_head < st->q_tail) {
     const int h = st->q_head++;
-    z = __ldcg(ch.q_pos + 3 * h);
-    y = __ldcg(ch.q_pos + 3 * h + 1);
-    x = __ldcg(ch.q_pos + 3 * h + 2);
-    const unsigned stamp = __ldcg(ch.lattice + lattice_index(p, st, z, y, x));
+    z = __ldcg(ob.q_pos + 3 * h);
+    y = __ldcg(ob.q_pos + 3 * h + 1);
+    x = __ldcg(ob.q_pos + 3 * h + 2);
+    const unsigned stamp = __ldcg(ob.lattice + lattice_index(p, st, z, y, x));
     const bool inside = z >= 0 && y >= 0 && x >= 0 && z < p.cv.sz && y < p.cv.sy && x < p.cv.sx;
     float v = 0.f;
     int sg = 0;
@@ -1211,6 +1212,7 @@ __device__ __forceinline__ bool warp_pop(const KParams& p, const LChain& L, int 
   const Geom& g = p.g;
   const CanvasDev& cv = p.cv;
   const ChainDev& ch = p.ch[L.k];
+  const ObjDev& ob = p.ob[L.b];
   CanvasState* st = L.st;
   // inference.py:503-505: value of the object's start voxel — the same for every candidate of this call
   const bool weak = seed_value(p, L, st->start[0], st->start[1], st->start[2]) < cv.opt.move_threshold;
@@ -1222,10 +1224,10 @@ __device__ __forceinline__ bool warp_pop(const KParams& p, const LChain& L, int 
     bool restricted = false;
     if (act) {
       const int h = head + lane;
-      cz = __ldcg(ch.q_pos + 3 * h);
-      cy = __ldcg(ch.q_pos + 3 * h + 1);
-      cx = __ldcg(ch.q_pos + 3 * h + 2);
-      const unsigned stamp = __ldcg(ch.lattice + lattice_index(p, st, cz, cy, cx));
+      cz = __ldcg(ob.q_pos + 3 * h);
+      cy = __ldcg(ob.q_pos + 3 * h + 1);
+      cx = __ldcg(ob.q_pos + 3 * h + 2);
+      const unsigned stamp = __ldcg(ob.lattice + lattice_index(p, st, cz, cy, cx));
       const bool inside = cz >= 0 && cy >= 0 && cx >= 0 && cz < cv.sz && cy < cv.sy && cx < cv.sx;
       float v = 0.f, old = 0.f;
       int sg = 0;
@@ -1243,7 +1245,7 @@ __device__ __forceinline__ bool warp_pop(const KParams& p, const LChain& L, int 
             old = __ldcg(ch.seed_raw[L.par] + row);
           }
         }
-        if (!in_fov) v = __ldcg(ch.seed + i);
+        if (!in_fov) v = __ldcg(ob.seed + i);
       }
       if (in_fov && L.disco && old < 0.f && v > old) v = old;
       const bool border = cz - g.mz < 0 || cy - g.my < 0 || cx - g.mx < 0 || cz + g.mz >= cv.sz ||
@@ -1353,7 +1355,7 @@ __device__ __forceinline__ void after_step(const Ctx& c, const LChain& L) {
     }
     if (st->seg_all) {   // trajectory: the positions whose `segmentation <= 0` test this object relied on
       if (st->iters < (long long)p.cv.traj_cap) {
-        int* t = p.ch[L.k].traj + 3 * st->iters;
+        int* t = p.ob[L.b].traj + 3 * st->iters;
         t[0] = st->cur[0];
         t[1] = st->cur[1];
         t[2] = st->cur[2];
@@ -1416,12 +1418,12 @@ __device__ __forceinline__ int gate_seed(const Ctx& c, Sched* sc, long long idx,
 }
 
 // Did any FoV position of the (early) run get a label since it was tested?  Warp-collective.
-__device__ __forceinline__ bool run_conflicts(const Ctx& c, int k, const CanvasState* st) {
+__device__ __forceinline__ bool run_conflicts(const Ctx& c, int b, const CanvasState* st) {
   const KParams& p = *c.p;
   bool bad = false;
   const long long n = min(st->iters, (long long)p.cv.traj_cap);
   for (long long i = c.lane; i < n; i += 32) {
-    const int* t = p.ch[k].traj + 3 * i;
+    const int* t = p.ob[b].traj + 3 * i;
     if (__ldcg(p.cv.seg + cv_index(p.cv, __ldcg(t), __ldcg(t + 1), __ldcg(t + 2))) > 0) bad = true;
   }
   return __any_sync(0xffffffffu, bad);
@@ -1448,19 +1450,21 @@ __device__ __forceinline__ void finalize_seed(Sched* sc, CanvasState* st) {
   st->phase = PH_FREE;
 }
 
-// A free chain asks for work (warp-collective; lane 0 mutates).  First the head of the line: while nobody
-// holds the seed at commit_idx, gate it in order (the reference's loop, inference.py:552-581) and run the
-// first accepted one HERE, in turn.  Otherwise look ahead for a seed worth starting early: not taken, would
-// pass the gating as things stand, and not next to an object another chain is growing right now.
-__device__ __forceinline__ void assign_seed(const Ctx& c, int k, CanvasState* st, Sched* sc) {
+// The head of the line (warp-collective; lane 0 mutates): while nobody holds the seed at commit_idx, gate it in
+// order (the reference's loop, inference.py:552-581) and run the first accepted one HERE, in turn, in the free
+// buffer L.b of chain k.  Stops when an object in flight (running, parked or suspended, in any buffer) holds the
+// seed: that buffer becomes the owner.
+__device__ __forceinline__ void advance_pointer(const Ctx& c, const LChain& L, Sched* sc) {
   const KParams& p = *c.p;
-  const unsigned full = 0xffffffffu;
+  CanvasState* st = L.st;
   while (sc->owner < 0 && sc->commit_idx < p.job.n_seeds) {
     const long long i = sc->commit_idx;
-    if (__ldcg(p.job.seed_status + i) != 0) {      // an early run holds it: its chain is now at the head of the line
+    if (__ldcg(p.job.seed_status + i) != 0) {      // an early run holds it: its buffer is now at the head of the line
       int who = -1;
       for (int q = 0; q < p.nchains; ++q)
-        if (chain_state(c, q)->seed_index == i && chain_state(c, q)->phase != PH_FREE) who = q;
+        if (chain_state(c, q)->seed_index == i && chain_state(c, q)->phase != PH_FREE) who = sc->active[q];
+      for (int b = 0; b < p.nchains * kBufsPerChain; ++b)
+        if ((sc->bkind[b] == 1 || sc->bkind[b] == 2) && sc->bseed[b] == i) who = b;
       if (c.lane == 0) sc->owner = who;
       __syncwarp();
       if (who < 0) {   // cannot happen; do not spin on it
@@ -1475,7 +1479,7 @@ __device__ __forceinline__ void assign_seed(const Ctx& c, int k, CanvasState* st
     if (c.lane == 0) {
       if (ok) {
         p.job.seed_status[i] = 1;
-        sc->owner = k;
+        sc->owner = L.b;
         start_object(st, sc, i, 0, sz, sy, sx);
       } else {
         sc->commit_idx = i + 1;
@@ -1484,9 +1488,17 @@ __device__ __forceinline__ void assign_seed(const Ctx& c, int k, CanvasState* st
     __syncwarp();
     if (ok) return;
   }
-  if (sc->owner == k || p.nchains == 1 || (p.job.debug & 2)) return;
-  // ---- look ahead
-  constexpr int kWindow = 128;
+}
+
+// Look ahead for a seed worth starting early in the free buffer L.b: not taken, would pass the gating as things
+// stand, and not next to an object a chain is growing right now (warp-collective; lane 0 mutates).
+__device__ __forceinline__ void lookahead(const Ctx& c, const LChain& L, Sched* sc) {
+  const KParams& p = *c.p;
+  const int k = L.k;
+  CanvasState* st = L.st;
+  const unsigned full = 0xffffffffu;
+  if (sc->owner == L.b || p.nchains == 1 || (p.job.debug & 2)) return;
+  constexpr int kWindow = 256;
   const long long base = sc->commit_idx + 1;
   for (int w = 0; w < kWindow; w += 32) {
     const long long j = base + w + c.lane;
@@ -1507,7 +1519,7 @@ __device__ __forceinline__ void assign_seed(const Ctx& c, int k, CanvasState* st
           for (int yy = max(sy - mbd[1], 0); yy < min(sy + mbd[1] + 1, cv.sy); ++yy)
             for (int xx = max(sx - mbd[2], 0); xx < min(sx + mbd[2] + 1, cv.sx); ++xx)
               if (__ldcg(cv.seg + cv_index(cv, zz, yy, xx)) > 0) ok = false;
-        // keep clear of the objects in flight: inside (their touched box + a FoV) the run would most likely be wasted
+        // keep clear of the objects being grown: inside (their touched box + a FoV) the run would most likely be wasted
         for (int q = 0; q < p.nchains; ++q) {
           const CanvasState* o = chain_state(c, q);
           if (q == k || o->phase == PH_FREE) continue;
@@ -1542,13 +1554,62 @@ __device__ __forceinline__ void assign_seed(const Ctx& c, int k, CanvasState* st
   }
 }
 
+// A chain turns to another of its object buffers (warp-collective): the object it leaves is written back to its
+// buffer's state block (empty, parked = finished and waiting for its turn, or suspended = a run that goes on
+// later) and the target buffer's state is loaded.  A suspended run must not go on before the round after: its
+// last paste lands during this one.
+__device__ __forceinline__ void swap_buffers(const Ctx& c, LChain& L, Sched* sc, int nb) {
+  const KParams& p = *c.p;
+  CanvasState* st = L.st;
+  constexpr int kStateWords = (int)(sizeof(CanvasState) / 8);
+  const int kind = st->phase == PH_FREE ? 0 : (st->phase == PH_FINISHED ? 1 : 2);
+  const long long left_seed = st->seed_index;
+  if (c.lane == 0 && kind == 2) st->have_cur = 0;
+  __syncwarp();
+  for (int w = c.lane; w < kStateWords; w += 32)
+    reinterpret_cast<unsigned long long*>(p.ob[L.b].st)[w] = reinterpret_cast<const unsigned long long*>(st)[w];
+  __syncwarp();
+  for (int w = c.lane; w < kStateWords; w += 32)
+    reinterpret_cast<unsigned long long*>(st)[w] = __ldcg(reinterpret_cast<const unsigned long long*>(p.ob[nb].st) + w);
+  if (c.lane == 0) {
+    sc->bkind[L.b] = kind;
+    sc->bseed[L.b] = kind ? left_seed : -1;
+    sc->bround[L.b] = (int)sc->round;
+    sc->bkind[nb] = 3;
+    sc->active[L.k] = nb;
+  }
+  L.b = nb;
+  __syncwarp();
+}
+
+// Buffers of chain k other than the active one: a parked object whose turn has come (sets the owner) / an empty
+// buffer / a suspended run that may go on (suspended before this round).  -1: none.  Uniform over the warp.
+__device__ __forceinline__ int find_turn_buf(const Sched* sc, int k) {
+  for (int b = k * kBufsPerChain; b < (k + 1) * kBufsPerChain; ++b)
+    if (sc->bkind[b] == 1 && (sc->owner == b || (sc->owner < 0 && sc->bseed[b] == sc->commit_idx))) return b;
+  return -1;
+}
+__device__ __forceinline__ int find_empty_buf(const Sched* sc, int k) {
+  for (int b = k * kBufsPerChain; b < (k + 1) * kBufsPerChain; ++b)
+    if (sc->bkind[b] == 0) return b;
+  return -1;
+}
+__device__ __forceinline__ int find_suspended_buf(const Sched* sc, int k, bool& too_early) {
+  too_early = false;
+  for (int b = k * kBufsPerChain; b < (k + 1) * kBufsPerChain; ++b)
+    if (sc->bkind[b] == 2) {
+      if ((int)sc->round > sc->bround[b]) return b;
+      too_early = true;
+    }
+  return -1;
+}
+
 // One chain's state machine up to its next collective action (the leader warp; serial transitions on
 // lane 0, queue pops / gating / scans as warp collectives).  Returns the action of this round.
-__device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sched* sc, bool pause) {
+__device__ __forceinline__ int chain_advance(const Ctx& c, LChain L, Sched* sc, bool pause) {
   const KParams& p = *c.p;
   const Geom& g = p.g;
   const CanvasDev& cv = p.cv;
-  const ChainDev& ch = p.ch[L.k];
   CanvasState* st = L.st;
   const unsigned full = 0xffffffffu;
   for (int guard = 0; guard < (1 << 20); ++guard) {
@@ -1560,6 +1621,17 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sche
       if (c.lane == 0) st->have_cur = 0;   // by the next launch every paste has landed in the canvas
       __syncwarp();
       return ACT_EXIT;
+    }
+    // A finished object parked in one of this chain's buffers is at the head of the line: the chain turns to it
+    // now (whatever it is growing is suspended and goes on after the commit).
+    if (st->seg_all && (phase == PH_FREE || phase == PH_POP || phase == PH_AFTER_CLEAR || phase == PH_FINISHED)) {
+      const int tb = find_turn_buf(sc, L.k);
+      if (tb >= 0) {
+        if (c.lane == 0) sc->owner = tb;
+        __syncwarp();
+        swap_buffers(c, L, sc, tb);
+        continue;
+      }
     }
     if (phase == PH_FORCE_STEP) {          // Canvas.update_at driven from the host: one step at st->cur
       if (c.lane == 0) {
@@ -1597,7 +1669,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sche
         // in-turn object (what Canvas.seed shows after segment_all), move that box to the snapshot array instead
         // of just clearing it
         int act = ACT_CLEAR;
-        if (st->seg_all && st->spec && sc->last_chain == L.k && !sc->last_in_snap && p.snap && !(p.job.debug & 8)) {
+        if (st->seg_all && st->spec && sc->last_chain == L.b && !sc->last_in_snap && p.snap && !(p.job.debug & 8)) {
           act = ACT_CLEAR_MOVE;
           if (c.lane == 0) {
             for (int q = 0; q < 3; ++q) {
@@ -1618,7 +1690,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sche
       // init_seed (inference.py:443-450) + reset_state (:291-310) + first queue item (:492-496)
       if (c.lane == 0) {
         if (st->reset_seed) {   // Canvas.reset_seed_per_segment (inference.py:486-490): seed and extents start over
-          ch.seed[cv_index(cv, st->start[0], st->start[1], st->start[2])] = cv.opt.init_activation;
+          p.ob[L.b].seed[cv_index(cv, st->start[0], st->start[1], st->start[2])] = cv.opt.init_activation;
           for (int q = 0; q < 3; ++q) {
             st->dirty_lo[q] = st->start[q];
             st->dirty_hi[q] = st->start[q] + 1;
@@ -1678,18 +1750,24 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sche
       if (st->have_cur && st->fin_round == (int)sc->round) return ACT_IDLE;
       if (c.lane == 0) st->have_cur = 0;
       __syncwarp();
-      if (sc->owner != L.k) {
+      if (sc->owner != L.b) {
         if (sc->owner < 0 && st->seed_index >= 0 && st->seed_index == sc->commit_idx) {
-          if (c.lane == 0) sc->owner = L.k;
+          if (c.lane == 0) sc->owner = L.b;
           __syncwarp();
         } else {
-          return ACT_IDLE;
+          // not its turn yet: park it and use the chain for another buffer (the suspended run, or a new object)
+          bool too_early;
+          int nb = find_suspended_buf(sc, L.k, too_early);
+          if (nb < 0 && !too_early) nb = find_empty_buf(sc, L.k);
+          if (nb < 0) return ACT_IDLE;
+          swap_buffers(c, L, sc, nb);
+          continue;
         }
       }
       if (st->spec) {
         int sz, sy, sx;
         const int ok = gate_seed(c, sc, st->seed_index, true, sz, sy, sx);   // the reference's gating, now, in order
-        const bool conflict = ok && (run_conflicts(c, L.k, st) || (p.job.debug & 1) ||
+        const bool conflict = ok && (run_conflicts(c, L.b, st) || (p.job.debug & 1) ||
                                      ((p.job.debug & 4) && sc->max_id != st->start_max_id));
         if (!ok || conflict) {
           if (c.lane == 0) {
@@ -1720,7 +1798,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sche
         FfnCounters zero{};
         st->ctr = zero;
         if (st->overflow) sc->overflow |= st->overflow;
-        sc->last_chain = L.k;        // Canvas.seed now shows this object
+        sc->last_chain = L.b;        // Canvas.seed now shows this object (buffer index)
         sc->last_in_snap = 0;
       }
       __syncwarp();
@@ -1733,7 +1811,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sche
         __syncwarp();
         continue;
       }
-      if (__ldcg(ch.seed + si) < cv.opt.move_threshold) {
+      if (__ldcg(p.ob[L.b].seed + si) < cv.opt.move_threshold) {
         if (c.lane == 0) {
           if (__ldcg(cv.seg + si) == 0) cv.seg[si] = -1;
           sc->ctr.invalid_weak++;
@@ -1817,8 +1895,19 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, const LChain& L, Sche
       continue;
     }
     if (phase == PH_FREE) {
-      assign_seed(c, L.k, st, sc);
-      if (st->phase == PH_FREE) return ACT_IDLE;   // nothing to start right now
+      advance_pointer(c, L, sc);                     // the head of the line first: an object whose turn it is runs here
+      if (st->phase != PH_FREE) continue;
+      {                                              // then a run this chain suspended
+        bool too_early;
+        const int nb = find_suspended_buf(sc, L.k, too_early);
+        if (nb >= 0) {
+          swap_buffers(c, L, sc, nb);
+          continue;
+        }
+        if (too_early) return ACT_IDLE;
+      }
+      lookahead(c, L, sc);                           // then an object ahead of its turn
+      if (st->phase == PH_FREE) return ACT_IDLE;     // nothing to start right now
       continue;
     }
     return ACT_EXIT;   // unknown phase
@@ -1837,7 +1926,7 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
   constexpr int kStateWords = (int)(sizeof(CanvasState) / 8);
   constexpr int kSchedWords = (int)(sizeof(Sched) / 8);
   static_assert(sizeof(CanvasState) <= 384 && sizeof(CanvasState) % 8 == 0, "state copy area");
-  static_assert(sizeof(Sched) <= 320 && sizeof(Sched) % 8 == 0, "scheduler copy area");
+  static_assert(sizeof(Sched) <= 512 && sizeof(Sched) % 8 == 0, "scheduler copy area");
   static_assert(kSchedWords <= 64 && 256 + 64 <= kThreads - kMaxChains, "scheduler copy uses threads 256..319");
   const unsigned par = (c.round & 1u) ^ 1u;   // parity the finished round was staged with
   const long long t_all = prof_now(c);
@@ -1849,8 +1938,9 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
   for (int i = c.tid; i < K * kStateWords; i += 256) {
     if (c.tid >= 256) break;
     const int k = i / kStateWords, w = i - k * kStateWords;
+    const int b = __ldcg(&p.sched->active[k]);   // the object buffer chain k works on
     reinterpret_cast<unsigned long long*>(chain_state(c, k))[w] =
-        __ldcg(reinterpret_cast<const unsigned long long*>(p.ch[k].st) + w);
+        __ldcg(reinterpret_cast<const unsigned long long*>(p.ob[b].st) + w);
   }
   if (c.tid >= 256 && c.tid - 256 < kSchedWords)
     reinterpret_cast<unsigned long long*>(sc)[c.tid - 256] = __ldcg(reinterpret_cast<const unsigned long long*>(p.sched) + (c.tid - 256));
@@ -1865,14 +1955,14 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
     for (int t = c.warp; t < K * 6; t += kThreads / 32) {
       const int k = t / 6, f = t - 6 * k;
       if (!((stepped >> k) & 1u)) continue;
-      LChain L{k, chain_state(c, k), par, c.s_misc[4 + k] != 0};
+      LChain L{k, sc->active[k], chain_state(c, k), par, c.s_misc[4 + k] != 0};
       face_argmax(c, L, f);
     }
   }
   __syncthreads();
   // ---- phase A.2: one warp per chain: queue pushes, bookkeeping, the pop that decides the next step
   if (c.warp < K && ((stepped >> c.warp) & 1u)) {
-    LChain L{c.warp, chain_state(c, c.warp), par, c.s_misc[4 + c.warp] != 0};
+    LChain L{c.warp, sc->active[c.warp], chain_state(c, c.warp), par, c.s_misc[4 + c.warp] != 0};
     if (L.st->phase == PH_AFTER_STEP) after_step(c, L);
   }
   if (c.tid == 0) prof_add(c, 12, prof_now(c) - t_pol);
@@ -1894,7 +1984,7 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
     for (int k = 0; k < kMaxChains; ++k) {
       acts[k] = ACT_EXIT;
       if (k < K) {
-        LChain L{k, chain_state(c, k), par, ((stepped >> k) & 1u) && c.s_misc[4 + k] != 0};
+        LChain L{k, sc->active[k], chain_state(c, k), par, ((stepped >> k) & 1u) && c.s_misc[4 + k] != 0};
         acts[k] = chain_advance(c, L, sc, pause);
         if (acts[k] != ACT_EXIT && acts[k] != ACT_IDLE) any = true;
         if (acts[k] == ACT_IDLE && c.lane == 0) {
@@ -1910,6 +2000,7 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
     if (p.job.mode == MODE_SEGMENT && s0->seg_all && !pause) {
       bool all_free = true;
       for (int k = 0; k < K; ++k) all_free = all_free && chain_state(c, k)->phase == PH_FREE;
+      for (int b = 0; b < K * kBufsPerChain; ++b) all_free = all_free && sc->bkind[b] != 1 && sc->bkind[b] != 2;
       if (all_free && sc->commit_idx >= p.job.n_seeds && sc->owner < 0) {
         if (c.lane == 0) {
           sc->all_done = 1;
@@ -1922,6 +2013,8 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
         bool waiting = false;
         for (int k = 0; k < K; ++k)
           waiting = waiting || (chain_state(c, k)->phase == PH_FINISHED && chain_state(c, k)->fin_round + 1 >= (int)sc->round);
+        for (int b = 0; b < K * kBufsPerChain; ++b)   // a run suspended this round goes on next round
+          waiting = waiting || (sc->bkind[b] == 2 && sc->bround[b] + 1 >= (int)sc->round);
         any = waiting;
       }
     }
@@ -1943,6 +2036,7 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
           p.ctl->pos[k][0] = s->cur[0];
           p.ctl->pos[k][1] = s->cur[1];
           p.ctl->pos[k][2] = s->cur[2];
+          p.ctl->buf[k] = sc->active[k];
         }
       }
     }
@@ -1952,7 +2046,7 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
   for (int i = c.tid; i < K * kStateWords; i += 256) {
     if (c.tid >= 256) break;
     const int k = i / kStateWords, w = i - k * kStateWords;
-    reinterpret_cast<unsigned long long*>(p.ch[k].st)[w] = reinterpret_cast<const unsigned long long*>(chain_state(c, k))[w];
+    reinterpret_cast<unsigned long long*>(p.ob[sc->active[k]].st)[w] = reinterpret_cast<const unsigned long long*>(chain_state(c, k))[w];
   }
   if (c.tid >= 256 && c.tid - 256 < kSchedWords)
     reinterpret_cast<unsigned long long*>(p.sched)[c.tid - 256] = reinterpret_cast<const unsigned long long*>(sc)[c.tid - 256];
@@ -1974,9 +2068,9 @@ __device__ __forceinline__ void load3(const int* src, int (&dst)[3]) {
   dst[2] = __ldcg(src + 2);
 }
 
-__device__ __forceinline__ void clear_dirty(Ctx& c, int k) {   // NumpyArray.clear restricted to the touched box
+__device__ __forceinline__ void clear_dirty(Ctx& c, int b) {   // NumpyArray.clear restricted to the touched box
   const KParams& p = *c.p;
-  const CanvasState* st = p.ch[k].st;
+  const CanvasState* st = p.ob[b].st;
   int dlo[3], dhi[3];
   load3(st->dirty_lo, dlo);
   load3(st->dirty_hi, dhi);
@@ -1988,17 +2082,17 @@ __device__ __forceinline__ void clear_dirty(Ctx& c, int k) {   // NumpyArray.cle
   const float nanv = CUDART_NAN_F;
   for (long long l = (long long)c.cta * (kThreads / 32) + c.warp; l < lines; l += (long long)c.G * (kThreads / 32)) {
     const int z = lo[0] + (int)(l / ny), y = lo[1] + (int)(l % ny);
-    float* row = p.ch[k].seed + cv_index(p.cv, z, y, lo[2]);
+    float* row = p.ob[b].seed + cv_index(p.cv, z, y, lo[2]);
     for (int x = c.lane; x < nx; x += 32) row[x] = nanv;
   }
 }
 
 // Moves chain k's touched box into the snapshot array (and clears it), after clearing what the snapshot held
 // before.  The two passes write disjoint voxels of the snapshot array, so no barrier is needed between them.
-__device__ __forceinline__ void clear_move(Ctx& c, int k) {
+__device__ __forceinline__ void clear_move(Ctx& c, int b) {
   const KParams& p = *c.p;
   const Sched* sc = p.sched;
-  const CanvasState* st = p.ch[k].st;
+  const CanvasState* st = p.ob[b].st;
   int olo[3], ohi[3], dlo[3], dhi[3];
   load3(sc->snap_old_lo, olo);
   load3(sc->snap_old_hi, ohi);
@@ -2030,17 +2124,17 @@ __device__ __forceinline__ void clear_move(Ctx& c, int k) {
         const int z = lo[0] + (int)(l / ny), y = lo[1] + (int)(l % ny);
         const size_t base = cv_index(p.cv, z, y, lo[2]);
         for (int x = c.lane; x < nx; x += 32) {
-          p.snap[base + x] = __ldcg(p.ch[k].seed + base + x);
-          p.ch[k].seed[base + x] = nanv;
+          p.snap[base + x] = __ldcg(p.ob[b].seed + base + x);
+          p.ob[b].seed[base + x] = nanv;
         }
       }
     }
   }
 }
 
-__device__ __forceinline__ void commit_count(Ctx& c, int k) {   // inference.py:624-636
+__device__ __forceinline__ void commit_count(Ctx& c, int b) {   // inference.py:624-636
   const KParams& p = *c.p;
-  CanvasState* st = p.ch[k].st;
+  CanvasState* st = p.ob[b].st;
   int lo[3], hi[3];
   load3(st->box_lo, lo);
   load3(st->box_hi, hi);
@@ -2051,7 +2145,7 @@ __device__ __forceinline__ void commit_count(Ctx& c, int k) {   // inference.py:
     const int z = lo[0] + (int)(l / ny), y = lo[1] + (int)(l % ny);
     const size_t base = cv_index(p.cv, z, y, lo[2]);
     for (int x = c.lane; x < nx; x += 32) {
-      const float s = __ldcg(p.ch[k].seed + base + x);
+      const float s = __ldcg(p.ob[b].seed + base + x);
       if (!(s >= p.cv.opt.segment_threshold)) continue;
       ++raw;
       const int sg = __ldcg(p.cv.seg + base + x);
@@ -2075,9 +2169,9 @@ __device__ __forceinline__ void commit_count(Ctx& c, int k) {   // inference.py:
   }
 }
 
-__device__ __forceinline__ void commit_write(Ctx& c, int k) {   // inference.py:653-658
+__device__ __forceinline__ void commit_write(Ctx& c, int b) {   // inference.py:653-658
   const KParams& p = *c.p;
-  const CanvasState* st = p.ch[k].st;
+  const CanvasState* st = p.ob[b].st;
   int lo[3], hi[3];
   load3(st->box_lo, lo);
   load3(st->box_hi, hi);
@@ -2088,7 +2182,7 @@ __device__ __forceinline__ void commit_write(Ctx& c, int k) {   // inference.py:
     const int z = lo[0] + (int)(l / ny), y = lo[1] + (int)(l % ny);
     const size_t base = cv_index(p.cv, z, y, lo[2]);
     for (int x = c.lane; x < nx; x += 32) {
-      const float s = __ldcg(p.ch[k].seed + base + x);
+      const float s = __ldcg(p.ob[b].seed + base + x);
       if (!(s >= p.cv.opt.segment_threshold)) continue;
       if (__ldcg(p.cv.seg + base + x) > 0) continue;
       p.cv.seg[base + x] = sid;
@@ -2147,7 +2241,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   c.s_tmem = reinterpret_cast<uint32_t*>(c.mb_sig + kMaxChains);
   c.load_cnt = c.mma_cnt = c.epi_cnt = 0;
   c.s_misc = reinterpret_cast<int*>(smem_raw + L.bars + 160);      // 8 + 3 * 32 ints
-  c.s_round = reinterpret_cast<int*>(smem_raw + L.bars + 640);     // 2 * kMaxChains * 4 ints
+  c.s_round = reinterpret_cast<int*>(smem_raw + L.bars + 640);     // 2 * kMaxChains * 8 ints
   c.s_xchg = reinterpret_cast<float*>(smem_raw + L.bars + 1024);
   c.s_dot = c.s_xchg + 2 * 2 * 4 * 2 * 16;
   c.s_state = reinterpret_cast<CanvasState*>(smem_raw + L.bars + 4096);
@@ -2167,7 +2261,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   for (int i = c.tid; i < p.g.nconv * 32; i += kThreads) c.s_bias[i] = p.w.bias[i];
   if (c.tid < 32) c.s_bias[p.g.nconv * 32 + c.tid] = p.w.w_lom[c.tid];
   if (c.tid == 0) c.s_bias[p.g.nconv * 32 + 32] = p.w.b_lom;
-  if (c.tid < 2 * kMaxChains * 4) c.s_round[c.tid] = 0;
+  if (c.tid < 2 * kMaxChains * 8) c.s_round[c.tid] = 0;
   if (tc) {
     if (c.tid == 0) {
       sm100::mbar_init(&c.mb_w[0], 1);
@@ -2208,13 +2302,13 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
       unsigned mask = 0;
       for (int k = 0; k < K; ++k)
         if (b0 + k < p.job.batch) {
-          stage_fov(c, k, 0, 0, 0, b0 + k);
+          stage_fov(c, k, 0, 0, 0, 0, b0 + k);
           mask |= 1u << k;
         }
       run_layers(c, mask);
       grid_barrier(c);
       for (int k = 0; k < K; ++k)
-        if ((mask >> k) & 1u) tail_paste(c, k, c.round & 1u, 0, 0, 0, b0 + k, false);
+        if ((mask >> k) & 1u) tail_paste(c, k, 0, c.round & 1u, 0, 0, 0, b0 + k, false);
       ++c.round;
       if (c.tid == 0) c.s_misc[7] = sm100::ld_volatile_s32(p.ws.abort_flag);   // one reader: no divergent exit
       __syncthreads();
@@ -2230,16 +2324,17 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
       const long long t_paste = prof_now(c);
       const unsigned ppar = (c.round & 1u) ^ 1u;
       for (int k = 0; k < K; ++k) {
-        int* prev = c.s_round + 4 * (kMaxChains + k);   // read by the next stage of this chain (two CTA barriers from here)
+        int* prev = c.s_round + 8 * (kMaxChains + k);   // read by the next stage of this chain (two CTA barriers from here)
         if ((stepped >> k) & 1u) {
-          const int* cur = c.s_round + 4 * k;
+          const int* cur = c.s_round + 8 * k;
           const bool disco = disco_active(p, k, ppar);
-          tail_paste(c, k, ppar, cur[1], cur[2], cur[3], 0, disco);
+          tail_paste(c, k, cur[4], ppar, cur[1], cur[2], cur[3], 0, disco);
           if (c.tid == 0) {
             prev[0] = 1 | (disco ? 2 : 0);
             prev[1] = cur[1];
             prev[2] = cur[2];
             prev[3] = cur[3];
+            prev[4] = cur[4];
           }
         } else if (c.tid == 0) {
           prev[0] = 0;
@@ -2254,34 +2349,35 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
       __syncthreads();
       const int abort_now = c.s_misc[7];
       if (c.tid < K) {
-        int* cur = c.s_round + 4 * c.tid;
+        int* cur = c.s_round + 8 * c.tid;
         cur[0] = sm100::ld_volatile_s32(&p.ctl->action[c.tid]);
         cur[1] = sm100::ld_volatile_s32(&p.ctl->pos[c.tid][0]);
         cur[2] = sm100::ld_volatile_s32(&p.ctl->pos[c.tid][1]);
         cur[3] = sm100::ld_volatile_s32(&p.ctl->pos[c.tid][2]);
+        cur[4] = sm100::ld_volatile_s32(&p.ctl->buf[c.tid]);
       }
       __syncthreads();
       if (abort_now != 0) break;
       bool all_exit = true;
-      for (int k = 0; k < K; ++k) all_exit = all_exit && c.s_round[4 * k] == ACT_EXIT;
+      for (int k = 0; k < K; ++k) all_exit = all_exit && c.s_round[8 * k] == ACT_EXIT;
       if (all_exit) break;
       // ---- collectives of this round, then the FoV steps
       long long t0 = prof_now(c);
       unsigned mask = 0;
       for (int k = 0; k < K; ++k) {
-        const int* cur = c.s_round + 4 * k;
-        const int action = cur[0];
+        const int* cur = c.s_round + 8 * k;
+        const int action = cur[0], b = cur[4];
         if (action == ACT_STEP) {
-          stage_fov(c, k, cur[1], cur[2], cur[3], 0);
+          stage_fov(c, k, b, cur[1], cur[2], cur[3], 0);
           mask |= 1u << k;
         } else if (action == ACT_CLEAR) {
-          clear_dirty(c, k);
+          clear_dirty(c, b);
         } else if (action == ACT_CLEAR_MOVE) {
-          clear_move(c, k);
+          clear_move(c, b);
         } else if (action == ACT_COUNT) {
-          commit_count(c, k);
+          commit_count(c, b);
         } else if (action == ACT_WRITE) {
-          commit_write(c, k);
+          commit_write(c, b);
         }
       }
       if (c.tid == 0) prof_add(c, 6, prof_now(c) - t0);

@@ -456,6 +456,12 @@ def run_multi(args, rank, local_rank, world):
     dist.barrier()
     torch.cuda.synchronize()
 
+  # warm-up: NCCL connections (the first collective sets them up), allocator, kernels
+  wt = torch.zeros(1 << 20, dtype=torch.int32, device=dev)
+  dist.all_reduce(wt)
+  dist.gather(wt, [torch.empty_like(wt) for _ in range(world)] if rank == 0 else None, dst=0)
+  D.gather_max_ids(0, device=dev)
+  torch.cuda.synchronize()
   warm = eng.DeviceCanvas(engine, vols[0].numpy()[:160, :160, :160].copy(), opts, 128.0, 33.0)
   wseeds, _ = device_seeds(warm)
   warm.segment_all(wseeds[:max(8 * max(args.warmup, 3), 24)])

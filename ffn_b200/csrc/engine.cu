@@ -948,6 +948,10 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   c->last_spec[6] = sc.idle_wait;
   c->last_spec[7] = K;
   if (counters_out) *counters_out = st.ctr;
+  // single-object calls (segment_at, update_at) work on buffer 0 through chain 0
+  for (int k = 0; k < kMaxChains; ++k) sc.active[k] = kBufsPerChain * k;
+  sc.owner = -1;
+  if (cudaMemcpy(c->d_sched, &sc, sizeof(Sched), cudaMemcpyHostToDevice) != cudaSuccess) return fail("scheduler state upload failed");
   if (push_state(c)) return 1;
   return rc;
 }

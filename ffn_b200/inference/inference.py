@@ -436,6 +436,13 @@ class Canvas:
     with timer_counter(self.counters, 'segment_all'):
       with timer_counter(self.counters, 'seed-policy'):
         coords = self.seed_policy.remaining()
+      if (partial_segment_iters or getattr(self, '_resume_pending', False)) and coords.shape[0]:
+        # A checkpoint taken inside an object stores the seed policy one step back (inference.py:745-747), so the
+        # first remaining seed IS the restored in-flight object: the device finishes that object first
+        # (ffn_canvas_set_resume), the list continues behind it.
+        coords = coords[1:]
+        self.seed_policy.idx += 1
+      self._resume_pending = False
       self.counters['seed-policy-calls'].IncrementBy(max(coords.shape[0] - 1, 0))
       first = True
       pos = 0
@@ -520,6 +527,7 @@ class Canvas:
     with self._exec_client.engine_lock:
       self._dev.set_max_id(self._max_id)
     self._last_counters = self._dev.counters()
+    self._resume_pending = bool(partial)
     if partial:
       # the next segment_all (or segment_at(..., partial_segment_iters=...)) first finishes this object
       with self._exec_client.engine_lock:

@@ -296,13 +296,40 @@ def load_segmentation(segmentation_dir, corner, allow_cpoint=False, threshold=No
       seg = data['segmentation']
     else:
       raise ValueError('FFN NPZ file %s does not contain valid segmentation.' % target_path)
-    origins = data['origins'].item()
+    origins = _load_origins(data, target_path)
     output = seg.astype(np.uint64)
     if threshold is not None:
       threshold_segmentation(segmentation_dir, corner, output, threshold)
     if min_size:
       segmentation.clear_dust(output, min_size)
   return output, origins
+
+
+def _load_origins(data, path):
+  """`origins` of a seg-*.npz.  Files written by the original (Python 2, internal) code base — e.g. the reference's
+  shipped results/fib25/sample-training2.npz — pickle OriginInfo under its old module path with py2 strings: they
+  are read with encoding='latin1' and the old module name mapped onto this package's OriginInfo."""
+  try:
+    return data['origins'].item()
+  except (UnicodeDecodeError, ModuleNotFoundError, ImportError, AttributeError):
+    pass
+  import sys
+  import types
+  legacy = 'google3.research.neuromancer.segmentation.ffn.storage'
+  added = []
+  parts = legacy.split('.')
+  for i in range(1, len(parts) + 1):
+    name = '.'.join(parts[:i])
+    if name not in sys.modules:
+      sys.modules[name] = types.ModuleType(name)
+      added.append(name)
+  sys.modules[legacy].OriginInfo = OriginInfo
+  try:
+    with np.load(path, allow_pickle=True, encoding='latin1') as again:
+      return again['origins'].item()
+  finally:
+    for name in added:
+      sys.modules.pop(name, None)
 
 
 def copy_file(src, dst):

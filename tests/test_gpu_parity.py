@@ -484,6 +484,55 @@ def test_canvas_checkpoint_roundtrip(tmp_path, golden_dir, g64):
   exe.close()
 
 
+def test_segment_all_resumes_mid_object_checkpoint(tmp_path, golden_dir, g64):
+  """A checkpoint taken INSIDE an object (the reference saves the seed policy one step back, inference.py:745-747):
+  restore + segment_all finishes that object and goes on with the NEXT seed — the in-flight seed is not run a
+  second time — and the result equals the uninterrupted reference run."""
+  from ffn.inference import executor, inference, inference_pb2, inference_utils, seed as seed_mod
+  from ffn.training.models import convstack_3d
+  from ffn_b200 import _lib
+  model = convstack_3d.ConvStack3DFFNModel(fov_size=[33, 33, 33], deltas=[8, 8, 8], depth=12)
+  exe = executor.B200Executor(executor.ExecutorInterface(), model, inference_utils.Counters(),
+                              checkpoint_path=os.path.join(golden_dir, 'fib25_convstack.npz'),
+                              compute_mode=_lib.COMPUTE_FP16X2_TC)
+  opts = inference_pb2.InferenceOptions(init_activation=0.95, pad_value=0.05, move_threshold=0.9,
+                                        segment_threshold=0.6, min_segment_size=1000)
+  opts.min_boundary_dist.x = opts.min_boundary_dist.y = opts.min_boundary_dist.z = 1
+  seeds = np.asarray(g64['seeds'])
+
+  class ListPolicy(seed_mod.BaseSeedPolicy):
+    def init_coords(self):
+      self.coords = seeds.copy()
+
+  def make():
+    return inference.Canvas(model.info, exe.get_client(inference_utils.Counters()), g64['volume'], opts,
+                            keep_probability_maps=True, image_mean=128, image_stddev=33)
+  # an object of the golden run with enough steps to stop inside: the seeds in front of it are processed normally
+  row = next(r for r in g64['origins'] if int(r[4]) >= 15)
+  k = next(i for i, sd in enumerate(seeds.tolist()) if tuple(sd) == tuple(int(v) for v in row[1:4]))
+
+  class HeadPolicy(seed_mod.BaseSeedPolicy):
+    def init_coords(self):
+      self.coords = seeds[:k].copy()
+  a = make()
+  a.segment_all(seed_policy=HeadPolicy)
+  a.seed_policy = ListPolicy(a)
+  a.seed_policy.init_coords()
+  a.seed_policy.idx = k + 1                       # the policy has handed out seed k, which is now in flight
+  n = a.segment_at(tuple(int(v) for v in seeds[k]), max_steps=7)
+  assert n == 7
+  path = str(tmp_path / 'mid.cpoint')
+  a.save_checkpoint(path, partial_segment_iters=n)
+  b = make()
+  assert b.restore_checkpoint(path) == 7
+  b.segment_all(seed_policy=ListPolicy)
+  np.testing.assert_array_equal(np.asarray(b.segmentation), g64['segmentation'])
+  assert sorted((v.start_zyx, v.iters) for v in b.origins.values()) == sorted(
+      (tuple(int(x) for x in row[1:4]), int(row[4])) for row in g64['origins'])
+  assert b.counters['segment_at-loop-calls'].value >= 1
+  exe.close()
+
+
 def test_concurrent_canvases_batch_size_two(golden_dir, g64):
   """InferenceRequest.batch_size semantics: two canvases served concurrently (two engines, half the
   SMs each, one host thread per canvas) produce exactly what the whole-GPU engine produces."""

@@ -388,3 +388,22 @@ def test_bench_traffic_comes_from_committed_ncu_capture():
   t = bench.ncu_dram_traffic()
   assert t is not None and t['steps_per_launch'] >= 16
   assert 1e5 < t['bytes_per_step'] < 431244 * 2      # at most about the compulsory 431 KB/step (u8 image, L2 reuse)
+
+
+def test_load_segmentation_reads_the_reference_shipped_result(tmp_path):
+  """results/fib25/sample-training2.npz of the reference checkout: a Python-2 pickle of OriginInfo under the
+  original module path — storage.load_segmentation reads it (latin1 + module mapping).  Skipped where the
+  reference checkout is absent (the GPU box)."""
+  import shutil
+  import pytest
+  from ffn.inference import storage
+  src = '/root/reference/results/fib25/sample-training2.npz'
+  if not os.path.exists(src):
+    pytest.skip('reference checkout not present')
+  d = tmp_path / '0' / '0'
+  d.mkdir(parents=True)
+  shutil.copy(src, str(d / 'seg-0_0_0.npz'))
+  seg, origins = storage.load_segmentation(str(tmp_path), (0, 0, 0))
+  assert seg.shape == (250, 250, 250) and seg.dtype == np.uint64
+  assert len(origins) == 254 and origins[1].iters == 1884
+  assert all(seg[tuple(int(v) for v in o.start_zyx)] == sid for sid, o in origins.items())   # every origin carries its own id

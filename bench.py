@@ -12,8 +12,8 @@ Workloads (BASELINE.json):
           fov 33^3, deltas 8, FIB-25 weights, on the synthetic stand-in for training_sample2 (Voronoi phantom,
           seed 0).  ONE timed pass = the whole canvas (~25.6 k FoV steps, ~585 objects): a flood
           fill has no meaningful K-step prefix (seed policy, object commits and the last objects are part of
-          the metric), so --steps only caps the seed list when it is small (profiler runs: --steps < 1000 means
-          "first K seeds") and is otherwise ignored; `steps` in the output line is the number of FoV steps done.
+          the metric), so --steps is IGNORED for sizing (profiler runs cap the seed list with --max-seeds);
+          `steps` in the output line is the number of FoV steps done.
           `value` = FoV steps / wall clock of segment_all (device PolicyPeaks included) with the volume resident
           in HBM; `e2e` = the same metric through Runner.run (volume file -> pinned H2D -> segment_all -> D2H ->
           seg-*.npz / .prob written), which is what a user of run_inference.py gets.
@@ -70,7 +70,7 @@ def load_weights():
 
 def make_volume(shape, seed):
   from ffn_b200.synthetic import voronoi_phantom
-  cache = os.path.join(REPO, 'gpurun_out', '.bench_vol_%d_%d.npy' % (shape[0], seed))
+  cache = os.path.join(os.environ.get('FFN_BENCH_CACHE', '/tmp/ffn_bench_cache'), 'vol_%d_%d.npy' % (shape[0], seed))
   if os.path.exists(cache):
     return np.load(cache)
   vol = voronoi_phantom(shape, seed)
@@ -321,7 +321,7 @@ def run_n1(args, rank, local_rank):
   pinned = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
   pinned.numpy()[...] = vol
   opts = eng.make_options()
-  seed_cap = args.steps if 0 < args.steps < 1000 else 0
+  seed_cap = args.max_seeds
 
   # ---- warm-up: W short flood fills on a scratch canvas (allocator, instruction cache, weights in L2)
   warm = eng.DeviceCanvas(engine, pinned.numpy(), opts, 128.0, 33.0)
@@ -385,7 +385,7 @@ def run_n1(args, rank, local_rank):
       'config': {
           'workload': WORKLOAD_N1,
           'weights': wdesc, 'accumulate': 'f32', 'timed_pass': 'one whole segment_all (device PolicyPeaks + flood fill + commits); '
-          '--steps is ignored unless < 1000 (then: first K seeds)',
+          '--steps is ignored (a flood fill has no meaningful K-step prefix)' + (' — capped at %d seeds' % seed_cap if seed_cap else ''),
           'l2': 'canvas state (image u8 + 4 seed f32 arrays + segmentation i32 + qprob u8 = 330 MB) exceeds L2; '
                 'the ~36 MB activation working set of three chains is L2-resident by design',
           'published_reference_p100': {'fov_steps_per_sec': 65.5, 'voxels_per_sec': 35216},
@@ -552,6 +552,7 @@ def main():
   ap.add_argument('--compute', default='fp16', choices=['fp16', 'fp32', 'x2'])
   ap.add_argument('--chains', type=int, default=0, help='objects in flight per GPU (1..3, 0 = default 3)')
   ap.add_argument('--slab', type=int, default=0, help='N > 1: slab edge instead of 512 (tests)')
+  ap.add_argument('--max-seeds', type=int, default=0, help='N = 1: only the first K PolicyPeaks seeds (profiler runs)')
   ap.add_argument('--cpu-baseline-steps', type=int, default=24)
   ap.add_argument('--skip-extras', action='store_true', help='no single-seed / predict / cpu_baseline legs (profiler runs)')
   ap.add_argument('--skip-e2e', action='store_true', help='no Runner.run leg (profiler runs; the line then repeats the device-resident value)')

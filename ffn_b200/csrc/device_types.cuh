@@ -28,7 +28,7 @@ constexpr int kFeat = 32;         // feature maps of every hidden layer (UMMA N)
 constexpr int kGroupTiles = 3;    // accumulator slots in TMEM (the residual stream starts behind them)
 constexpr int kMaxConv = 32;      // 2 * depth limit
 constexpr int kMaxChains = 3;     // flood-fill chains (execution slots) time-multiplexed over the SMs of one kernel
-constexpr int kBufsPerChain = 4;  // object buffers per chain: finished objects that wait for their turn to commit are parked
+constexpr int kBufsPerChain = 8;  // object buffers per chain: finished objects that wait for their turn to commit are parked
 constexpr int kMaxBufs = kMaxChains * kBufsPerChain;
 constexpr int kSplitShift = 10;   // FFN_COMPUTE_FP16X2_TC: weights are split as w * 2^10 = hi + lo (keeps lo a normal fp16
                                   // number for |w| down to ~1e-4); the epilogue scales the accumulators back (exact)
@@ -283,7 +283,7 @@ __host__ __device__ inline SmemLayout smem_layout(const Geom& g) {
   const int act_bytes = kActStages * 3 * 4 * seg_rows * 16;
   s.bias = s.act + act_bytes;
   s.bars = s.bias + (kMaxConv + 1) * 32 * 4 + 16;
-  s.total = s.bars + 4096 + kMaxChains * 384 + 512;   // barriers/misc | prof | epilogue exchange + conv_lom dots | leader's chain-state / scheduler copies
+  s.total = s.bars + 4096 + kMaxChains * 352 + 704;   // barriers/misc | prof | epilogue exchange + conv_lom dots | leader's chain-state / scheduler copies
   return s;
 }
 

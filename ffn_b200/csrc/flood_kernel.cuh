@@ -84,7 +84,7 @@ __device__ __forceinline__ void ev_add(Ctx& c, int k, unsigned n) {
   else c.ev2 += n;
 }
 __device__ __forceinline__ CanvasState* chain_state(const Ctx& c, int k) {
-  return reinterpret_cast<CanvasState*>(reinterpret_cast<unsigned char*>(c.s_state) + k * 384);
+  return reinterpret_cast<CanvasState*>(reinterpret_cast<unsigned char*>(c.s_state) + k * 352);
 }
 
 __device__ __forceinline__ bool aborted(const Ctx& c) {
@@ -1747,7 +1747,21 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, LChain L, Sched* sc, 
     if (phase == PH_FINISHED) {
       // The last step's paste lands during the round the object finished in; and labels are committed in
       // seed order, so an object that ran ahead waits until it is at the head of the line.
-      if (st->have_cur && st->fin_round == (int)sc->round) return ACT_IDLE;
+      if (st->have_cur && st->fin_round == (int)sc->round) {
+        // nothing can be decided about this object before the next round; if it is not at the head of the line
+        // the chain need not wait with it: park it at once and go on in another buffer
+        const bool at_head = sc->owner == L.b || (sc->owner < 0 && st->seed_index >= 0 && st->seed_index == sc->commit_idx);
+        if (!at_head) {
+          bool too_early;
+          int nb = find_suspended_buf(sc, L.k, too_early);
+          if (nb < 0 && !too_early) nb = find_empty_buf(sc, L.k);
+          if (nb >= 0) {
+            swap_buffers(c, L, sc, nb);
+            continue;
+          }
+        }
+        return ACT_IDLE;
+      }
       if (c.lane == 0) st->have_cur = 0;
       __syncwarp();
       if (sc->owner != L.b) {
@@ -1925,9 +1939,9 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
   Sched* sc = c.s_sched;
   constexpr int kStateWords = (int)(sizeof(CanvasState) / 8);
   constexpr int kSchedWords = (int)(sizeof(Sched) / 8);
-  static_assert(sizeof(CanvasState) <= 384 && sizeof(CanvasState) % 8 == 0, "state copy area");
-  static_assert(sizeof(Sched) <= 512 && sizeof(Sched) % 8 == 0, "scheduler copy area");
-  static_assert(kSchedWords <= 64 && 256 + 64 <= kThreads - kMaxChains, "scheduler copy uses threads 256..319");
+  static_assert(sizeof(CanvasState) <= 352 && sizeof(CanvasState) % 8 == 0, "state copy area");
+  static_assert(sizeof(Sched) <= 704 && sizeof(Sched) % 8 == 0, "scheduler copy area");
+  static_assert(256 + kSchedWords <= kThreads - kMaxChains, "scheduler copy uses threads 256 ..");
   const unsigned par = (c.round & 1u) ^ 1u;   // parity the finished round was staged with
   const long long t_all = prof_now(c);
   // Watchdog: one launch covers at most 2^15 FoV steps (a few seconds).  A launch that is still going after
@@ -2013,8 +2027,8 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
         bool waiting = false;
         for (int k = 0; k < K; ++k)
           waiting = waiting || (chain_state(c, k)->phase == PH_FINISHED && chain_state(c, k)->fin_round + 1 >= (int)sc->round);
-        for (int b = 0; b < K * kBufsPerChain; ++b)   // a run suspended this round goes on next round
-          waiting = waiting || (sc->bkind[b] == 2 && sc->bround[b] + 1 >= (int)sc->round);
+        for (int b = 0; b < K * kBufsPerChain; ++b)   // an object parked / a run suspended this round goes on next round
+          waiting = waiting || ((sc->bkind[b] == 1 || sc->bkind[b] == 2) && sc->bround[b] + 1 >= (int)sc->round);
         any = waiting;
       }
     }
@@ -2245,7 +2259,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   c.s_xchg = reinterpret_cast<float*>(smem_raw + L.bars + 1024);
   c.s_dot = c.s_xchg + 2 * 2 * 4 * 2 * 16;
   c.s_state = reinterpret_cast<CanvasState*>(smem_raw + L.bars + 4096);
-  c.s_sched = reinterpret_cast<Sched*>(smem_raw + L.bars + 4096 + kMaxChains * 384);
+  c.s_sched = reinterpret_cast<Sched*>(smem_raw + L.bars + 4096 + kMaxChains * 352);
   static_assert((2 + 2 * kActStages + 2 * kAccSlots + kMaxChains) * 8 + 8 <= 160, "mbarrier area");
   c.prof = nullptr;
   if (FFN_PROFILE && p.ws.prof && (c.cta == 0 || c.cta == c.G - 1)) {

@@ -179,9 +179,11 @@ class DeviceCanvas:
     _lib.check(self._lib.ffn_canvas_set_mask(self._h, which, _lib.ptr(m)))
 
   # -- hot loop ------------------------------------------------------------------------------
-  def segment_at(self, start_zyx, reset: bool = True, max_steps: int = 0) -> _lib.SegStats:
+  def segment_at(self, start_zyx, reset: bool = True, max_steps: int = 0, keep_seed: bool = False) -> _lib.SegStats:
+    """reset=False resumes the object in flight; keep_seed=True starts a new object WITHOUT init_seed / extent
+    reset (Canvas.reset_seed_per_segment == False, inference.py:486-490)."""
     st = _lib.SegStats()
-    _lib.check(self._lib.ffn_canvas_segment_at(self._h, _lib.i3(start_zyx), 1 if reset else 0,
+    _lib.check(self._lib.ffn_canvas_segment_at(self._h, _lib.i3(start_zyx), (2 if keep_seed else 1) if reset else 0,
                                                 int(max_steps), C.byref(st)))
     return st
 

@@ -412,7 +412,7 @@ class Canvas:
       with self._exec_client.engine_lock:
         if not partial_segment_iters:
           self.reset_state(start_pos, reset_extents=self.reset_seed_per_segment)
-          st = self._dev.segment_at(start_pos, reset=True, max_steps=max_steps)
+          st = self._dev.segment_at(start_pos, reset=True, max_steps=max_steps, keep_seed=not self.reset_seed_per_segment)
         else:
           st = self._dev.segment_at(start_pos, reset=False, max_steps=max_steps)
       self._min_pos = np.array(list(st.min_pos))

@@ -128,26 +128,44 @@ class PolicyPeaks(BaseSeedPolicy):
       with self.canvas._exec_client.engine_lock:         # pylint: disable=protected-access
         self.coords = dev.seed_peaks(self.canvas.voxel_size_zyx, noise).astype(np.int64).reshape(-1, 3)
       return
-    image = np.asarray(self.canvas.image).astype(np.float32)
-    edges = ndimage.generic_gradient_magnitude(image, ndimage.sobel)
-    sigma = 49.0 / 6.0
-    thresh_image = np.zeros(edges.shape, dtype=np.float32)
-    ndimage.gaussian_filter(edges, sigma, output=thresh_image, mode='reflect')
-    filt_edges = edges > thresh_image
-    del edges, thresh_image
-    mask = self.get_exclusion_mask()
-    if self.canvas.restrictor is not None:
-      if self.canvas.restrictor.mask is not None:
-        filt_edges[self.canvas.restrictor.mask] = 1
-      if self.canvas.restrictor.seed_mask is not None:
-        filt_edges[self.canvas.restrictor.seed_mask] = 1
-    if np.all(filt_edges == 1):
+    # host path (shift masks / no device canvas): the same stages with scipy
+    blocked = self._blocked_voxels()
+    is_edge = _edge_mask(np.asarray(self.canvas.image), blocked)
+    if is_edge.all():
       return
-    dt = ndimage.distance_transform_edt(1 - filt_edges, sampling=self.canvas.voxel_size_zyx).astype(np.float32)
-    dt[mask] = -1
-    dt[~np.isfinite(dt)] = -1
-    idxs = _find_peaks(dt, min_distance=3, threshold_abs=0, threshold_rel=0)
-    self.coords = np.array(sorted((int(z), int(y), int(x)) for z, y, x in idxs)).reshape(-1, 3)
+    dist = _distance_map(is_edge, self.canvas.voxel_size_zyx, self.get_exclusion_mask())
+    peaks = _find_peaks(dist, min_distance=3, threshold_abs=0, threshold_rel=0)
+    self.coords = np.array(sorted(map(tuple, peaks.astype(int).tolist()))).reshape(-1, 3)
+
+  def _blocked_voxels(self):
+    """Voxels the restrictor forbids (movement mask | seed mask), or None."""
+    r = self.canvas.restrictor
+    parts = [m for m in (getattr(r, 'mask', None), getattr(r, 'seed_mask', None)) if m is not None]
+    if not parts:
+      return None
+    out = np.zeros(self.canvas.shape, dtype=bool)
+    for m in parts:
+      out |= np.asarray(m).astype(bool)
+    return out
+
+
+def _edge_mask(image, blocked):
+  """Sobel gradient magnitude above its local (gaussian, sigma 49/6) average; blocked voxels count as edges so that
+  large masked regions do not distort the distance transform (seed.py:152-173)."""
+  grad = ndimage.generic_gradient_magnitude(image.astype(np.float32), ndimage.sobel)
+  local = np.empty_like(grad)
+  ndimage.gaussian_filter(grad, 49.0 / 6.0, output=local, mode='reflect')
+  out = grad > local
+  if blocked is not None:
+    out |= blocked
+  return out
+
+
+def _distance_map(is_edge, voxel_size_zyx, excluded):
+  """Distance (physical units) to the nearest edge, -1 where seeds are not allowed (seed.py:183-188)."""
+  dist = ndimage.distance_transform_edt(~is_edge, sampling=voxel_size_zyx).astype(np.float32)
+  dist[excluded | ~np.isfinite(dist)] = -1
+  return dist
 
 
 class PolicyMax(BaseSeedPolicy):

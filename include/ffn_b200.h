@@ -158,8 +158,9 @@ void ffn_canvas_destroy(FfnCanvas* canvas);
 /* MovementRestrictor.mask / .seed_mask (movement.py:290-314); mask: host uint8 [Z,Y,X] or NULL. */
 int ffn_canvas_set_mask(FfnCanvas* canvas, int which, const uint8_t* mask);
 
-/* Canvas.segment_at (inference.py:460-533).  reset != 0: init_seed + reset_state first
- * (partial_segment_iters == 0 path); reset == 0 resumes the current object.  Runs at most
+/* Canvas.segment_at (inference.py:460-533).  reset == 1: init_seed + reset_state first
+ * (partial_segment_iters == 0 path); reset == 2: reset_state only — the seed and the extents are kept
+ * (Canvas.reset_seed_per_segment == False, inference.py:486-490); reset == 0 resumes the current object.  Runs at most
  * max_steps FoV steps (<= 0: unlimited) inside ONE persistent kernel launch per ~budget. */
 int ffn_canvas_segment_at(FfnCanvas* canvas, const int32_t start_zyx[3], int reset,
                           int64_t max_steps, FfnSegStats* out);

@@ -279,6 +279,52 @@ def test_batched_predict_shares_rounds(engines, golden_dir):
     np.testing.assert_array_equal(e.predict(seeds[i], imgs[i]), ref[i])
 
 
+def test_device_movement_policy_known_answers(golden_dir):
+  """get_scored_move_offsets + FaceMaxMovementPolicy.update on the DEVICE against the reference's own outputs
+  (tests/golden/moves.npz: random faces, exact ties, nothing above threshold, anisotropic deltas).  A network
+  with all-zero weights returns logits == the seed patch, so the canvas is loaded with the fixture's logits,
+  ONE FoV step is run with the seed kept (reset_seed_per_segment=False) and the pushes are read from the
+  event log: same offsets in the same order (descending (score, (dz, dy, dx)), movement.py:218)."""
+  from ffn_b200 import _lib, engine as eng
+  g = np.load(os.path.join(golden_dir, 'moves.npz'))
+  th = float(g['threshold'])
+  engines = {}
+  checked = 0
+  for i in range(int(g['n'])):
+    logits = g['logits_%d' % i]
+    deltas = tuple(int(v) for v in g['deltas_%d' % i])
+    fov = tuple(int(v) for v in logits.shape)
+    if min(fov) < 3:
+      continue                                    # 2-D models are outside the engine's geometry
+    key = (fov, deltas)
+    if key not in engines:
+      w = [np.zeros((3, 3, 3, 2 if l == 0 else 32, 32), np.float32) for l in range(4)] + [np.zeros((1, 1, 1, 32, 1), np.float32)]
+      b = [np.zeros(32, np.float32) for _ in range(4)] + [np.zeros(1, np.float32)]
+      engines[key] = eng.Engine(w, b, fov, deltas, compute_mode=_lib.COMPUTE_FP16_TC)
+    e = engines[key]
+    cv = eng.DeviceCanvas(e, np.zeros(fov, np.float32), eng.make_options(policy_score_threshold=th))
+    pos = tuple(s // 2 for s in fov)
+    seed = logits.astype(np.float32).copy()
+    seed[pos] = np.float32(10.0)                  # the start voxel must pass is_valid_pos; it is on no face
+    cv.write(_lib.ARRAY_SEED, seed)
+    cv.start_trace(64)
+    st = cv.segment_at(pos, max_steps=1, keep_seed=True)
+    assert st.iters == 1
+    ev = cv.get_trace()
+    pushes = [tuple(int(v) - p for v, p in zip(r[1:4], pos)) for r in ev if r[0] == 1][1:]   # [0] is the start item
+    moves = g['moves_%d' % i]
+    want = sorted(((float(m[0]), (int(m[1]), int(m[2]), int(m[3]))) for m in moves), reverse=True)
+    assert pushes == [w_[1] for w_ in want], (i, pushes, want)
+    for off in pushes:                            # the score of a move is the logit at its position
+      z, y, x = (p + o for p, o in zip(pos, off))
+      assert float(logits[z, y, x]) >= th
+    checked += 1
+    cv.close()
+  assert checked >= 20
+  for e in engines.values():
+    e.close()
+
+
 def test_masks_and_rejections_vs_hybrid_oracle(engines):
   """Movement mask, seed mask, min_boundary_dist, small-object rejection (-1 markers)."""
   from ffn_b200 import _lib, engine as eng

@@ -241,6 +241,7 @@ struct Job {
   int ovl_ids;
   unsigned char* seed_status;   // [n_seeds] 0: not started, 1: taken by a chain
   long long round_cap;          // segment_all: rounds one launch may run (watchdog)
+  long long watchdog_ns;        // wall-clock limit of one launch
   int debug;                    // scheduler experiments (FFN_B200_DEBUG): 1 = treat every early run as conflicting, 2 = no early runs
 };
 

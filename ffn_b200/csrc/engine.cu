@@ -180,6 +180,11 @@ int launch(FfnEngine* e, FfnCanvas* c, int nchains, const Job& job) {
   std::memcpy(p.tmap, e->tmap, sizeof(p.tmap));
   p.use_tmap = e->use_tmap;
   p.job = job;
+  {
+    const char* env = std::getenv("FFN_B200_WATCHDOG_S");
+    const long long secs = env ? std::atoll(env) : 60;
+    p.job.watchdog_ns = (secs > 0 ? secs : 60) * 1000000000ll;
+  }
   p.compute_mode = e->compute_mode;
   CUDA_OK(cudaMemsetAsync(e->ws.bar, 0, sizeof(unsigned), cudaStreamPerThread));
   CUDA_OK(cudaMemsetAsync(e->ws.abort_flag, 0, sizeof(int), cudaStreamPerThread));
@@ -770,7 +775,11 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   // trace (Canvas.history) run one object at a time.
   int K = 1;
   if (e->compute_mode == FFN_COMPUTE_FP16_TC && !c->cv.trace) K = chain_limit(e);
-  if (ensure_bufs(c, K > 1 ? kBufsPerChain * K : 1)) return 1;
+  if (ensure_bufs(c, K > 1 ? kBufsPerChain * K : 1)) {
+    // not enough device memory for the object buffers of several chains: run one object at a time
+    cudaGetLastError();
+    K = 1;
+  }
   int* d_seeds = nullptr;
   FfnOrigin* d_orig = nullptr;
   FfnOverlap* d_ovl = nullptr;
@@ -873,6 +882,17 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
       return fail("scheduler state copy failed");
     }
     if (sc.all_done) break;
+    if ((job.debug & 64) && sc.steps_executed < job.step_budget) {   // a launch ended early without being done: why?
+      std::vector<CanvasState> dbg(kMaxBufs);
+      cudaMemcpy(dbg.data(), c->d_state, sizeof(CanvasState) * kMaxBufs, cudaMemcpyDeviceToHost);
+      std::fprintf(stderr, "[ffn] launch %lld ended early: commit_idx %lld / %lld owner %d round %u active %d %d %d\n", launches,
+                   sc.commit_idx, (long long)n_seeds, sc.owner, sc.round, sc.active[0], sc.active[1], sc.active[2]);
+      for (int b = 0; b < K * kBufsPerChain; ++b)
+        if (sc.bkind[b] > 0)
+          std::fprintf(stderr, "   buf %d kind %d seed %lld bround %d | phase %d seed %lld spec %d iters %lld fin_round %d have_cur %d\n", b,
+                       sc.bkind[b], sc.bseed[b], sc.bround[b], dbg[b].phase, dbg[b].seed_index, dbg[b].spec, dbg[b].iters,
+                       dbg[b].fin_round, dbg[b].have_cur);
+    }
     if (sc.overflow & 16) stuck = 3;   // the device watchdog tripped
     (void)before_round;
     if (stuck < 3) stuck = (sc.steps_executed == before_steps && sc.commit_idx == before_idx) ? stuck + 1 : 0;

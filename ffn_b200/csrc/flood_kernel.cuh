@@ -1218,6 +1218,7 @@ __device__ __forceinline__ bool warp_pop(const KParams& p, const LChain& L, int 
   const bool weak = seed_value(p, L, st->start[0], st->start[1], st->start[2]) < cv.opt.move_threshold;
   for (;;) {
     const int head = st->q_head, n = st->q_tail - head;
+    __syncwarp();   // every lane has read the queue bounds before lane 0 advances them
     if (n <= 0) return false;
     const bool act = lane < n;
     int cz = 0, cy = 0, cx = 0, cls = 0;   // 0 done, 1 below threshold, 2 invalid, 3 valid
@@ -1459,6 +1460,7 @@ __device__ __forceinline__ void advance_pointer(const Ctx& c, const LChain& L, S
   CanvasState* st = L.st;
   while (sc->owner < 0 && sc->commit_idx < p.job.n_seeds) {
     const long long i = sc->commit_idx;
+    __syncwarp();   // reads of this iteration before lane 0's writes
     if (__ldcg(p.job.seed_status + i) != 0) {      // an early run holds it: its buffer is now at the head of the line
       int who = -1;
       for (int q = 0; q < p.nchains; ++q)
@@ -1614,6 +1616,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, LChain L, Sched* sc, 
   const unsigned full = 0xffffffffu;
   for (int guard = 0; guard < (1 << 20); ++guard) {
     const int phase = st->phase;
+    __syncwarp();   // every lane has read the state of this iteration before lane 0 changes it
     // ------------------------------------------------------------- terminal / idle phases
     if (phase == PH_IDLE || phase == PH_SEGMENT_DONE || phase == PH_ALL_DONE) return ACT_EXIT;
     if (pause) {
@@ -1714,6 +1717,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, LChain L, Sched* sc, 
     if (phase == PH_POP) {
       if (!st->popped) chain_pop(c, L);
       const bool run = st->pop_run != 0;
+      __syncwarp();
       if (run) {
         if (c.lane == 0) {
           st->popped = 0;
@@ -1762,6 +1766,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, LChain L, Sched* sc, 
         }
         return ACT_IDLE;
       }
+      __syncwarp();
       if (c.lane == 0) st->have_cur = 0;
       __syncwarp();
       if (sc->owner != L.b) {
@@ -1945,8 +1950,9 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
   const unsigned par = (c.round & 1u) ^ 1u;   // parity the finished round was staged with
   const long long t_all = prof_now(c);
   // Watchdog: one launch covers at most 2^15 FoV steps (a few seconds).  A launch that is still going after
-  // 60 s has stalled; raise the abort flag so that every CTA leaves at this round boundary and the host reports it.
-  if (c.tid == 0 && sm100::globaltimer_ns() - c.t_start > 60000000000ull) atomicExch(p.ws.abort_flag, 5);
+  // 60 s (FFN_B200_WATCHDOG_S; sanitizer runs need more) has stalled; raise the abort flag so that every CTA leaves
+  // at this round boundary and the host reports it.
+  if (c.tid == 0 && sm100::globaltimer_ns() - c.t_start > (unsigned long long)p.job.watchdog_ns) atomicExch(p.ws.abort_flag, 5);
   // Work on shared-memory copies: the serial code is full of read-after-write on these fields, and in
   // global memory every one of those is an L2 round trip.
   for (int i = c.tid; i < K * kStateWords; i += 256) {
@@ -2015,6 +2021,7 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
       bool all_free = true;
       for (int k = 0; k < K; ++k) all_free = all_free && chain_state(c, k)->phase == PH_FREE;
       for (int b = 0; b < K * kBufsPerChain; ++b) all_free = all_free && sc->bkind[b] != 1 && sc->bkind[b] != 2;
+      __syncwarp();   // every lane has read the phases before lane 0 changes them
       if (all_free && sc->commit_idx >= p.job.n_seeds && sc->owner < 0) {
         if (c.lane == 0) {
           sc->all_done = 1;
@@ -2029,7 +2036,9 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
           waiting = waiting || (chain_state(c, k)->phase == PH_FINISHED && chain_state(c, k)->fin_round + 1 >= (int)sc->round);
         for (int b = 0; b < K * kBufsPerChain; ++b)   // an object parked / a run suspended this round goes on next round
           waiting = waiting || ((sc->bkind[b] == 1 || sc->bkind[b] == 2) && sc->bround[b] + 1 >= (int)sc->round);
-        any = waiting;
+        // the head of the line was handed to an object of a chain that had already been looked at this round
+        // (chains are processed in order): it acts next round
+        any = waiting || sc->owner >= 0;
       }
     }
     // watchdog: a launch that runs far more rounds than its step budget and seed count allow is reported, not spun on

@@ -217,7 +217,7 @@ class Runner:
                            overlaps=canvas.overlaps)
     if canvas.seg_prob is not None:
       with storage.atomic_file(prob_path) as fd:
-        np.savez_compressed(fd, qprob=np.asarray(canvas.seg_prob))
+        storage.savez_deflate(fd, qprob=np.asarray(canvas.seg_prob))
 
   def run(self, corner, subvol_size, reset_counters=True):
     """Runs FFN inference over a subvolume; returns the Canvas (None if already done / masked)."""

@@ -135,12 +135,26 @@ def dequantize_probability(prob):
   return ret
 
 
+def savez_deflate(fd, compresslevel=3, **arrays):
+  """Writes what np.savez_compressed writes — a zip archive of .npy members with DEFLATE, readable by np.load —
+  at a chosen zlib level.  Level 3 is ~2x faster than numpy's fixed level 6 on label volumes for ~35 % more bytes;
+  once the flood fill runs at 10^4 steps/s the compression of seg-*.npz / .prob is a visible
+  part of Runner.run."""
+  import zipfile
+  from numpy.lib import format as npy_format
+  with zipfile.ZipFile(fd, mode='w', compression=zipfile.ZIP_DEFLATED, allowZip64=True, compresslevel=compresslevel) as zf:
+    for name, value in arrays.items():
+      arr = np.asanyarray(value)
+      with zf.open(name + '.npy', 'w', force_zip64=True) as member:
+        npy_format.write_array(member, arr, allow_pickle=True)
+
+
 def save_subvolume(labels, origins, output_path, **misc_items):
   """seg-*.npz writer: segmentation (minimal uint dtype), origins, extra items (:154-171)."""
   seg = segmentation.reduce_id_bits(labels)
   os.makedirs(os.path.dirname(output_path), exist_ok=True)
   with atomic_file(output_path) as fd:
-    np.savez_compressed(fd, segmentation=seg, origins=origins, **misc_items)
+    savez_deflate(fd, segmentation=seg, origins=origins, **misc_items)
 
 
 def legacy_subvolume_path(output_dir, corner, suffix):

@@ -69,6 +69,8 @@ struct Weights {
 };
 
 // Buffers shared by all chains (the fp32 / split-fp16 parity modes run one chain at a time).
+constexpr int kTraceEvents = 8, kTraceTiles = 2048, kTraceCta = 1;
+
 struct Workspace {
   __half* act0_l;      // fp16 lo parts (FFN_COMPUTE_FP16X2_TC): x = hi + lo with hi = fp16(x), lo = fp16(x - hi)
   __half* act_l[2];
@@ -77,7 +79,7 @@ struct Workspace {
   float4* res;         // [8][rows_alloc] fp32 residual stream (fp32 mode)
   unsigned* bar;       // grid barrier counter
   int* abort_flag;     // != 0: a wait timed out, everybody bails
-  long long* prof;     // [2][16] cycle counters of CTA 0 and CTA G-1 (debug/profiling)
+  long long* prof;     // [2][16] cycle counters of CTA 0 and CTA G-1, then [kTraceEvents][kTraceTiles] event times of CTA kTraceCta (profiled build)
 };
 
 struct CanvasDev {

@@ -1,6 +1,7 @@
 // engine.cu — host side of libffn_b200.so: device context, weight packing, canvases, launches,
 // and the extern "C" entry points declared in include/ffn_b200.h.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -91,6 +92,7 @@ struct FfnCanvas {
   ffn::ObjDev ob[ffn::kMaxBufs]{};        // object buffers; [0] holds the canvas's own seed array
   int nbufs_alloc = 1;
   float* d_snap = nullptr;                // snapshot seed array (Sched::last_chain), allocated with the extra chains
+  std::vector<void*> pools;               // allocations behind object buffers 1.. and the snapshot array
   ffn::CanvasState* d_state = nullptr;    // [kMaxBufs]
   ffn::CanvasState h_state{};             // buffer 0
   ffn::Sched* d_sched = nullptr;
@@ -234,16 +236,43 @@ int alloc_buf(FfnCanvas* c, int k) {
   return 0;
 }
 
-// Object buffers 1 .. n-1 and the snapshot array, on first use.
+// Object buffers 1 .. n-1 and the snapshot array, on first use: ONE allocation for the seed arrays and one for the
+// small per-object arrays (two dozen separate cudaMalloc calls of 60 MB took 6 - 100 ms of a 2 s segment_all).
 int ensure_bufs(FfnCanvas* c, int n) {
-  for (int k = c->nbufs_alloc; k < n; ++k) {
-    if (alloc_buf(c, k)) return 1;
-    c->nbufs_alloc = k + 1;
-  }
-  if (n > 1 && !c->d_snap) {
-    if (dev_alloc(&c->d_snap, c->nvox, false)) return 1;
-    fill_f32_kernel<<<c->eng->sm_count * 8, 256, 0, cudaStreamPerThread>>>(c->d_snap, c->nvox, NAN);
+  const int first = c->nbufs_alloc;
+  const bool need_snap = n > 1 && !c->d_snap;
+  if (first >= n && !need_snap) return 0;
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const int nnew = std::max(n - first, 0);
+  const size_t seed_b = up(c->nvox * sizeof(float));
+  const size_t lat_b = up(c->lattice_cells * sizeof(*c->ob[0].lattice)), qs_b = up(c->q_cap * sizeof(*c->ob[0].q_score)),
+               qp_b = up(c->q_cap * 3 * sizeof(*c->ob[0].q_pos)), tr_b = up(c->traj_cap * 3 * sizeof(*c->ob[0].traj));
+  const size_t small_b = lat_b + qs_b + qp_b + tr_b;
+  unsigned char *big = nullptr, *small = nullptr;
+  const size_t big_total = seed_b * (size_t)(nnew + (need_snap ? 1 : 0));
+  if (big_total) {
+    CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&big), big_total));
+    c->pools.push_back(big);
+    fill_f32_kernel<<<c->eng->sm_count * 8, 256, 0, cudaStreamPerThread>>>(reinterpret_cast<float*>(big), big_total / sizeof(float), NAN);
     CUDA_OK(cudaGetLastError());
+  }
+  if (nnew) {
+    CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&small), small_b * (size_t)nnew));
+    c->pools.push_back(small);
+    CUDA_OK(cudaMemsetAsync(small, 0, small_b * (size_t)nnew, cudaStreamPerThread));
+  }
+  for (int i = 0; i < nnew; ++i) {
+    ObjDev& ob = c->ob[first + i];
+    ob.seed = reinterpret_cast<float*>(big + seed_b * (size_t)i);
+    unsigned char* q = small + small_b * (size_t)i;
+    ob.lattice = reinterpret_cast<decltype(ob.lattice)>(q);
+    ob.q_score = reinterpret_cast<decltype(ob.q_score)>(q + lat_b);
+    ob.q_pos = reinterpret_cast<decltype(ob.q_pos)>(q + lat_b + qs_b);
+    ob.traj = reinterpret_cast<decltype(ob.traj)>(q + lat_b + qs_b + qp_b);
+  }
+  c->nbufs_alloc = std::max(first, n);
+  if (need_snap) {
+    c->d_snap = reinterpret_cast<float*>(big + seed_b * (size_t)nnew);
     for (int q = 0; q < 3; ++q) c->h_sched.snap_lo[q] = c->h_sched.snap_hi[q] = 0;
   }
   CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
@@ -426,7 +455,7 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
   if (dev_alloc(&ws.res, 8 * ra)) return 1;
   if (dev_alloc(&ws.bar, 1)) return 1;
   if (dev_alloc(&ws.abort_flag, 1)) return 1;
-  if (dev_alloc(&ws.prof, 32)) return 1;
+  if (dev_alloc(&ws.prof, 32 + kTraceEvents * kTraceTiles)) return 1;
   for (void* p : std::vector<void*>{ws.act0_l, ws.act_l[0], ws.act_l[1], ws.act0_f, ws.act_f[0], ws.act_f[1], ws.res,
                                     ws.bar, ws.abort_flag, ws.prof})
     e->owned.push_back(p);
@@ -544,6 +573,15 @@ int ffn_engine_profile(FfnEngine* e, int64_t out[32], int reset) {
   return 0;
 }
 
+int ffn_engine_trace(FfnEngine* e, int64_t* out, int64_t n, int reset) {
+  if (!e || !out || n < 0 || n > (int64_t)kTraceEvents * kTraceTiles) return fail("bad argument");
+  if (set_device(e)) return 1;
+  static_assert(sizeof(long long) == sizeof(int64_t), "trace element");
+  CUDA_OK(cudaMemcpy(out, e->ws.prof + 32, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (reset) CUDA_OK(cudaMemset(e->ws.prof + 32, 0, sizeof(long long) * kTraceEvents * kTraceTiles));
+  return 0;
+}
+
 int ffn_predict(FfnEngine* e, const float* seed, const float* image, int batch, float* logits_out) {
   if (!e || !seed || !image || !logits_out || batch < 1) return fail("bad argument");
   if (set_device(e)) return 1;
@@ -655,14 +693,12 @@ void ffn_canvas_destroy(FfnCanvas* c) {
   FfnEngine* e = c->eng;
   cudaSetDevice(e->device);
   cudaFree(c->d_image);
-  for (int k = 0; k < kMaxBufs; ++k) {
-    cudaFree(c->ob[k].seed);
-    cudaFree(c->ob[k].lattice);
-    cudaFree(c->ob[k].q_score);
-    cudaFree(c->ob[k].q_pos);
-    cudaFree(c->ob[k].traj);
-  }
-  cudaFree(c->d_snap);
+  cudaFree(c->ob[0].seed);      // buffer 0 is allocated with the canvas; the others and the snapshot array live in pools
+  cudaFree(c->ob[0].lattice);
+  cudaFree(c->ob[0].q_score);
+  cudaFree(c->ob[0].q_pos);
+  cudaFree(c->ob[0].traj);
+  for (void* q : c->pools) cudaFree(q);
   cudaFree(c->cv.seg);
   cudaFree(c->cv.qprob);
   cudaFree(c->cv.trace);
@@ -775,11 +811,16 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   // trace (Canvas.history) run one object at a time.
   int K = 1;
   if (e->compute_mode == FFN_COMPUTE_FP16_TC && !c->cv.trace) K = chain_limit(e);
+  const auto t_enter = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+  };
   if (ensure_bufs(c, K > 1 ? kBufsPerChain * K : 1)) {
     // not enough device memory for the object buffers of several chains: run one object at a time
     cudaGetLastError();
     K = 1;
   }
+  const double ms_bufs = since(t_enter);
   int* d_seeds = nullptr;
   FfnOrigin* d_orig = nullptr;
   FfnOverlap* d_ovl = nullptr;
@@ -866,6 +907,7 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
   long long launches = 0;
   int stuck = 0;
   int rc = 0;
+  const double ms_setup = since(t_enter);
   for (;;) {
     const long long before_steps = sc.steps_executed, before_idx = sc.commit_idx;
     const unsigned before_round = sc.round;
@@ -909,6 +951,7 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
       break;
     }
   }
+  const double ms_loop = since(t_enter);
   if (!rc && pull_state(c)) rc = 1;
   // ---- Canvas.seed shows the last object segment_at ran on: bring it into the canvas's own array
   if (!rc && (sc.last_in_snap || sc.last_chain > 0)) {
@@ -952,6 +995,9 @@ int ffn_canvas_segment_all(FfnCanvas* c, const int32_t* seeds, int64_t n_seeds, 
                    cudaMemcpyDeviceToHost) != cudaSuccess)
       rc = fail("overlaps copy failed");
   cleanup();
+  if (job.debug & 128)
+    std::fprintf(stderr, "[ffn] segment_all host ms: buffers %.2f, setup %.2f, launches %.2f (kernel %.2f), tail %.2f\n", ms_bufs,
+                 ms_setup - ms_bufs, ms_loop - ms_setup, secs * 1e3, since(t_enter) - ms_loop);
   st.ctr = sc.ctr;
   st.ctr.max_id = sc.max_id;
   st.ctr.device_seconds += secs;

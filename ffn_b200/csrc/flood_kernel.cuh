@@ -67,6 +67,10 @@ struct Ctx {
   Sched* s_sched;              // CTA 0: working copy of the scheduler state
   long long* prof;             // profiling slots of this CTA in SHARED memory (null unless CTA 0 / G-1);
                                // flushed to global once, at kernel end, so timing does not stall the timed code
+#if FFN_PROFILE
+  long long* trace;            // per-tile event times of CTA kTraceCta (global, [kTraceEvents][kTraceTiles]); else null
+  unsigned sig_cnt;            // signaller: releases so far
+#endif
   // mbarrier phase parities and pending-prefetch flags as ONE bit field: dynamically indexed arrays
   // would push this whole struct into local memory (behind the L1 every grid barrier invalidates).
   uint32_t bits;   // bit b: weights[b] parity; 8+b: weights[b] in flight
@@ -98,9 +102,16 @@ __device__ __forceinline__ long long prof_now(const Ctx& c) { return c.prof ? cl
 __device__ __forceinline__ void prof_add(const Ctx& c, int slot, long long dt) {
   if (c.prof) c.prof[slot] += dt;
 }
+// Tile timeline of one CTA (ffn_engine_trace): event e of the role's idx-th tile since kernel start.
+//   0 producer saw the chain barrier   1 tile's copies issued   2 UMMA issuer saw the operands   3 ... got a TMEM slot
+//   4 UMMAs issued   5 epilogue saw the accumulators   6 epilogue done   7 signaller released (idx = signal number)
+__device__ __forceinline__ void trace_ev(const Ctx& c, int ev, unsigned idx) {
+  if (c.trace && idx < (unsigned)kTraceTiles) c.trace[ev * kTraceTiles + idx] = clock64();
+}
 #else
 __device__ __forceinline__ long long prof_now(const Ctx&) { return 0ll; }
 __device__ __forceinline__ void prof_add(const Ctx&, int, long long) {}
+__device__ __forceinline__ void trace_ev(const Ctx&, int, unsigned) {}
 #endif
 
 // Bounded spin on an mbarrier phase; a timeout raises the abort flag instead of hanging the GPU.
@@ -428,6 +439,7 @@ __device__ __forceinline__ int tc_epilogue(Ctx& c, int k, int layer, int ntiles)
     long long t0 = prof_now(c);
     mbar_wait(c, &c.mb_tfull[slot], (c.epi_cnt / kAccSlots) & 1u);
     if (c.tid == 0) prof_add(c, 4, prof_now(c) - t0);
+    if (c.tid == 0) trace_ev(c, 5, c.epi_cnt);
     t0 = prof_now(c);
     sm100::tc_fence_after();
     const uint32_t tbase = c.tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(slot * kStackN + half * 16);
@@ -548,6 +560,7 @@ __device__ __forceinline__ int tc_epilogue(Ctx& c, int k, int layer, int ntiles)
     }
     if (kWriteRes) sm100::tmem_st_wait();
     if (c.tid == 0) prof_add(c, 5, prof_now(c) - t0);
+    if (c.tid == 0) trace_ev(c, 6, c.epi_cnt);
     ++c.epi_cnt;
   }
   return hit;
@@ -609,7 +622,10 @@ __device__ __forceinline__ void layers_pipelined(Ctx& c, unsigned mask) {
         const ChainDev& ch = p.ch[k];
         const __half* in = layer == 0 ? ch.act0_h : ch.act_h[(layer - 1) & 1];
         chain_wait(c, k, (unsigned)layer + 1u);   // event 1 = staged, event l + 1 = layer l - 1 complete everywhere
-        sm100::fence_proxy_async_global();        // other CTAs' generic-proxy stores (ordered by the acquire) -> async proxy
+        if (c.lane == 0) trace_ev(c, 0, c.load_cnt);
+#ifndef FFN_EXP_NO_READER_FENCE
+        sm100::fence_proxy_async_global();
+#endif        // other CTAs' generic-proxy stores (ordered by the acquire) -> async proxy
         for (int j = 0; j < ntiles; ++j) {
           const int s = c.load_cnt % kActStages;
           mbar_wait(c, &c.mb_empty[s], ((c.load_cnt / kActStages) & 1u) ^ 1u);
@@ -635,6 +651,7 @@ __device__ __forceinline__ void layers_pipelined(Ctx& c, unsigned mask) {
             }
           }
           __syncwarp();
+          if (c.lane == 0) trace_ev(c, 1, c.load_cnt);
           ++c.load_cnt;
         }
       }
@@ -657,11 +674,18 @@ __device__ __forceinline__ void layers_pipelined(Ctx& c, unsigned mask) {
         if (!((mask >> k) & 1u)) continue;
         for (int j = 0; j < ntiles; ++j) {
           const int s = c.mma_cnt % kActStages, slot = c.mma_cnt % kAccSlots;
+#ifdef FFN_EXP_TEMPTY_FIRST
+          mbar_wait(c, &c.mb_tempty[slot], ((c.mma_cnt / kAccSlots) & 1u) ^ 1u);
+#endif
           t0 = prof_now(c);
           mbar_wait(c, &c.mb_full[s], (c.mma_cnt / kActStages) & 1u);
           if (c.lane == 0) prof_add(c, 1, prof_now(c) - t0);
+          if (c.lane == 0) trace_ev(c, 2, c.mma_cnt);
+#ifndef FFN_EXP_TEMPTY_FIRST
           mbar_wait(c, &c.mb_tempty[slot], ((c.mma_cnt / kAccSlots) & 1u) ^ 1u);
+#endif
           sm100::tc_fence_after();
+          if (c.lane == 0) trace_ev(c, 3, c.mma_cnt);
           t0 = prof_now(c);
           const uint32_t a_lo = ((sm100::smem_u32(act_smem + (size_t)s * stage_bytes) >> 4) & 0x3FFFu) | ((uint32_t)(3 * seg_rows) << 16);
           const uint32_t d = c.tmem_base + (uint32_t)(slot * kStackN);
@@ -676,6 +700,7 @@ __device__ __forceinline__ void layers_pipelined(Ctx& c, unsigned mask) {
           }
           __syncwarp();
           if (c.lane == 0) prof_add(c, 3, prof_now(c) - t0);
+          if (c.lane == 0) trace_ev(c, 4, c.mma_cnt);
           ++c.mma_cnt;
         }
       }
@@ -687,6 +712,10 @@ __device__ __forceinline__ void layers_pipelined(Ctx& c, unsigned mask) {
         if (!((mask >> k) & 1u)) continue;
         // phase of the chain's mbarrier: nconv - 1 (odd) arrivals per round the chain was active in
         chain_signal(c, k, ((ev_get(c, k) / (unsigned)nconv) + (unsigned)layer) & 1u);
+#if FFN_PROFILE
+        if (c.lane == 0) trace_ev(c, 7, c.sig_cnt);
+        ++c.sig_cnt;
+#endif
       }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-7)
@@ -2275,6 +2304,10 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
     c.prof = reinterpret_cast<long long*>(smem_raw + L.bars + 832);
     if (c.tid < 16) c.prof[c.tid] = 0;
   }
+#if FFN_PROFILE
+  c.trace = (p.ws.prof && c.cta == kTraceCta) ? p.ws.prof + 32 : nullptr;
+  c.sig_cnt = 0;
+#endif
   const long long t_kernel = prof_now(c);
   c.bits = 0;
   c.tmem_base = 0;

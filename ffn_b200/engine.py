@@ -117,6 +117,12 @@ class Engine:
     return {'cta0': dict(zip(self.PROFILE_SLOTS, [int(v) for v in buf[:16]])),
             'cta_last': dict(zip(self.PROFILE_SLOTS, [int(v) for v in buf[16:32]]))}
 
+  def trace(self, reset: bool = True) -> np.ndarray:
+    """[8 events][2048 tiles] SM-clock timeline of CTA 1 (see ffn_engine_trace); needs enable_profiling()."""
+    buf = np.zeros((8, 2048), dtype=np.int64)
+    _lib.check(self._lib.ffn_engine_trace(self._h, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, 1 if reset else 0))
+    return buf
+
   def predict(self, seed: np.ndarray, image: np.ndarray) -> np.ndarray:
     """(Z,Y,X) or (B,Z,Y,X) float32 patches -> logits of the same shape (executor.py:134-139)."""
     seed = np.ascontiguousarray(seed, dtype=np.float32)

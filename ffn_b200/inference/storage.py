@@ -135,11 +135,96 @@ def dequantize_probability(prob):
   return ret
 
 
+_DEFLATE_CHUNK = 4 << 20
+_deflate_pool = None
+
+
+def _pool():
+  global _deflate_pool
+  if _deflate_pool is None:
+    from concurrent.futures import ThreadPoolExecutor
+    _deflate_pool = ThreadPoolExecutor(max_workers=max(1, min(16, (os.cpu_count() or 2) - 1)), thread_name_prefix='ffn-deflate')
+  return _deflate_pool
+
+
+def _deflate_piece(view, level, last):
+  """Raw-deflate one independent piece; not-last pieces end on a byte boundary without the final-block bit, so the
+  concatenation of the pieces is ONE valid deflate stream (what pigz -i does).  zlib releases the GIL."""
+  import zlib
+  co = zlib.compressobj(level, zlib.DEFLATED, -15)
+  return co.compress(view) + co.flush(zlib.Z_FINISH if last else zlib.Z_FULL_FLUSH)
+
+
+def _npy_parts(arr):
+  """The bytes of an .npy member as a list of buffers (header, data) without copying the data."""
+  import io
+  from numpy.lib import format as npy_format
+  if arr.dtype.hasobject or arr.nbytes < (1 << 16):
+    bio = io.BytesIO()
+    npy_format.write_array(bio, arr, allow_pickle=True)
+    return [bio.getvalue()]
+  arr = np.ascontiguousarray(arr)
+  bio = io.BytesIO()
+  npy_format.write_array_header_1_0(bio, npy_format.header_data_from_array_1_0(arr))
+  return [bio.getvalue(), memoryview(arr.reshape(-1).view(np.uint8))]
+
+
 def savez_deflate(fd, compresslevel=3, **arrays):
-  """Writes what np.savez_compressed writes — a zip archive of .npy members with DEFLATE, readable by np.load —
-  at a chosen zlib level.  Level 3 is ~2x faster than numpy's fixed level 6 on label volumes for ~35 % more bytes;
-  once the flood fill runs at 10^4 steps/s the compression of seg-*.npz / .prob is a visible
-  part of Runner.run."""
+  """Writes what np.savez_compressed writes — a zip archive of DEFLATE-compressed .npy members, readable by
+  np.load — but compresses 4 MB pieces of every member on a thread pool (and at zlib level 3 instead of numpy's
+  fixed 6): once the flood fill runs at 10^4 steps/s, single-threaded zlib over seg-*.npz / .prob was a sixth of
+  Runner.run.  Members of 4 GB or more take the plain zipfile path (zip64)."""
+  import struct
+  import time
+  import zlib
+  members = []
+  for name, value in arrays.items():
+    parts = _npy_parts(np.asanyarray(value))
+    if sum(len(x) for x in parts) >= 0xFFFFFFF0:
+      return _savez_deflate_serial(fd, compresslevel, arrays)
+    members.append((name + '.npy', parts))
+  pool = _pool()
+  jobs = []
+  for name, parts in members:
+    pieces = []
+    for part in parts:
+      view = memoryview(part)
+      for off in range(0, max(len(view), 1), _DEFLATE_CHUNK):
+        pieces.append(view[off:off + _DEFLATE_CHUNK])
+    futs = [pool.submit(_deflate_piece, v, compresslevel, i == len(pieces) - 1) for i, v in enumerate(pieces)]
+
+    def crc_of(parts=parts):
+      crc = 0
+      for part in parts:
+        crc = zlib.crc32(part, crc)
+      return crc
+    jobs.append((name, parts, futs, pool.submit(crc_of)))
+  t = time.localtime()
+  dostime = (t.tm_hour << 11) | (t.tm_min << 5) | (t.tm_sec // 2)
+  dosdate = ((max(t.tm_year, 1980) - 1980) << 9) | (t.tm_mon << 5) | t.tm_mday
+  central = []
+  offset = 0
+  for name, parts, futs, crc_f in jobs:
+    chunks = [f.result() for f in futs]
+    csize = sum(len(x) for x in chunks)
+    usize = sum(len(x) for x in parts)
+    crc = crc_f.result() & 0xFFFFFFFF
+    fname = name.encode('utf-8')
+    if offset + csize >= 0xFFFFFFF0:
+      raise ValueError('archive too large for the non-zip64 writer')
+    fd.write(struct.pack('<IHHHHHIIIHH', 0x04034b50, 20, 0, 8, dostime, dosdate, crc, csize, usize, len(fname), 0))
+    fd.write(fname)
+    for x in chunks:
+      fd.write(x)
+    central.append(struct.pack('<IHHHHHHIIIHHHHHII', 0x02014b50, 20, 20, 0, 8, dostime, dosdate, crc, csize, usize,
+                               len(fname), 0, 0, 0, 0, 0o600 << 16, offset) + fname)
+    offset += 30 + len(fname) + csize
+  cd = b''.join(central)
+  fd.write(cd)
+  fd.write(struct.pack('<IHHHHIIH', 0x06054b50, 0, 0, len(central), len(central), len(cd), offset, 0))
+
+
+def _savez_deflate_serial(fd, compresslevel, arrays):
   import zipfile
   from numpy.lib import format as npy_format
   with zipfile.ZipFile(fd, mode='w', compression=zipfile.ZIP_DEFLATED, allowZip64=True, compresslevel=compresslevel) as zf:

@@ -141,6 +141,11 @@ int ffn_engine_info(FfnEngine* engine, int64_t info[8]);
  * Off by default (reading the clock perturbs the critical CTA): ffn_engine_profile(e, NULL, 1) switches
  * the counters on, (e, NULL, 0) off; with out != NULL the counters are returned (and reset if reset). */
 int ffn_engine_profile(FfnEngine* engine, int64_t out[32], int reset);
+/* Tile timeline of one CTA (CTA 1) recorded while the counters are on: out[e * 2048 + i] = SM clock when event e
+ * happened to that role's i-th tile since kernel start (0 producer saw the chain barrier, 1 copies issued, 2 UMMA
+ * issuer saw the operands, 3 got an accumulator slot, 4 UMMAs issued, 5 epilogue saw the accumulators, 6 epilogue
+ * done, 7 i-th barrier release by the signal warp); 0 = not recorded.  n <= 8 * 2048.  Debug / profiles only. */
+int ffn_engine_trace(FfnEngine* engine, int64_t* out, int64_t n, int reset);
 
 /* ---- L0 drop-in: ExecutorClient.predict (ffn/inference/executor.py:134-139, 266-340) -------
  * seed, image: host float32 [batch, Z, Y, X]; logits_out: host float32 [batch, Z, Y, X]

@@ -89,6 +89,34 @@ def test_storage_paths_and_quantisation(tmp_path, golden_dir):
     assert z['segmentation'].dtype == np.uint16
 
 
+def test_savez_deflate_is_a_plain_npz(tmp_path):
+  """The seg-*.npz / .prob writer (deflate pieces compressed on a thread pool, stitched into one stream per
+  member): np.load and zipfile read it back, large members included, object members pickled as numpy does."""
+  import io
+  import zipfile
+  rng = np.random.RandomState(3)
+  big = (rng.rand(96, 128, 130) < 0.2).astype(np.uint8) * rng.randint(1, 200, (96, 128, 130)).astype(np.uint8)
+  assert big.nbytes > (1 << 20)
+  old_chunk = storage._DEFLATE_CHUNK
+  storage._DEFLATE_CHUNK = 1 << 18                      # several pieces per member
+  try:
+    bio = io.BytesIO()
+    storage.savez_deflate(bio, segmentation=big, origins={7: (1, 2, 3)}, request=b'\x00\x01', counters='{}',
+                          overlaps=np.zeros((0, 3), np.int64), fortran=np.asfortranarray(rng.rand(40, 50, 60)),
+                          empty=np.zeros((0,), np.float32))
+  finally:
+    storage._DEFLATE_CHUNK = old_chunk
+  bio.seek(0)
+  assert zipfile.ZipFile(bio).testzip() is None         # CRCs and sizes of every member
+  bio.seek(0)
+  with np.load(bio, allow_pickle=True) as z:
+    np.testing.assert_array_equal(z['segmentation'], big)
+    assert z['origins'].item() == {7: (1, 2, 3)} and z['request'].item() == b'\x00\x01' and z['counters'].item() == '{}'
+    assert z['overlaps'].shape == (0, 3) and z['empty'].shape == (0,)
+    assert z['fortran'].shape == (40, 50, 60)
+  assert len(bio.getvalue()) < big.nbytes // 2 + 40 * 50 * 60 * 8 + 4096     # the label member really is deflated
+
+
 def test_counters_and_timer():
   c = inference_utils.Counters()
   sub = c.get_sub_counters()

@@ -415,7 +415,9 @@ def test_bench_traffic_comes_from_committed_ncu_capture():
   import bench
   t = bench.ncu_dram_traffic()
   assert t is not None and t['steps_per_launch'] >= 16
-  assert 1e5 < t['bytes_per_step'] < 431244 * 2      # at most about the compulsory 431 KB/step (u8 image, L2 reuse)
+  # at most about the compulsory 431 KB/step (u8 image); far less when the touched part of the canvas stays in the
+  # 126 MB L2 between steps (250^3 bench canvas: 55 KB/step)
+  assert 1e4 < t['bytes_per_step'] < 431244 * 2
 
 
 def test_load_segmentation_reads_the_reference_shipped_result(tmp_path):

@@ -303,7 +303,7 @@ def extras_n1(engine, eng, _lib, args):
   rate = batch / (ns * 1e-9)
   out['predict_batch48'] = {'patches_per_s': rate, 'kernel_us': ns / 1e3,
                             'roofline_frac': rate * flops_per_step() / 1e12 / measured_peaks()[0],
-                            'note': 'ffn_predict(batch=48): the conv stack alone, three patches per round'}
+                            'note': 'ffn_predict(batch=48): the conv stack alone, four patches per round'}
   return out
 
 
@@ -387,7 +387,7 @@ def run_n1(args, rank, local_rank):
           'weights': wdesc, 'accumulate': 'f32', 'timed_pass': 'one whole segment_all (device PolicyPeaks + flood fill + commits); '
           '--steps is ignored (a flood fill has no meaningful K-step prefix)' + (' — capped at %d seeds' % seed_cap if seed_cap else ''),
           'l2': 'canvas state (image u8 + 4 seed f32 arrays + segmentation i32 + qprob u8 = 330 MB) exceeds L2; '
-                'the ~36 MB activation working set of three chains is L2-resident by design',
+                'the ~25 MB activation working set of four chains is L2-resident by design',
           'published_reference_p100': {'fov_steps_per_sec': 65.5, 'voxels_per_sec': 35216},
       },
       'voxels_per_sec': float(ctr.voxels_segmented) / wall,
@@ -395,7 +395,7 @@ def run_n1(args, rank, local_rank):
       'seed_policy_seconds': t_seed,
       'device_only': {'value': kernel_rate, 'unit': 'FoV steps/s', 'seconds': dev_seconds,
                       'note': 'CUDA events around the flood-kernel launches only'},
-      'chains': {'max': args.chains or 3, **spec},
+      'chains': {'max': args.chains or 4, **spec},
       'gpu_launches': int(launches),
       'clocks': clocks,
       'e2e': {'value': e2e_steps / e2e_seconds, 'unit': 'FoV steps/s', 'voxels_per_sec': e2e_vox / e2e_seconds,
@@ -550,7 +550,7 @@ def main():
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--compute', default='fp16', choices=['fp16', 'fp32', 'x2'])
-  ap.add_argument('--chains', type=int, default=0, help='objects in flight per GPU (1..3, 0 = default 3)')
+  ap.add_argument('--chains', type=int, default=0, help='objects in flight per GPU (1..4, 0 = default 4)')
   ap.add_argument('--slab', type=int, default=0, help='N > 1: slab edge instead of 512 (tests)')
   ap.add_argument('--max-seeds', type=int, default=0, help='N = 1: only the first K PolicyPeaks seeds (profiler runs)')
   ap.add_argument('--cpu-baseline-steps', type=int, default=24)

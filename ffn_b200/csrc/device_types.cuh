@@ -19,21 +19,32 @@ constexpr int kSigWarp = 10;
 #define FFN_ACT_STAGES 3
 #endif
 constexpr int kActStages = FFN_ACT_STAGES;     // shared-memory ring of per-tile activation operands
-constexpr int kAccSlots = 3;      // TMEM ring of per-tile accumulators
+#ifndef FFN_ACC_SLOTS
+#define FFN_ACC_SLOTS 2
+#endif
+constexpr int kAccSlots = FFN_ACC_SLOTS;      // TMEM ring of per-tile accumulators (measured: 2 slots cost nothing against 3 — the tile loads
+                                              // and the UMMA issue pace the pipeline — and leave TMEM columns for a fourth chain's residual)
 constexpr int kTileM = 128;       // UMMA M: accumulator rows per tensor-core tile
 constexpr int kTileOut = 126;     // FoV rows a tile OUTPUTS: the dx = -1/+1 partial sums live one row up/down, so
                                   // the first and last accumulator row of every tile only feed their neighbours
 constexpr int kStackN = 96;       // UMMA N: the three dx taps of a (dz, dy) tap-row stacked along N
 constexpr int kFeat = 32;         // feature maps of every hidden layer (UMMA N)
-constexpr int kGroupTiles = 3;    // accumulator slots in TMEM (the residual stream starts behind them)
+constexpr int kGroupTiles = kAccSlots;    // accumulator slots in TMEM (the residual stream starts behind them)
 constexpr int kMaxConv = 32;      // 2 * depth limit
-constexpr int kMaxChains = 3;     // flood-fill chains (execution slots) time-multiplexed over the SMs of one kernel
-constexpr int kBufsPerChain = 8;  // object buffers per chain: finished objects that wait for their turn to commit are parked
+#ifndef FFN_MAX_CHAINS
+#define FFN_MAX_CHAINS 4
+#endif
+#ifndef FFN_BUFS_PER_CHAIN
+#define FFN_BUFS_PER_CHAIN 6
+#endif
+constexpr int kMaxChains = FFN_MAX_CHAINS;     // flood-fill chains (execution slots) time-multiplexed over the SMs of one kernel
+constexpr int kBufsPerChain = FFN_BUFS_PER_CHAIN;  // object buffers per chain: finished objects that wait for their turn to commit are parked
 constexpr int kMaxBufs = kMaxChains * kBufsPerChain;
 constexpr int kSplitShift = 10;   // FFN_COMPUTE_FP16X2_TC: weights are split as w * 2^10 = hi + lo (keeps lo a normal fp16
                                   // number for |w| down to ~1e-4); the epilogue scales the accumulators back (exact)
 constexpr int kTmemCols = 512;    // accumulators (kGroupTiles * kStackN columns) + fp32 residual stream (32 per tile)
-constexpr int kMaxTilesPerCta = (kTmemCols - kGroupTiles * kStackN) / kFeat;   // 7: bound by the TMEM-resident residual
+constexpr int kMaxTilesPerCta = (kTmemCols - kGroupTiles * kStackN) / kFeat;   // 7 (3 slots) / 10 (2 slots): bound by the TMEM-resident residual
+static_assert(kAccSlots >= 2 && kAccSlots <= 3 && kMaxChains >= 1 && kMaxChains <= 5, "chains / accumulator slots");
 
 // Field-of-view geometry in the "row" space the kernels work in.
 //
@@ -158,7 +169,10 @@ struct CanvasState {
   int seg_all;                // 1: segment_all mode, 0: segment_at mode
   int weak;                   // last object ended by 'seed_got_too_weak'
   int popped, pop_run, pop_pos[3];   // leader scratch: queue already popped for this round (phase A)
-  int start_max_id, was_early;   // Sched::max_id when the object started; run ahead of its turn (scheduler experiments)
+  int start_max_id;           // Sched::max_id when the object started (scheduler experiments)
+  int n_unstepped;            // segment_all: positions that passed Canvas.is_valid_pos but were not stepped on (the pop that ended the
+                              // object as 'seed_got_too_weak', pops skipped by the restrictor): logged at the END of the trajectory
+                              // buffer, because their verdict — and with it the reference's counters — depends on the labels too
   // commit scratch
   int box_lo[3], box_hi[3];
   unsigned long long cnt_raw, cnt_actual;
@@ -269,6 +283,24 @@ struct KParams {
   int act_smem_bytes;   // 3 * 4 * seg_rows_max * 16
 };
 
+// The small-structures area at SmemLayout::bars (byte offsets from there):
+//   [0, 160)        mbarriers + the TMEM base address
+//   kOffMisc        s_misc: ints [0, kMaxChains) per-chain step-count accumulators, [7] abort flag copy,
+//                   [8, 8 + kMaxChains) disco flags, [16 + 32 k ...) movement-policy scratch of chain k
+//   kOffRound       s_round: [2 * kMaxChains][8] ints
+//   kOffProf        16 cycle counters (profiled build)
+//   kOffXchg        epilogue exchange (2 KB) + conv_lom dots (1 KB).  The leader's working copies of the chain states
+//                   (kStateSlot bytes each) and of the scheduler block ALIAS this region: CTA 0 uses them only between
+//                   the grid barrier and the end of leader_round, when no epilogue is running.
+constexpr int kStateSlot = 352;
+constexpr int kOffMisc = 160;
+constexpr int kMiscAbort = 7, kMiscDisco = 8, kMiscScratch = 16;
+constexpr int kOffRound = kOffMisc + (kMiscScratch + 32 * kMaxChains) * 4;
+constexpr int kOffProf = kOffRound + 2 * kMaxChains * 8 * 4;
+constexpr int kOffXchg = (kOffProf + 16 * 8 + 15) / 16 * 16;
+constexpr int kXchgBytes = 2 * 2 * 4 * 2 * 16 * 4 + 2 * 128 * 4;   // s_xchg + s_dot
+constexpr int kBarsAreaBytes = kOffXchg + kXchgBytes;
+
 // Shared-memory carve-up (bytes from the 1024-aligned base).
 struct SmemLayout {
   int wbuf;        // tc: 2 x 55296 ; fp32: 1 x 110592
@@ -286,7 +318,7 @@ __host__ __device__ inline SmemLayout smem_layout(const Geom& g) {
   const int act_bytes = kActStages * 3 * 4 * seg_rows * 16;
   s.bias = s.act + act_bytes;
   s.bars = s.bias + (kMaxConv + 1) * 32 * 4 + 16;
-  s.total = s.bars + 4096 + kMaxChains * 352 + 704;   // barriers/misc | prof | epilogue exchange + conv_lom dots | leader's chain-state / scheduler copies
+  s.total = s.bars + kBarsAreaBytes;
   return s;
 }
 

@@ -46,7 +46,7 @@ struct Ctx {
   int tid, warp, lane, cta, G;
   int t_begin, t_end;          // tiles owned by this CTA
   unsigned bar_target;         // whole-grid barrier
-  unsigned ev0, ev1, ev2;      // split-phase barrier events completed so far (this launch), per chain
+  unsigned ev0, ev1, ev2, ev3, ev4;   // split-phase barrier events completed so far (this launch), per chain
   unsigned round;              // rounds completed in this launch (parity of seed_raw / count buffers)
   unsigned long long t_start;  // globaltimer at kernel entry (watchdog)
   unsigned char* smem;
@@ -59,7 +59,7 @@ struct Ctx {
   uint64_t* mb_sig;            // [kMaxChains] epilogue -> signal warp: a chain's layer is stored (8 arrivals)
   unsigned load_cnt, mma_cnt, epi_cnt;   // per-role running tile counters (ring index + phase parity)
   uint32_t* s_tmem;            // TMEM base address
-  int* s_misc;                 // [0..3) per-chain step-count accumulators, [4..7) disco flags, [8..) leader scratch
+  int* s_misc;                 // per-chain step-count accumulators, abort copy, disco flags, leader scratch (device_types.cuh: kOffMisc)
   int* s_round;                // [k][8] this round: action, z, y, x, buffer ; [kMaxChains + k][8] previous step: flags, z, y, x, buffer
   float* s_xchg;               // [2 tile parities][2 halves][4 warps][2][16] partial sums crossing warp boundaries
   float* s_dot;                // [2][128] conv_lom partial dot products of the upper channel half
@@ -81,14 +81,18 @@ __device__ __forceinline__ uint32_t bit_get(const Ctx& c, int k) { return (c.bit
 __device__ __forceinline__ void bit_flip(Ctx& c, int k) { c.bits ^= 1u << k; }
 __device__ __forceinline__ void bit_set(Ctx& c, int k, bool v) { c.bits = (c.bits & ~(1u << k)) | ((v ? 1u : 0u) << k); }
 
-__device__ __forceinline__ unsigned ev_get(const Ctx& c, int k) { return k == 0 ? c.ev0 : (k == 1 ? c.ev1 : c.ev2); }
+__device__ __forceinline__ unsigned ev_get(const Ctx& c, int k) {
+  return k == 0 ? c.ev0 : (k == 1 ? c.ev1 : (k == 2 ? c.ev2 : (k == 3 ? c.ev3 : c.ev4)));
+}
 __device__ __forceinline__ void ev_add(Ctx& c, int k, unsigned n) {
   if (k == 0) c.ev0 += n;
   else if (k == 1) c.ev1 += n;
-  else c.ev2 += n;
+  else if (k == 2) c.ev2 += n;
+  else if (k == 3) c.ev3 += n;
+  else c.ev4 += n;
 }
 __device__ __forceinline__ CanvasState* chain_state(const Ctx& c, int k) {
-  return reinterpret_cast<CanvasState*>(reinterpret_cast<unsigned char*>(c.s_state) + k * 352);
+  return reinterpret_cast<CanvasState*>(reinterpret_cast<unsigned char*>(c.s_state) + k * kStateSlot);
 }
 
 __device__ __forceinline__ bool aborted(const Ctx& c) {
@@ -1030,7 +1034,7 @@ __device__ __forceinline__ void push_move(const KParams& p, const LChain& L, flo
 }
 
 // Policy scratch of chain k in shared memory: score[6] floats, rel[6][3], ok[6].
-__device__ __forceinline__ int* policy_scratch(const Ctx& c, int k) { return c.s_misc + 8 + 32 * k; }
+__device__ __forceinline__ int* policy_scratch(const Ctx& c, int k) { return c.s_misc + kMiscScratch + 32 * k; }
 
 // movement.get_scored_move_offsets (movement.py:42-100) for ONE face of the step just executed at
 // st->cur: arg-max of the merged logits over the face (first index, C order); one warp, every load of
@@ -1298,6 +1302,29 @@ __device__ __forceinline__ bool warp_pop(const KParams& p, const LChain& L, int 
     const unsigned m_stop = __ballot_sync(full, act && cls == 3 && (weak || !restricted));
     const int f = m_stop ? __ffs(m_stop) - 1 : -1;
     const unsigned before = f >= 0 ? ((1u << f) - 1u) : m_act;
+    if (st->seg_all) {
+      // Candidates that passed Canvas.is_valid_pos without being stepped on — skipped by the restrictor
+      // (inference.py:507-509), or the one in hand when the loop ends with 'seed_got_too_weak' (:503-505) — relied on
+      // `segmentation <= 0` like a FoV step does: an object run ahead of its turn is only the reference's run if they
+      // are still unlabelled when its turn comes (run_conflicts), so they go into the trajectory log, from its end.
+      const unsigned m_log = (m_res & before) | ((f >= 0 && weak) ? (1u << f) : 0u);
+      if (m_log) {
+        const int slot = st->n_unstepped + __popc(m_log & ((1u << lane) - 1u));
+        if ((m_log >> lane) & 1u) {
+          if (st->iters + slot + 1 < (long long)p.cv.traj_cap) {
+            int* t = ob.traj + 3 * ((long long)p.cv.traj_cap - 1 - slot);
+            t[0] = cz;
+            t[1] = cy;
+            t[2] = cx;
+          }
+        }
+        __syncwarp();   // every lane has read n_unstepped
+        if (lane == 0) {
+          if (st->iters + st->n_unstepped + __popc(m_log) + 1 >= (long long)p.cv.traj_cap) st->overflow |= 8;
+          st->n_unstepped += __popc(m_log);
+        }
+      }
+    }
     if (lane == 0) {
       st->ctr.skip_threshold += __popc(m_thr & before);
       st->ctr.skip_invalid_pos += __popc(m_inv & before);
@@ -1384,7 +1411,7 @@ __device__ __forceinline__ void after_step(const Ctx& c, const LChain& L) {
       st->max_pos[q] = max(st->max_pos[q], st->cur[q]);
     }
     if (st->seg_all) {   // trajectory: the positions whose `segmentation <= 0` test this object relied on
-      if (st->iters < (long long)p.cv.traj_cap) {
+      if (st->iters + st->n_unstepped < (long long)p.cv.traj_cap) {
         int* t = p.ob[L.b].traj + 3 * st->iters;
         t[0] = st->cur[0];
         t[1] = st->cur[1];
@@ -1456,13 +1483,17 @@ __device__ __forceinline__ bool run_conflicts(const Ctx& c, int b, const CanvasS
     const int* t = p.ob[b].traj + 3 * i;
     if (__ldcg(p.cv.seg + cv_index(p.cv, __ldcg(t), __ldcg(t + 1), __ldcg(t + 2))) > 0) bad = true;
   }
+  // ... or any position it popped as valid without stepping on it (see warp_pop)
+  for (long long i = c.lane; i < min((long long)st->n_unstepped, (long long)p.cv.traj_cap - n); i += 32) {
+    const int* t = p.ob[b].traj + 3 * ((long long)p.cv.traj_cap - 1 - i);
+    if (__ldcg(p.cv.seg + cv_index(p.cv, __ldcg(t), __ldcg(t + 1), __ldcg(t + 2))) > 0) bad = true;
+  }
   return __any_sync(0xffffffffu, bad);
 }
 
 __device__ __forceinline__ void start_object(CanvasState* st, const Sched* sc, long long idx, int spec, int sz, int sy, int sx) {
   st->seed_index = idx;
   st->start_max_id = sc->max_id;
-  st->was_early = spec;
   st->spec = spec;
   st->start[0] = sz;
   st->start[1] = sy;
@@ -1550,11 +1581,14 @@ __device__ __forceinline__ void lookahead(const Ctx& c, const LChain& L, Sched* 
           for (int yy = max(sy - mbd[1], 0); yy < min(sy + mbd[1] + 1, cv.sy); ++yy)
             for (int xx = max(sx - mbd[2], 0); xx < min(sx + mbd[2] + 1, cv.sx); ++xx)
               if (__ldcg(cv.seg + cv_index(cv, zz, yy, xx)) > 0) ok = false;
-        // keep clear of the objects being grown: inside (their touched box + a FoV) the run would most likely be wasted
+        // keep clear of the objects being grown: inside (their touched box + half a FoV) the run would most likely be wasted
         for (int q = 0; q < p.nchains; ++q) {
           const CanvasState* o = chain_state(c, q);
           if (q == k || o->phase == PH_FREE) continue;
-          const int ez = g.fz, ey = g.fy, ex = g.fx;
+          // (measured on the 250^3 bench canvas: half a FoV of clearance beats a whole one for 3, 4 and 5 chains — fewer
+          // chain-rounds spent waiting; scheduler experiments: FFN_B200_DEBUG bit 256 = a whole FoV, bit 512 = two)
+          const int ms = (p.job.debug & 256) ? 2 : ((p.job.debug & 512) ? 4 : 1);
+          const int ez = g.fz * ms / 2, ey = g.fy * ms / 2, ex = g.fx * ms / 2;
           const bool has_box = o->dirty_hi[0] > o->dirty_lo[0];
           const int lo0 = (has_box ? min(o->dirty_lo[0], o->start[0]) : o->start[0]) - ez,
                     hi0 = (has_box ? max(o->dirty_hi[0], o->start[0] + 1) : o->start[0] + 1) + ez;
@@ -1564,6 +1598,15 @@ __device__ __forceinline__ void lookahead(const Ctx& c, const LChain& L, Sched* 
                     hi2 = (has_box ? max(o->dirty_hi[2], o->start[2] + 1) : o->start[2] + 1) + ex;
           if (sz >= lo0 && sz < hi0 && sy >= lo1 && sy < hi1 && sx >= lo2 && sx < hi2) ok = false;
         }
+        // ... and of the finished objects that wait for their turn (parked) or were suspended: one that comes EARLIER in
+        // the seed order writes its labels before this seed's turn, and a seed inside it is then rejected by the
+        // in-order gating (inference.py:562-568) — its run would be thrown away.  The object's own seed array says
+        // which voxels it will label (>= segment_threshold, inference.py:635; NaN compares false).
+        if (!(p.job.debug & 32))
+          for (int b = 0; ok && b < p.nchains * kBufsPerChain; ++b)
+            if ((sc->bkind[b] == 1 || sc->bkind[b] == 2) && sc->bseed[b] >= 0 && sc->bseed[b] < j &&
+                __ldcg(p.ob[b].seed + i) >= cv.opt.segment_threshold)
+              ok = false;
       }
     }
     const unsigned m = __ballot_sync(full, ok);
@@ -1732,6 +1775,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, LChain L, Sched* sc, 
         st->epoch++;
         st->q_head = st->q_tail = 0;
         st->iters = 0;
+        st->n_unstepped = 0;
         st->have_cur = 0;
         st->weak = 0;
         push_move(p, L, (float)(cv.opt.policy_score_threshold * 2.0), st->start[0], st->start[1], st->start[2]);
@@ -1923,7 +1967,7 @@ __device__ __forceinline__ int chain_advance(const Ctx& c, LChain L, Sched* sc, 
             o.start_zyx[2] = st->start[2];
             o.iters = st->iters;
             o.walltime_sec = (double)(sm100::globaltimer_ns() - st->seg_t0) * 1e-9;
-            if (p.job.debug & 16) o.walltime_sec = st->was_early * 1e6 + L.k * 1e5 + st->start_max_id;   // experiments
+            if (p.job.debug & 16) o.walltime_sec = L.k * 1e5 + st->start_max_id;   // experiments
             p.job.origins[sc->n_origins] = o;
           } else {
             sc->overflow |= 4;
@@ -1973,9 +2017,9 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
   Sched* sc = c.s_sched;
   constexpr int kStateWords = (int)(sizeof(CanvasState) / 8);
   constexpr int kSchedWords = (int)(sizeof(Sched) / 8);
-  static_assert(sizeof(CanvasState) <= 352 && sizeof(CanvasState) % 8 == 0, "state copy area");
-  static_assert(sizeof(Sched) <= 704 && sizeof(Sched) % 8 == 0, "scheduler copy area");
-  static_assert(256 + kSchedWords <= kThreads - kMaxChains, "scheduler copy uses threads 256 ..");
+  static_assert(sizeof(CanvasState) <= kStateSlot && sizeof(CanvasState) % 8 == 0, "state copy area");
+  static_assert(sizeof(Sched) % 8 == 0 && kMaxChains * kStateSlot + sizeof(Sched) <= kXchgBytes,
+                "the leader's working copies alias the epilogue exchange area");
   const unsigned par = (c.round & 1u) ^ 1u;   // parity the finished round was staged with
   const long long t_all = prof_now(c);
   // Watchdog: one launch covers at most 2^15 FoV steps (a few seconds).  A launch that is still going after
@@ -1991,11 +2035,12 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
     reinterpret_cast<unsigned long long*>(chain_state(c, k))[w] =
         __ldcg(reinterpret_cast<const unsigned long long*>(p.ob[b].st) + w);
   }
-  if (c.tid >= 256 && c.tid - 256 < kSchedWords)
-    reinterpret_cast<unsigned long long*>(sc)[c.tid - 256] = __ldcg(reinterpret_cast<const unsigned long long*>(p.sched) + (c.tid - 256));
+  if (c.tid >= 256)
+    for (int i = c.tid - 256; i < kSchedWords; i += kThreads - 256)
+      reinterpret_cast<unsigned long long*>(sc)[i] = __ldcg(reinterpret_cast<const unsigned long long*>(p.sched) + i);
   if (c.tid >= kThreads - kMaxChains) {
     const int k = c.tid - (kThreads - kMaxChains);
-    if (k < K) c.s_misc[4 + k] = (((stepped >> k) & 1u) && disco_active(p, k, par)) ? 1 : 0;
+    if (k < K) c.s_misc[kMiscDisco + k] = (((stepped >> k) & 1u) && disco_active(p, k, par)) ? 1 : 0;
   }
   __syncthreads();
   // ---- phase A.1: the six faces of every chain that stepped, one warp per (chain, face)
@@ -2004,14 +2049,14 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
     for (int t = c.warp; t < K * 6; t += kThreads / 32) {
       const int k = t / 6, f = t - 6 * k;
       if (!((stepped >> k) & 1u)) continue;
-      LChain L{k, sc->active[k], chain_state(c, k), par, c.s_misc[4 + k] != 0};
+      LChain L{k, sc->active[k], chain_state(c, k), par, c.s_misc[kMiscDisco + k] != 0};
       face_argmax(c, L, f);
     }
   }
   __syncthreads();
   // ---- phase A.2: one warp per chain: queue pushes, bookkeeping, the pop that decides the next step
   if (c.warp < K && ((stepped >> c.warp) & 1u)) {
-    LChain L{c.warp, sc->active[c.warp], chain_state(c, c.warp), par, c.s_misc[4 + c.warp] != 0};
+    LChain L{c.warp, sc->active[c.warp], chain_state(c, c.warp), par, c.s_misc[kMiscDisco + c.warp] != 0};
     if (L.st->phase == PH_AFTER_STEP) after_step(c, L);
   }
   if (c.tid == 0) prof_add(c, 12, prof_now(c) - t_pol);
@@ -2033,7 +2078,7 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
     for (int k = 0; k < kMaxChains; ++k) {
       acts[k] = ACT_EXIT;
       if (k < K) {
-        LChain L{k, sc->active[k], chain_state(c, k), par, ((stepped >> k) & 1u) && c.s_misc[4 + k] != 0};
+        LChain L{k, sc->active[k], chain_state(c, k), par, ((stepped >> k) & 1u) && c.s_misc[kMiscDisco + k] != 0};
         acts[k] = chain_advance(c, L, sc, pause);
         if (acts[k] != ACT_EXIT && acts[k] != ACT_IDLE) any = true;
         if (acts[k] == ACT_IDLE && c.lane == 0) {
@@ -2100,8 +2145,9 @@ __device__ __forceinline__ void leader_round(Ctx& c, unsigned stepped) {
     const int k = i / kStateWords, w = i - k * kStateWords;
     reinterpret_cast<unsigned long long*>(p.ob[sc->active[k]].st)[w] = reinterpret_cast<const unsigned long long*>(chain_state(c, k))[w];
   }
-  if (c.tid >= 256 && c.tid - 256 < kSchedWords)
-    reinterpret_cast<unsigned long long*>(p.sched)[c.tid - 256] = reinterpret_cast<const unsigned long long*>(sc)[c.tid - 256];
+  if (c.tid >= 256)
+    for (int i = c.tid - 256; i < kSchedWords; i += kThreads - 256)
+      reinterpret_cast<unsigned long long*>(p.sched)[i] = reinterpret_cast<const unsigned long long*>(sc)[i];
   __syncthreads();
   // everything above (ordered by bar.sync) becomes visible before the round is announced
   if (c.tid == 0) {
@@ -2278,7 +2324,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   c.t_begin = (int)(((long long)c.cta * p.g.nt) / c.G);
   c.t_end = (int)(((long long)(c.cta + 1) * p.g.nt) / c.G);
   c.bar_target = 0;
-  c.ev0 = c.ev1 = c.ev2 = 0;
+  c.ev0 = c.ev1 = c.ev2 = c.ev3 = c.ev4 = 0;
   c.round = 0;
   c.t_start = sm100::globaltimer_ns();
   c.smem = smem_raw;
@@ -2292,16 +2338,18 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
   c.mb_sig = c.mb_tempty + kAccSlots;
   c.s_tmem = reinterpret_cast<uint32_t*>(c.mb_sig + kMaxChains);
   c.load_cnt = c.mma_cnt = c.epi_cnt = 0;
-  c.s_misc = reinterpret_cast<int*>(smem_raw + L.bars + 160);      // 8 + 3 * 32 ints
-  c.s_round = reinterpret_cast<int*>(smem_raw + L.bars + 640);     // 2 * kMaxChains * 8 ints
-  c.s_xchg = reinterpret_cast<float*>(smem_raw + L.bars + 1024);
+  c.s_misc = reinterpret_cast<int*>(smem_raw + L.bars + kOffMisc);
+  c.s_round = reinterpret_cast<int*>(smem_raw + L.bars + kOffRound);   // 2 * kMaxChains * 8 ints
+  c.s_xchg = reinterpret_cast<float*>(smem_raw + L.bars + kOffXchg);
   c.s_dot = c.s_xchg + 2 * 2 * 4 * 2 * 16;
-  c.s_state = reinterpret_cast<CanvasState*>(smem_raw + L.bars + 4096);
-  c.s_sched = reinterpret_cast<Sched*>(smem_raw + L.bars + 4096 + kMaxChains * 352);
-  static_assert((2 + 2 * kActStages + 2 * kAccSlots + kMaxChains) * 8 + 8 <= 160, "mbarrier area");
+  // CTA 0's working copies of the chain states and the scheduler block live in the epilogue's exchange area: they are
+  // only used inside leader_round, between the grid barrier and the round's first tile
+  c.s_state = reinterpret_cast<CanvasState*>(smem_raw + L.bars + kOffXchg);
+  c.s_sched = reinterpret_cast<Sched*>(smem_raw + L.bars + kOffXchg + kMaxChains * kStateSlot);
+  static_assert((2 + 2 * kActStages + 2 * kAccSlots + kMaxChains) * 8 + 8 <= kOffMisc, "mbarrier area");
   c.prof = nullptr;
   if (FFN_PROFILE && p.ws.prof && (c.cta == 0 || c.cta == c.G - 1)) {
-    c.prof = reinterpret_cast<long long*>(smem_raw + L.bars + 832);
+    c.prof = reinterpret_cast<long long*>(smem_raw + L.bars + kOffProf);
     if (c.tid < 16) c.prof[c.tid] = 0;
   }
 #if FFN_PROFILE
@@ -2366,9 +2414,9 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
       for (int k = 0; k < K; ++k)
         if ((mask >> k) & 1u) tail_paste(c, k, 0, c.round & 1u, 0, 0, 0, b0 + k, false);
       ++c.round;
-      if (c.tid == 0) c.s_misc[7] = sm100::ld_volatile_s32(p.ws.abort_flag);   // one reader: no divergent exit
+      if (c.tid == 0) c.s_misc[kMiscAbort] = sm100::ld_volatile_s32(p.ws.abort_flag);   // one reader: no divergent exit
       __syncthreads();
-      if (c.s_misc[7] != 0) break;
+      if (c.s_misc[kMiscAbort] != 0) break;
     }
   } else {
     unsigned stepped = 0;   // chains that ran a FoV step in the round just finished
@@ -2400,10 +2448,10 @@ __global__ void __launch_bounds__(kThreads, 1) ffn_flood_kernel(const __grid_con
       // ---- the leader's decisions for this round
       if (c.tid == 0) {
         spin_until(c, p.round_flag, c.round + 1u, 4);
-        c.s_misc[7] = sm100::ld_volatile_s32(p.ws.abort_flag);   // one reader: the whole CTA must take the same branch
+        c.s_misc[kMiscAbort] = sm100::ld_volatile_s32(p.ws.abort_flag);   // one reader: the whole CTA must take the same branch
       }
       __syncthreads();
-      const int abort_now = c.s_misc[7];
+      const int abort_now = c.s_misc[kMiscAbort];
       if (c.tid < K) {
         int* cur = c.s_round + 8 * c.tid;
         cur[0] = sm100::ld_volatile_s32(&p.ctl->action[c.tid]);

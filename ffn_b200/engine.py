@@ -90,7 +90,7 @@ class Engine:
     _lib.check(self._lib.ffn_engine_set_grid(self._h, int(num_ctas)))
 
   def set_chains(self, max_chains: int):
-    """Objects / patches in flight at once in the persistent kernel (1..3, 0 = default); see ffn_engine_set_chains."""
+    """Objects / patches in flight at once in the persistent kernel (1..4, 0 = default 4); see ffn_engine_set_chains."""
     _lib.check(self._lib.ffn_engine_set_chains(self._h, int(max_chains)))
 
   def set_compute_mode(self, mode: int):

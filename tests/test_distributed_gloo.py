@@ -89,3 +89,61 @@ def test_merge_slabs_labels_and_probabilities_two_ranks(tmp_path):
       ids = set(np.unique(want[want > 0]).tolist())
       assert not ids & seen
       seen |= ids
+
+
+def _label_pieces(sub):
+  """Connected pieces of every cell of a ground-truth crop, ids from 1 (a slab's private id space)."""
+  from scipy import ndimage
+  lab = np.zeros(sub.shape, dtype=np.int32)
+  nxt = 0
+  for cid in np.unique(sub[sub > 0]):
+    comp, n = ndimage.label(sub == cid)
+    lab[comp > 0] = comp[comp > 0] + nxt
+    nxt += n
+  return lab, nxt
+
+
+def _worker_stitch(rank, world, port, out_dir):
+  from ffn_b200 import stitch
+  from ffn_b200.synthetic import voronoi_phantom
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  _, cells = voronoi_phantom((48, 56, 64), seed=11, return_cells=True, cell_volume=6000.0)
+  boxes = distributed.slab_boxes(cells.shape, 8)
+  labels, max_ids = [], []
+  for k in distributed.slabs_of_rank(8, rank, world):
+    lo, size = boxes[k]
+    lab, n = _label_pieces(cells[lo[0]:lo[0] + size[0], lo[1]:lo[1] + size[1], lo[2]:lo[2] + size[2]])
+    labels.append(torch.from_numpy(lab))
+    max_ids.append(n)
+  gl, _, _, total = distributed.merge_slabs(labels, None, max_ids, dst=0)
+  if rank == 0:
+    slabs = stitch.grid_of(gl, world, 8)
+    mapping, n_pairs = stitch.stitch_slabs(slabs, min_contact=4, min_fraction=0.5)
+    out = np.zeros(cells.shape, dtype=np.int64)
+    grid = distributed.slab_grid(8)
+    for k, (lo, size) in enumerate(boxes):
+      iz, rem = divmod(k, grid[1] * grid[2])
+      iy, ix = divmod(rem, grid[2])
+      out[lo[0]:lo[0] + size[0], lo[1]:lo[1] + size[1], lo[2]:lo[2] + size[2]] = slabs[(iz, iy, ix)].numpy()
+    np.save(os.path.join(out_dir, 'stitched.npy'), out)
+    np.save(os.path.join(out_dir, 'cells.npy'), cells)
+    np.save(os.path.join(out_dir, 'meta.npy'), np.array([total, n_pairs, len(mapping)]))
+  dist.destroy_process_group()
+
+
+def test_merge_then_stitch_two_ranks(tmp_path):
+  """configs[3] exchange step + cross-slab reconciliation (ffn_b200/stitch.py): 8 touching slabs on 2 ranks, private id
+  spaces -> NCCL-style gather (gloo here) -> union-find over the shared faces on rank 0.  No stitched object may span
+  two true cells, and the cut cells come back as one object."""
+  port = _free_port()
+  mp.spawn(_worker_stitch, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  out, cells = np.load(tmp_path / 'stitched.npy'), np.load(tmp_path / 'cells.npy')
+  total, n_pairs, n_mapped = np.load(tmp_path / 'meta.npy').tolist()
+  assert n_pairs > 0 and n_mapped > 0
+  fg = cells > 0
+  assert np.array_equal(out > 0, fg)
+  pair = np.unique(np.stack([out[fg], cells[fg].astype(np.int64)], axis=1), axis=0)
+  assert len(np.unique(pair[:, 0])) == len(pair), 'false merge across a slab face'
+  assert len(np.unique(out[fg])) < total          # ids were joined

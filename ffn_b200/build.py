@@ -31,16 +31,20 @@ def build(force=False, verbose=False, defines=(), out=None):
   out = out or OUT
   if out == OUT and not force and up_to_date():
     return OUT
+  tmp = out + '.tmp%d' % os.getpid()   # linked next to the target and renamed over it: a reader never sees a partial file
   cmd = [
       nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--default-stream', 'per-thread',
-      '-Xcompiler', '-fPIC', '-shared', '-o', out, SRC, '-lcudart',
+      '-Xcompiler', '-fPIC', '-shared', '-o', tmp, SRC, '-lcudart',
   ] + ['-D%s' % d for d in defines]
   if verbose:
     cmd.insert(1, '-Xptxas')
     cmd.insert(2, '-v')
   res = subprocess.run(cmd, capture_output=True, text=True)
   if res.returncode != 0:
+    if os.path.exists(tmp):
+      os.unlink(tmp)
     raise RuntimeError('nvcc failed:\n%s\n%s' % (res.stdout, res.stderr))
+  os.replace(tmp, out)
   if verbose:
     sys.stderr.write(res.stderr)
   return out

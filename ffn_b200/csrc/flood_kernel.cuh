@@ -586,10 +586,10 @@ __device__ __forceinline__ void publish_counts(Ctx& c, int k, int hit) {
 // One round of the conv stacks of the chains in `mask`, as ONE warp-specialised pipeline over the work
 // items (layer, chain, tile) in that order:
 //   warp 8  TMA producer : waits for the chain's split-phase barrier (previous layer complete in every
-//                          CTA), then per tile ONE tiled TMA through the buffer's tensor map (box: 8 halfs x
-//                          126 + 2*halo rows x 3 z-planes x k-chunks) into a 2-stage shared-memory ring
-//                                                                       full[stage]  <-  empty[stage]
-//   warp 9  UMMA issuer  : 18 UMMAs 128x96x16 per tile into a 3-slot TMEM ring; one commit frees the
+//                          CTA), then per tile twelve 1-D bulk copies (3 z-planes x 4 k-chunks of 126 + 2*halo
+//                          rows; or ONE tiled TMA through the buffer's tensor map, FFN_B200_TMAP=1) into a
+//                          kActStages-stage shared-memory ring            full[stage]  <-  empty[stage]
+//   warp 9  UMMA issuer  : 18 UMMAs 128x96x16 per tile into a kAccSlots-slot TMEM ring; one commit frees the
 //                          smem stage, one publishes the slot           tfull[slot]  <-  tempty[slot]
 //   warps 0-7 epilogue   : every tile by all eight warps (2 channel halves x 4 TMEM lane quarters); after a
 //                          chain's tiles of a layer they ARRIVE at that chain's barrier and go on

@@ -7,7 +7,7 @@ KEEP = ('Kernel Name', 'Block Size', 'Grid Size', 'gpu__time_duration.sum', 'sm_
         'lts__throughput', 'l1tex__data_pipe_lsu_wavefronts_mem_shared', 'launch__registers_per_thread', 'launch__block',
         'launch__grid_size', 'launch__shared_mem', 'launch__cluster', 'launch__occupancy_limit', 'sm__inst_executed.avg.per_cycle',
         'sm__throughput', 'smsp__warp_issue_stalled', 'sm__warps_active', 'smsp__cycles_active.avg', 'lts__t_sectors_srcunit_tex',
-        'sm__inst_executed_pipe_uniform', 'smsp__inst_executed.sum')
+        'sm__inst_executed_pipe_uniform', 'smsp__inst_executed.sum', 'xbar', 'lts__t_sectors.sum', 'lts__t_sectors_op', 'lts__t_bytes')
 
 
 def main():

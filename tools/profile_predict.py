@@ -1,4 +1,4 @@
-"""ffn_predict(batch=48) three times: the conv stack alone, three patches per round (for ncu captures)."""
+"""ffn_predict(batch=48) three times: the conv stack alone, four patches per round by default (for ncu captures)."""
 import os, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)

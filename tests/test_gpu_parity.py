@@ -766,3 +766,64 @@ def test_resegmentation_process_point(tmp_path, golden_dir):
       # the object re-grown from inside cell `sid` recovers most of it and stays mostly inside it
       assert (grown & orig).sum() > 0.3 * orig.sum(), ((grown & orig).sum(), orig.sum())
       assert (grown & orig).sum() > 0.7 * grown.sum(), ((grown & orig).sum(), grown.sum())
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'x2'])
+def test_resegmentation_process_point_equals_reference_golden(tmp_path, golden_dir, g64, mode):
+  """resegmentation.process_point against the REFERENCE's own process_point (resegmentation.py:111-293, run unmodified by
+  tests/golden/make_golden_reseg.py with the fp32 oracle network) on the golden volume: a pair point between two
+  objects of the reference's own segmentation and the same point as an endpoint.  Seeding (EDT maximum, margins,
+  init_exclusion_radius), the attempts, histories, history_deleted, the recovery test inside the analysis window and
+  the saved arrays must be the reference's — in both label-exact modes."""
+  from google.protobuf import text_format
+  from ffn.inference import inference_pb2, resegmentation, runner as runner_mod
+  from ffn_b200 import _lib
+  r = np.load(os.path.join(golden_dir, 'reseg_64.npz'))
+  pz, py, px = (int(v) for v in r['point_zyx'])
+  id_a, id_b = int(r['id_a']), int(r['id_b'])
+  rz, ry, rx = (int(v) for v in r['radius_zyx'])
+  az, ay, ax = (int(v) for v in r['analysis_radius_zyx'])
+  np.save(tmp_path / 'vol.npy', g64['volume'])
+  np.save(tmp_path / 'seg.npy', np.maximum(g64['segmentation'], 0)[np.newaxis].astype(np.uint64))
+  req = inference_pb2.ResegmentationRequest()
+  text_format.Parse('''inference { image { hdf5: "%s:raw" } init_segmentation { hdf5: "%s:seg" }
+      image_mean: 128 image_stddev: 33 seed_policy: "PolicyPeaks" model_checkpoint_path: "%s"
+      model_name: "convstack_3d.ConvStack3DFFNModel"
+      model_args: "{\\"depth\\": 12, \\"fov_size\\": [33, 33, 33], \\"deltas\\": [8, 8, 8]}"
+      segmentation_output_dir: "%s"
+      inference_options { init_activation: 0.95 pad_value: 0.05 move_threshold: 0.9 min_boundary_dist { x: 1 y: 1 z: 1}
+                          segment_threshold: 0.6 min_segment_size: 1000 } }
+      radius { x: %d y: %d z: %d } output_directory: "%s" max_retry_iters: %d
+      exclusion_radius { x: %d y: %d z: %d } init_exclusion_radius { x: %d y: %d z: %d }
+      analysis_radius { x: %d y: %d z: %d } segment_recovery_fraction: %r''' % (
+          tmp_path / 'vol.npy', tmp_path / 'seg.npy', os.path.join(golden_dir, 'fib25_convstack.npz'),
+          tmp_path / 'segout', rx, ry, rz, tmp_path / 'reseg', int(r['max_retry_iters']),
+          *([int(r['exclusion_radius'])] * 3), *([int(r['init_exclusion_radius'])] * 3), ax, ay, az,
+          float(r['segment_recovery_fraction'])), req)
+  for ids in ((id_a, id_b), (id_a,)):
+    pt = req.points.add()
+    pt.id_a = ids[0]
+    if len(ids) > 1:
+      pt.id_b = ids[1]
+    pt.point.x, pt.point.y, pt.point.z = px, py, pz
+  runner = runner_mod.Runner(compute_mode={'fp32': _lib.COMPUTE_FP32, 'x2': _lib.COMPUTE_FP16X2_TC}[mode])
+  runner.start(req.inference)
+  resegmentation.process(req, runner)
+  runner.stop_executor()
+  for tag, ids in (('pair', (id_a, id_b)), ('endpoint', (id_a,))):
+    name = '%d-%d_at_%d_%d_%d.npz' % (ids[0], ids[1] if len(ids) > 1 else 0, px, py, pz)
+    out = np.load(tmp_path / 'reseg' / name, allow_pickle=True)
+    np.testing.assert_array_equal(np.asarray(out['corner_zyx']), r[tag + '_corner_zyx'])
+    assert bool(out['is_shift']) == bool(r[tag + '_is_shift'])
+    n_obj = int(r[tag + '_n_objects'])
+    assert len(out['histories']) == n_obj and len(out['deletes']) == n_obj
+    for k in range(2):
+      np.testing.assert_array_equal(np.asarray(out['start_points'][k], dtype=np.int64).reshape(-1, 3), r['%s_starts_%d' % (tag, k)])
+    for k in range(n_obj):
+      np.testing.assert_array_equal(np.asarray(out['histories'][k], dtype=np.int32).reshape(-1, 3), r['%s_history_%d' % (tag, k)])
+      np.testing.assert_array_equal(np.asarray(out['deletes'][k], dtype=np.int64), r['%s_deletes_%d' % (tag, k)])
+    for key in ('raw_probs', 'probs'):
+      got, want = out[key].astype(int), r['%s_%s' % (tag, key)].astype(int)
+      assert got.shape == want.shape
+      diff = np.abs(got - want)
+      assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (key, int(diff.max()), float((diff > 0).mean()))   # quantisation bin edges

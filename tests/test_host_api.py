@@ -505,3 +505,94 @@ def test_stitch_slabs_recovers_objects_cut_by_slab_borders():
   assert uf.mapping() == {7: 3, 9: 3}
   m2, n2 = stitch.stitch_slabs(slabs, min_contact=4, min_fraction=0.5)
   assert all(uf2 == m2[k] for k, uf2 in m2.items()) and not m2   # second pass: nothing left to join
+
+
+def test_resegmentation_process_point_equals_reference_golden_with_oracle_canvas(tmp_path, golden_dir):
+  """The host side of resegmentation.process_point against the REFERENCE's own process_point (fixture reseg_64.npz,
+  tests/golden/make_golden_reseg.py): with the oracle canvas standing in for the device canvas (same fp32 network as
+  the fixture), seeding, attempts, histories, history_deleted, start points and the saved probability arrays must be
+  the reference's, bit for bit.  (-m gpu has the same comparison through Runner and the device canvas.)"""
+  from ffn.inference import align, inference_pb2, inference_utils, resegmentation
+  from ffn_b200 import tf_checkpoint
+  from oracle import flood_fill as ff
+  from oracle.network import ConvStackOracle
+  r = np.load(os.path.join(golden_dir, 'reseg_64.npz'))
+  g = np.load(os.path.join(golden_dir, 'flood_fill_64.npz'))
+  w, b = tf_checkpoint.load_convstack_npz(os.path.join(golden_dir, 'fib25_convstack.npz'))
+  net = ConvStackOracle(w, b)
+  seg_all = np.maximum(g['segmentation'], 0).astype(np.uint64)
+
+  class OracleCanvas:
+    def __init__(self, corner, size):
+      self.corner_zyx = np.asarray(corner)
+      sel = tuple(slice(int(c), int(c + s)) for c, s in zip(corner, size))
+      image = (g['volume'][sel].astype(np.float32) - np.float32(128.0)) / np.float32(33.0)
+      self._cv = ff.Canvas(net, image, (33, 33, 33), (8, 8, 8), ff.Options())
+      sub = seg_all[sel]
+      ids = np.unique(sub[sub > 0])                              # make_contiguous: ascending ids -> 1..n
+      self._g2l = {int(v): i + 1 for i, v in enumerate(ids)}
+      local = np.zeros(sub.shape, np.int32)
+      for gid, lid in self._g2l.items():
+        local[sub == gid] = lid
+      self._cv.segmentation[...] = local
+      self.segmentation = self._cv.segmentation
+      self.seg_prob = np.where(local > 0, 255, 0).astype(np.uint8)
+      self.margin = np.array([16, 16, 16])
+      self.restrictor = None
+      self.counters = inference_utils.Counters()
+
+    seed = property(lambda self: self._cv.seed)
+    history = property(lambda self: self._cv.history)
+    history_deleted = property(lambda self: self._cv.history_deleted)
+
+    def local_id(self, gid):
+      return self._g2l.get(int(gid), gid)
+
+    def log_info(self, *args, **kwargs):
+      pass
+
+    def _deregister_client(self):
+      pass
+
+    def segment_at(self, pos):
+      return self._cv.segment_at(tuple(int(p) for p in pos))
+
+  class OracleRunner:
+    counters = inference_utils.Counters()
+    init_seg_volume = seg_all[np.newaxis]
+
+    def make_canvas(self, corner, size, **kwargs):
+      assert kwargs == {'keep_history': True}
+      return OracleCanvas(corner, size), align.Alignment(corner, size)
+
+  pz, py, px = (int(v) for v in r['point_zyx'])
+  id_a, id_b = int(r['id_a']), int(r['id_b'])
+  req = inference_pb2.ResegmentationRequest()
+  req.radius.z, req.radius.y, req.radius.x = (int(v) for v in r['radius_zyx'])
+  req.output_directory = str(tmp_path)
+  req.max_retry_iters = int(r['max_retry_iters'])
+  req.exclusion_radius.x = req.exclusion_radius.y = req.exclusion_radius.z = int(r['exclusion_radius'])
+  req.init_exclusion_radius.x = req.init_exclusion_radius.y = req.init_exclusion_radius.z = int(r['init_exclusion_radius'])
+  req.analysis_radius.z, req.analysis_radius.y, req.analysis_radius.x = (int(v) for v in r['analysis_radius_zyx'])
+  req.segment_recovery_fraction = float(r['segment_recovery_fraction'])
+  req.inference.inference_options.segment_threshold = 0.6
+  req.inference.inference_options.min_segment_size = 1000
+  for ids in ((id_a, id_b), (id_a,)):
+    pt = req.points.add()
+    pt.id_a = ids[0]
+    if len(ids) > 1:
+      pt.id_b = ids[1]
+    pt.point.x, pt.point.y, pt.point.z = px, py, pz
+  resegmentation.process(req, OracleRunner())
+  for tag, ids in (('pair', (id_a, id_b)), ('endpoint', (id_a,))):
+    out = np.load(tmp_path / ('%d-%d_at_%d_%d_%d.npz' % (ids[0], ids[1] if len(ids) > 1 else 0, px, py, pz)), allow_pickle=True)
+    np.testing.assert_array_equal(np.asarray(out['corner_zyx']), r[tag + '_corner_zyx'])
+    n_obj = int(r[tag + '_n_objects'])
+    assert len(out['histories']) == n_obj
+    for k in range(2):
+      np.testing.assert_array_equal(np.asarray(out['start_points'][k], dtype=np.int64).reshape(-1, 3), r['%s_starts_%d' % (tag, k)])
+    for k in range(n_obj):
+      np.testing.assert_array_equal(np.asarray(out['histories'][k], dtype=np.int32).reshape(-1, 3), r['%s_history_%d' % (tag, k)])
+      np.testing.assert_array_equal(np.asarray(out['deletes'][k], dtype=np.int64), r['%s_deletes_%d' % (tag, k)])
+    np.testing.assert_array_equal(out['raw_probs'], r[tag + '_raw_probs'])
+    np.testing.assert_array_equal(out['probs'], r[tag + '_probs'])

@@ -827,3 +827,55 @@ def test_resegmentation_process_point_equals_reference_golden(tmp_path, golden_d
       assert got.shape == want.shape
       diff = np.abs(got - want)
       assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (key, int(diff.max()), float((diff > 0).mean()))   # quantisation bin edges
+
+
+def test_configs1_object_vs_pure_fp32_oracle(engines, weights):
+  """BASELINE configs[1] (256^3 phantom seed 1, one object from the centre; run on the 144^3 neighbourhood of the seed
+  so that the CPU side stays small) against the PURE fp32 oracle on the CPU (reference loop + fp32 network, no device
+  arithmetic in the checker), the whole object (a few hundred FoV steps): the split-fp16 mode must walk the same
+  positions and leave the same seed canvas unless a decision sits on a knife edge (then the object must still agree
+  voxel for voxel to 99 %); the fast fp16 mode is bounded by the overlap of the object it grows."""
+  import torch
+  from ffn_b200 import _lib, engine as eng
+  from ffn_b200.synthetic import interior_seed, voronoi_phantom
+  from oracle.network import ConvStackOracle
+  vol = voronoi_phantom((256, 256, 256), seed=1)
+  start = interior_seed(vol, (128, 128, 128))
+  # the object stays inside its cell: a crop around it keeps the oracle's arrays small; positions are crop-relative
+  lo = np.array(start) - 72
+  crop = vol[lo[0]:lo[0] + 144, lo[1]:lo[1] + 144, lo[2]:lo[2] + 144]
+  cstart = tuple(int(v) for v in np.array(start) - lo)
+  torch.set_num_threads(min(32, os.cpu_count() or 1))
+  w, b = weights
+  orc = ff.Canvas(ConvStackOracle(w, b), _image(crop), FOV, DELTAS, ff.Options())
+  n_ref = orc.segment_at(cstart)
+  ref_mask = orc.seed >= ff.f32_logit(0.6)
+  assert n_ref > 50 and ref_mask.sum() > 10000
+  th = eng.f32_logit(0.6)
+  report = {}
+  for mode in ('x2', 'tc'):
+    cv = eng.DeviceCanvas(engines[mode], crop, eng.make_options(), 128.0, 33.0)
+    cv.start_trace(1 << 16)
+    st = cv.segment_at(cstart)
+    ev = cv.get_trace()
+    steps = ev[ev[:, 0] == 6][:, 1:]
+    seed = cv.read(_lib.ARRAY_SEED)
+    cv.close()
+    mask = seed >= th
+    iou = float((mask & ref_mask).sum()) / float((mask | ref_mask).sum())
+    same = int(st.iters) == n_ref and np.array_equal(steps, np.asarray(orc.trace, dtype=steps.dtype).reshape(-1, 3))
+    n_same = 0
+    for a, b2 in zip(steps.tolist(), [list(p) for p in orc.trace]):
+      if a != b2:
+        break
+      n_same += 1
+    both = np.isfinite(seed) & np.isfinite(orc.seed)
+    err = float(np.abs(seed[both] - orc.seed[both]).max()) if same else float('nan')
+    report[mode] = dict(steps=int(st.iters), steps_ref=n_ref, same_positions=bool(same), first_divergent_step=n_same,
+                        object_iou=round(iou, 5), max_seed_err=err, min_margin_ref=float(orc.min_margin))
+    if mode == 'x2':
+      assert (same and err <= 1e-3) or iou >= 0.99, report
+    else:
+      assert iou >= 0.95 and abs(int(st.iters) - n_ref) <= 0.15 * n_ref, report
+  print('configs[1] object vs pure fp32 oracle:', json.dumps(report))
+

@@ -553,25 +553,42 @@ def run_multi(args, rank, local_rank, world):
   if rank == 0:
     gathered_vox = int(sum(int((t > 0).sum()) for row in gl for t in row))
     assert sum(t.numel() for row in gp for t in row) == n_slabs * slab[0] * slab[1] * slab[2]
-  if not args.stitch:
-    del gl
   del gp
   torch.cuda.synchronize()
   t_merge = time.perf_counter() - tm
   barrier()
   total = time.perf_counter() - t0
   clocks = sampler.stop()
-  stitch_info = None
-  if args.stitch:
-    # optional, OUTSIDE the timed region: reconcile ids across the touching slab faces (the reference leaves this
-    # to the user, doc/manual.md:119-127) on the gathered labels in rank 0's HBM
-    if rank == 0:
-      from ffn_b200 import stitch
-      ts = time.perf_counter()
-      mapping, n_pairs = stitch.stitch_slabs(stitch.grid_of(gl, world, n_slabs))
-      torch.cuda.synchronize()
-      stitch_info = {'seconds': time.perf_counter() - ts, 'joined_pairs': int(n_pairs), 'ids_renamed': len(mapping)}
-    del gl
+  # ---- OUTSIDE the timed region, rank 0 only, on the gathered labels in its HBM (no collectives from here to `del gl`)
+  merge_check, stitch_info = None, None
+  if rank == 0:
+    try:
+      # the merge must leave every slab with its own id range: (min id, max id) intervals pairwise disjoint, all within
+      # 1..total_ids — what `per-slab results with offsets` means for the reference's private id spaces (manual.md:107-127)
+      spans = []
+      for row in gl:
+        for t in row:
+          pos = t[t > 0]
+          if pos.numel():
+            spans.append((int(pos.min()), int(pos.max())))
+      spans.sort()
+      disjoint = all(spans[i][1] < spans[i + 1][0] for i in range(len(spans) - 1))
+      merge_check = {'slabs_with_labels': len(spans), 'id_ranges_disjoint': bool(disjoint),
+                     'max_id_seen': max([b for _, b in spans] or [0]), 'total_ids': int(total_ids),
+                     'ok': bool(disjoint and max([b for _, b in spans] or [0]) <= int(total_ids))}
+    except Exception as e:  # pylint: disable=broad-except
+      merge_check = {'error': repr(e)}
+    if args.stitch:
+      # optional: reconcile ids across the touching slab faces (the reference leaves this to the user, doc/manual.md:119-127)
+      try:
+        from ffn_b200 import stitch
+        ts = time.perf_counter()
+        mapping, n_pairs = stitch.stitch_slabs(stitch.grid_of(gl, world, n_slabs))
+        torch.cuda.synchronize()
+        stitch_info = {'seconds': time.perf_counter() - ts, 'joined_pairs': int(n_pairs), 'ids_renamed': len(mapping)}
+      except Exception as e:  # pylint: disable=broad-except
+        stitch_info = {'error': repr(e)}
+  del gl
   launches = engine.info()['launches'] - launches0 + 10 * len(vols)
 
   stats = torch.tensor([steps, vox, dev_s, t_work, t_merge, total, executed, launches, h2d], dtype=torch.float64, device=dev)
@@ -596,7 +613,7 @@ def run_multi(args, rank, local_rank, world):
         'imbalance': float(smax[3]) / max(float(smin[3]), 1e-9),
         'labelled_voxels_on_rank0_after_merge': gathered_vox, 'total_ids': int(total_ids),
         'steps_executed': int(ssum[6]),
-        'stitch': stitch_info,
+        'merge_check': merge_check, 'stitch': stitch_info,
         'gpu_launches': int(ssum[7]),
         'clocks': clocks,
         'e2e': {'value': value, 'unit': 'FoV steps/s', 'voxels_per_sec': float(ssum[1]) / wall,

@@ -5,8 +5,13 @@ Restates ffn/inference/seed.py:133-199 (`_find_peaks`, `PolicyPeaks.init_coords`
 (`get_exclusion_mask`) and the border filter of `BaseSeedPolicy.__next__` (:74-88), independently of
 `ffn_b200` (nothing from the product package is imported here).
 
+PINNED against the reference's own, unmodified `PolicyPeaks` (tests/golden/make_golden_peaks.py ->
+policy_peaks_ref.npz, tests/test_oracle_golden.py::test_seed_peaks_oracle_equals_reference_policy_peaks: isotropic,
+anisotropic, masked canvases; the seed lists are equal, order included) — for everything except the two third-party
+calls below, which that fixture injects by definition.
+
 Third-party pieces of the reference that are NOT under /root/reference (un-vendored, unpinned in
-setup.py:43,47 — `edt>=2.3.0`, `scikit-image>=0.11.0`), so this part of the oracle is **parity unpinned**:
+setup.py:43,47 — `edt>=2.3.0`, `scikit-image>=0.11.0`), so for these two definitions the oracle is **parity unpinned**:
 
   * `edt.edt(binary, anisotropy=voxel_size)`: the exact Euclidean distance transform of the foreground to the
     nearest background voxel, distances in physical units, float32 output (edt's documented semantics).

@@ -216,3 +216,23 @@ def test_seed_peaks_oracle_properties():
   np.testing.assert_array_equal(c, seed_peaks.policy_peaks(image, (1, 1, 1), segmentation=seg, mask=mask, margin_zyx=(4, 4, 4)))
   full = seed_peaks.policy_peaks(image, (2, 1, 1))
   assert full.shape[0] > 10 and not np.array_equal(full, seed_peaks.policy_peaks(image, (1, 1, 1)))
+
+
+def test_seed_peaks_oracle_equals_reference_policy_peaks(golden_dir):
+  """oracle/seed_peaks.py against the reference's OWN PolicyPeaks (seed.py:36-199, run unmodified by
+  tests/golden/make_golden_peaks.py with only the two un-vendored third-party calls — edt.edt and
+  skimage.feature.peak_local_max — injected by definition): isotropic, anisotropic voxel size, and a canvas with a
+  movement mask, a seed mask, existing labels and -1 markers.  The seed LIST (order included) must be equal."""
+  from oracle import seed_peaks
+  r = np.load(os.path.join(golden_dir, 'policy_peaks_ref.npz'))
+  for case in ('iso', 'aniso', 'masked'):
+    vol = r[case + '_volume']
+    image = (vol.astype(np.float32) - np.float32(128.0)) / np.float32(33.0)
+    kw = {}
+    if case == 'masked':
+      kw = dict(mask=r['masked_mask'], seed_mask=r['masked_seed_mask'])
+    got = seed_peaks.policy_peaks(image, voxel_size_zyx=tuple(float(v) for v in r[case + '_voxel']),
+                                  segmentation=r[case + '_segmentation'], margin_zyx=tuple(int(v) for v in r[case + '_margin']), **kw)
+    want = r[case + '_coords']
+    assert want.shape[0] >= 8, (case, want.shape)
+    np.testing.assert_array_equal(got, want, err_msg=case)

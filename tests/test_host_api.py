@@ -596,3 +596,44 @@ def test_resegmentation_process_point_equals_reference_golden_with_oracle_canvas
       np.testing.assert_array_equal(np.asarray(out['deletes'][k], dtype=np.int64), r['%s_deletes_%d' % (tag, k)])
     np.testing.assert_array_equal(out['raw_probs'], r[tag + '_raw_probs'])
     np.testing.assert_array_equal(out['probs'], r[tag + '_probs'])
+
+
+def test_subvolume_files_interoperate_with_the_reference_writer_and_reader(tmp_path, golden_dir):
+  """seg-*.npz both ways (fixtures from tests/golden/make_golden_storage.py): files written by the reference's own
+  `storage.save_subvolume` (ids <= 255 -> uint8, > 255 -> uint16) are read by this package's `load_segmentation` /
+  `load_origins`; and this package's writer produces, key by key, the arrays the reference wrote — the same file,
+  read by the reference's own `load_segmentation`, gave `*_read_by_reference` when the fixture was made."""
+  import shutil
+  from ffn.inference import storage
+  r = np.load(os.path.join(golden_dir, 'storage_roundtrip.npz'))
+  for tag, dtype in (('u8', np.uint8), ('u16', np.uint16)):
+    labels = r[tag + '_labels']
+    ids = r[tag + '_origin_ids'].tolist()
+    origins = {sid: storage.OriginInfo(tuple(int(v) for v in r[tag + '_origin_start'][k]), int(r[tag + '_origin_iters'][k]),
+                                       float(r[tag + '_origin_wall'][k])) for k, sid in enumerate(ids)}
+    # the reference's file -> our reader
+    ref_dir = tmp_path / ('ref_' + tag)
+    path = storage.segmentation_path(str(ref_dir), (0, 0, 0))
+    os.makedirs(os.path.dirname(path))
+    shutil.copy(os.path.join(golden_dir, 'ref_subvolume_%s.npz' % tag), path)
+    seg, got = storage.load_segmentation(str(ref_dir), (0, 0, 0), split_cc=False)
+    assert seg.dtype == np.uint64
+    np.testing.assert_array_equal(seg, labels.astype(np.uint64))
+    np.testing.assert_array_equal(seg, r[tag + '_read_by_reference'])
+    assert {k: (tuple(v.start_zyx), v.iters, v.walltime_sec) for k, v in got.items()} == {
+        k: (tuple(v.start_zyx), v.iters, v.walltime_sec) for k, v in origins.items()}
+    assert storage.load_origins(str(ref_dir), (0, 0, 0)).keys() == origins.keys()
+    # our writer == the reference's writer, array by array
+    ours = tmp_path / ('ours_' + tag) / 'seg.npz'
+    overlaps = {sid: np.array([[1, 2], [k, 3 * k]], dtype=np.int64) for k, sid in enumerate(ids)}
+    storage.save_subvolume(labels.copy(), origins, str(ours), request=b'request-bytes', counters='{"a": 1}', overlaps=overlaps)
+    a = np.load(ours, allow_pickle=True)
+    b = np.load(os.path.join(golden_dir, 'ref_subvolume_%s.npz' % tag), allow_pickle=True)
+    assert sorted(a.files) == sorted(b.files)
+    assert a['segmentation'].dtype == dtype == b['segmentation'].dtype
+    np.testing.assert_array_equal(a['segmentation'], b['segmentation'])
+    assert a['request'].tobytes() == b['request'].tobytes() and str(a['counters']) == str(b['counters'])
+    oa, ob = a['origins'].item(), b['origins'].item()
+    assert {k: tuple(v) for k, v in oa.items()} == {k: tuple(v) for k, v in ob.items()}
+    va, vb = a['overlaps'].item(), b['overlaps'].item()
+    assert va.keys() == vb.keys() and all(np.array_equal(va[k], vb[k]) for k in va)

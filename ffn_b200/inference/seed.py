@@ -243,7 +243,8 @@ class PolicyDenseSeeds(BaseSeedPolicy):
     if self._invert:
       x = ~x
     for _ in range(self._num_erosions):
-      x = ndimage.binary_erosion(x)
+      # skimage.morphology.binary_erosion (seed.py:488): connectivity-1 cross, outside of the image counts as foreground
+      x = ndimage.binary_erosion(x, border_value=True)
     self.coords = np.array(np.where(x)).T
 
 

@@ -637,3 +637,54 @@ def test_subvolume_files_interoperate_with_the_reference_writer_and_reader(tmp_p
     assert {k: tuple(v) for k, v in oa.items()} == {k: tuple(v) for k, v in ob.items()}
     va, vb = a['overlaps'].item(), b['overlaps'].item()
     assert va.keys() == vb.keys() and all(np.array_equal(va[k], vb[k]) for k in va)
+
+
+def test_seed_policies_and_counters_equal_the_reference_modules(golden_dir):
+  """The simple seed policies (PolicyMax, PolicyGrid2d / 3d with custom steps and offsets, PolicyDenseSeeds with
+  erosions / invert, ReverseCoords, SequentialPolicies — seed.py:307-313,411-544 behind the border filter of
+  BaseSeedPolicy.__next__, :63-95) and `Counters.dumps / loads` (inference_utils.py:90-150) against the outputs of the
+  reference's own modules (tests/golden/make_golden_policies.py)."""
+  import importlib.util
+  from ffn.inference import inference_utils, seed
+  spec = importlib.util.spec_from_file_location('make_golden_policies', os.path.join(golden_dir, 'make_golden_policies.py'))
+  r = np.load(os.path.join(golden_dir, 'seed_policies_ref.npz'))
+
+  class FakeCanvas:
+    image = r['image']
+    shape = tuple(r['image'].shape)
+    margin = r['margin']
+    restrictor = None
+    segmentation = np.zeros(r['image'].shape, np.int32)
+
+  cases = [
+      ('max', 'PolicyMax', {}),
+      ('grid2d', 'PolicyGrid2d', {'step': 6, 'offsets': (0, 3, 1)}),
+      ('grid3d', 'PolicyGrid3d', {'step': 5, 'offsets': (0, 2, 4)}),
+      ('dense', 'PolicyDenseSeeds', {'threshold': 0.5, 'num_erosions': 1}),
+      ('dense_inv', 'PolicyDenseSeeds', {'threshold': 0.55, 'num_erosions': 2, 'invert': True}),
+      ('reverse', 'ReverseCoords', {'policy_to_reverse': 'PolicyGrid3d', 'step': 6}),
+      ('sequential', 'SequentialPolicies', {'policies': [('PolicyGrid3d', {'step': 7}), ('PolicyGrid2d', {'step': 9})]}),
+  ]
+  del spec
+  for name, cls, kwargs in cases:
+    canvas = FakeCanvas()
+    got = np.array([tuple(int(v) for v in c) for c in getattr(seed, cls)(canvas, **kwargs)], dtype=np.int64).reshape(-1, 3)
+    np.testing.assert_array_equal(got, r['coords_' + name], err_msg=name)
+
+  c = inference_utils.Counters()
+  c['inference-calls'].IncrementBy(144)
+  c['voxels-segmented'].Set(123456)
+  c['inference-time-ms'].IncrementBy(2500)
+  sub = c.get_sub_counters()
+  sub['skip_invalid_pos'].IncrementBy(7)
+  sub['voxels-segmented'].IncrementBy(44)
+  assert json.loads(sub.dumps()) == json.loads(str(r['sub_counters_dumps']))
+  # Deliberate, documented difference (inference_utils.py here): sub-counters FEED their parent — the reference's
+  # get_sub_counters (inference_utils.py:133-134) builds children whose updates never reach the parent, so its
+  # Runner.counters / counters.txt miss everything the canvases counted.  Own values must agree:
+  ref = json.loads(str(r['counters_dumps']))
+  ours = json.loads(c.dumps())
+  assert ours == dict(ref, **{'voxels-segmented': ref['voxels-segmented'] + 44, 'skip_invalid_pos': 7})
+  d = inference_utils.Counters()
+  d.loads(str(r['counters_dumps']))
+  assert json.loads(d.dumps()) == json.loads(str(r['counters_after_loads']))

@@ -688,3 +688,28 @@ def test_seed_policies_and_counters_equal_the_reference_modules(golden_dir):
   d = inference_utils.Counters()
   d.loads(str(r['counters_dumps']))
   assert json.loads(d.dumps()) == json.loads(str(r['counters_after_loads']))
+
+
+def test_build_mask_equals_reference(golden_dir):
+  """storage.build_mask (MaskConfig lists: coordinate expressions, image channels, volume channels with value lists,
+  per-channel and per-config invert, OR of several configs) against the reference's own build_mask
+  (storage.py:323-411; fixture from tests/golden/make_golden_build_mask.py) — the `request.masks` / `seed_masks` path
+  of Runner.make_restrictor."""
+  import importlib.util
+  from google.protobuf import text_format
+  from ffn.inference import inference_pb2, storage
+  spec = importlib.util.spec_from_file_location('make_golden_build_mask', os.path.join(golden_dir, 'make_golden_build_mask.py'))
+  gen = importlib.util.module_from_spec(spec)
+  sys_path = list(__import__('sys').path)
+  try:
+    spec.loader.exec_module(gen)             # only for its CASES table (no reference import happens at module level)
+  finally:
+    __import__('sys').path[:] = sys_path
+  r = np.load(os.path.join(golden_dir, 'build_mask_ref.npz'))
+  corner, size = tuple(int(v) for v in r['corner']), tuple(int(v) for v in r['size'])
+  for name, texts in gen.CASES.items():
+    configs = [text_format.Parse(t, inference_pb2.MaskConfig()) for t in texts]
+    cache = {c.volume.mask.SerializeToString(): r['volume'] for c in configs if c.WhichOneof('source') == 'volume'}
+    got = storage.build_mask(configs, corner, size, mask_volume_map=cache, image=r['image'])
+    assert got.dtype == bool
+    np.testing.assert_array_equal(got, r['mask_' + name], err_msg=name)

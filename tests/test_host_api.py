@@ -713,3 +713,84 @@ def test_build_mask_equals_reference(golden_dir):
     got = storage.build_mask(configs, corner, size, mask_volume_map=cache, image=r['image'])
     assert got.dtype == bool
     np.testing.assert_array_equal(got, r['mask_' + name], err_msg=name)
+
+
+def test_small_host_helpers_equal_the_reference(tmp_path, golden_dir):
+  """align.Alignment / Aligner, storage.clip_subvolume_to_bounds / dequantize_probability / threshold_segmentation /
+  path helpers / get_existing_subvolume_path / get_existing_corners, segmentation.reduce_id_bits / clear_dust against
+  the outputs of the reference's own functions (tests/golden/make_golden_helpers.py -> helpers_ref.npz)."""
+  import importlib.util
+  import sys
+  from ffn.inference import align, segmentation, storage
+  saved = list(sys.path)
+  try:
+    spec = importlib.util.spec_from_file_location('make_golden_helpers', os.path.join(golden_dir, 'make_golden_helpers.py'))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)                         # only its CROPS / CLIPS / CORNERS tables
+  finally:
+    sys.path[:] = saved
+  r = np.load(os.path.join(golden_dir, 'helpers_ref.npz'))
+  # ---- align
+  for i, (sc, ss, dc, ds, fill) in enumerate(gen.CROPS):
+    a = align.Alignment(dc, ds)
+    got = a.align_and_crop(np.array(sc), r['crop_src_%d' % i], np.array(dc), np.array(ds), fill=fill)
+    np.testing.assert_array_equal(got, r['crop_out_%d' % i], err_msg='crop %d' % i)
+    assert got.dtype == r['crop_out_%d' % i].dtype
+  a = align.Aligner().generate_alignment((4, 5, 6), (10, 20, 30))
+  np.testing.assert_array_equal(a.corner, r['align_corner'])
+  np.testing.assert_array_equal(a.size, r['align_size'])
+  for fwd in (True, False):
+    c, s = a.expand_bounds(np.array((1, 2, 3)), np.array((7, 8, 9)), forward=fwd)
+    np.testing.assert_array_equal(np.stack([c, s]), r['expand_%d' % fwd])
+  pts = np.array([[1, 2, 3], [4, 5, 6]]).T
+  np.testing.assert_array_equal(a.transform(pts), r['transform'])
+  rs = a.rescaled(np.array((1.0, 0.5, 0.5)))
+  np.testing.assert_array_equal(np.stack([rs.corner, rs.size]).astype(np.float64), r['rescaled'])
+  np.testing.assert_array_equal(a.transform_shift_mask(np.array((4, 5, 6)), 2, r['shift_in']), r['shift_out'])
+  # ---- clip
+  vol3, vol4 = np.zeros((20, 24, 28)), np.zeros((2, 20, 24, 28))
+  k = 0
+  for corner, size in gen.CLIPS:
+    for vol in (vol3, vol4):
+      want = r['clips'][k]
+      k += 1
+      if want[0] == -1 and want[3] == -1:
+        continue                                                   # disjoint boxes: the reference raises
+      c, s = storage.clip_subvolume_to_bounds(np.array(corner), np.array(size), vol)
+      assert list(np.asarray(c).astype(int)) + list(np.asarray(s).astype(int)) == want.tolist(), (corner, size)
+  # ---- probabilities
+  got = storage.dequantize_probability(np.arange(256, dtype=np.uint8))
+  np.testing.assert_array_equal(np.isnan(got), np.isnan(r['dequantized']))
+  np.testing.assert_array_equal(got[1:], r['dequantized'][1:])
+  assert got.dtype == r['dequantized'].dtype
+  corner = (5, 6, 7)
+  prob_path = storage.object_prob_path(str(tmp_path), corner)
+  os.makedirs(os.path.dirname(prob_path), exist_ok=True)
+  with open(prob_path, 'wb') as f:
+    np.savez_compressed(f, qprob=r['thr_qprob'])
+  labels = r['thr_labels'].copy()
+  storage.threshold_segmentation(str(tmp_path), corner, labels, 0.7)
+  np.testing.assert_array_equal(labels, r['thr_out'])
+  # ---- paths
+  paths = json.loads(str(r['paths_json']))
+  for c in gen.CORNERS:
+    ours = [storage.subvolume_path('/out', c, 'npz'), storage.legacy_subvolume_path('/out', c, 'npz'),
+            storage.segmentation_path('/out', c), storage.object_prob_path('/out', c), storage.checkpoint_path('/out', c),
+            storage.legacy_segmentation_path('/out', c), storage.legacy_object_prob_path('/out', c)]
+    assert ours == paths[str(tuple(c))]
+    assert storage.get_corner_from_path(ours[0]) == tuple(c)
+  d2 = tmp_path / 'existing'
+  for c, legacy, suffix in (((1, 2, 3), False, 'npz'), ((4, 5, 6), True, 'npz'), ((7, 8, 9), False, 'cpoint')):
+    p = storage.legacy_subvolume_path(str(d2), c, suffix) if legacy else storage.subvolume_path(str(d2), c, suffix)
+    os.makedirs(os.path.dirname(p), exist_ok=True)
+    open(p, 'wb').close()
+  existing = json.loads(str(r['existing_json']))
+  for c in ((1, 2, 3), (4, 5, 6), (7, 8, 9), (9, 9, 9)):
+    for allow in (False, True):
+      got = storage.get_existing_subvolume_path(str(d2), c, allow)
+      assert (None if got is None else os.path.relpath(got, str(d2))) == existing['%r/%d' % (c, allow)]
+  assert sorted(storage.get_existing_corners(str(d2))) == [tuple(v) for v in r['existing_corners'].tolist()]
+  # ---- segmentation helpers
+  for top in (200, 300, 70000):
+    assert str(segmentation.reduce_id_bits(r['reduce_in_%d' % top]).dtype) == str(r['reduce_dtype_%d' % top])
+  np.testing.assert_array_equal(segmentation.clear_dust(r['dust_in'].copy(), min_size=9), r['dust_out'])

@@ -236,3 +236,49 @@ def test_seed_peaks_oracle_equals_reference_policy_peaks(golden_dir):
     want = r[case + '_coords']
     assert want.shape[0] >= 8, (case, want.shape)
     np.testing.assert_array_equal(got, want, err_msg=case)
+
+
+def test_network_oracle_equals_an_independent_correlation_restatement(golden_dir):
+  """The torch-based network oracle against a second, torch-free restatement of the same TensorFlow semantics
+  (convstack_3d.py:26-56,83-95; model.py:168-183): every Conv3D as a sum of scipy.ndimage.correlate calls — one per
+  (input, output) channel pair, zero padding ('SAME'), kernel NOT flipped (cross-correlation), DHWIO weights indexed
+  directly — BiasAdd, ReLU placement (tf_slim: `_a` convolutions activated, `_b` linear), pre-activation residual
+  modules, 1x1x1 conv_lom, logits = seed + update.  Full FIB-25 depth on a small patch, float64 on both sides."""
+  import torch
+  from scipy import ndimage
+  from ffn_b200 import tf_checkpoint
+  from oracle.network import ConvStackOracle
+  w, b = tf_checkpoint.load_convstack_npz(os.path.join(golden_dir, 'fib25_convstack.npz'))
+  rng = np.random.RandomState(2)
+  shape = (7, 9, 10)
+  image = rng.randn(*shape).astype(np.float32)
+  seed = np.where(rng.rand(*shape) < 0.4, rng.randn(*shape) * 2, -2.9444).astype(np.float32)
+
+  def conv(x, wk, bias):                                   # x [C_in, Z, Y, X], wk [3, 3, 3, C_in, C_out]
+    out = np.empty((wk.shape[4],) + x.shape[1:], dtype=np.float64)
+    for co in range(wk.shape[4]):
+      acc = np.zeros(x.shape[1:], dtype=np.float64)
+      for ci in range(wk.shape[3]):
+        acc += ndimage.correlate(x[ci], wk[:, :, :, ci, co].astype(np.float64), mode='constant', cval=0.0)
+      out[co] = acc + np.float64(bias[co])
+    return out
+
+  relu = lambda t: np.maximum(t, 0.0)
+  depth = (len(w) - 1) // 2
+  net = np.stack([image, seed]).astype(np.float64)         # channel 0 = image, 1 = seed (convstack_3d.py:86)
+  net = relu(conv(net, w[0], b[0]))
+  net = conv(net, w[1], b[1])
+  for m in range(1, depth):
+    skip = net
+    net = relu(net)
+    net = relu(conv(net, w[2 * m], b[2 * m]))
+    net = conv(net, w[2 * m + 1], b[2 * m + 1])
+    net = net + skip
+  net = relu(net)
+  update = np.tensordot(w[-1][0, 0, 0, :, 0].astype(np.float64), net, axes=(0, 0)) + np.float64(b[-1][0])
+  want = seed.astype(np.float64) + update
+  orc = ConvStackOracle(w, b, dtype=torch.float64)
+  got64 = seed.astype(np.float64) + orc.update(seed, image)
+  assert np.abs(got64 - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
+  got32 = ConvStackOracle(w, b)(seed, image)
+  assert np.abs(got32 - want).max() <= 2e-4

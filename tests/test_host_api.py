@@ -794,3 +794,53 @@ def test_small_host_helpers_equal_the_reference(tmp_path, golden_dir):
   for top in (200, 300, 70000):
     assert str(segmentation.reduce_id_bits(r['reduce_in_%d' % top]).dtype) == str(r['reduce_dtype_%d' % top])
   np.testing.assert_array_equal(segmentation.clear_dust(r['dust_in'].copy(), min_size=9), r['dust_out'])
+
+
+def test_every_proto_field_matches_the_reference_proto_sources(golden_dir):
+  """The runtime-built descriptors (ffn_b200/inference/protos.py) against the reference's .proto SOURCES, field by
+  field: name, number, label, type (scalar / message / enum), default, oneof membership; enum values too (fixture:
+  tests/golden/make_golden_schema.py parses inference.proto, bounding_box.proto, vector.proto)."""
+  from google.protobuf import descriptor
+  from ffn.inference import inference_pb2
+  from ffn.utils import bounding_box_pb2, vector_pb2
+  schema = json.load(open(os.path.join(golden_dir, 'proto_schema_ref.json')))
+  pool = inference_pb2.InferenceRequest.DESCRIPTOR.file.pool
+  del bounding_box_pb2, vector_pb2
+  scalar = {descriptor.FieldDescriptor.TYPE_DOUBLE: 'double', descriptor.FieldDescriptor.TYPE_FLOAT: 'float',
+            descriptor.FieldDescriptor.TYPE_INT64: 'int64', descriptor.FieldDescriptor.TYPE_UINT64: 'uint64',
+            descriptor.FieldDescriptor.TYPE_INT32: 'int32', descriptor.FieldDescriptor.TYPE_BOOL: 'bool',
+            descriptor.FieldDescriptor.TYPE_STRING: 'string', descriptor.FieldDescriptor.TYPE_BYTES: 'bytes',
+            descriptor.FieldDescriptor.TYPE_UINT32: 'uint32'}
+  checked = 0
+  for full, ref in schema.items():
+    if full.endswith('.<file>'):
+      continue
+    d = pool.FindMessageTypeByName(full)
+    assert sorted(f.name for f in d.fields) == sorted(ref['fields']), full
+    for name, (number, label, ftype, default, oneof) in ref['fields'].items():
+      f = d.fields_by_name[name]
+      where = '%s.%s' % (full, name)
+      assert f.number == number, where
+      repeated = f.is_repeated() if callable(getattr(f, 'is_repeated', None)) else bool(getattr(f, 'is_repeated', f.label == f.LABEL_REPEATED))
+      assert repeated == (label == 'repeated'), where
+      if f.type == f.TYPE_MESSAGE:
+        assert f.message_type.full_name.split('.')[-1] == ftype.split('.')[-1], where
+      elif f.type == f.TYPE_ENUM:
+        assert f.enum_type.name == ftype.split('.')[-1], where
+      else:
+        assert scalar[f.type] == ftype, where
+      if default is not None:
+        assert f.has_default_value, where
+        got = f.default_value
+        if f.type == f.TYPE_ENUM:
+          got = f.enum_type.values_by_number[got].name
+        elif f.type == f.TYPE_BOOL:
+          got = 'true' if got else 'false'
+        assert (float(got) == float(default)) if f.type in (f.TYPE_FLOAT, f.TYPE_DOUBLE, f.TYPE_INT32, f.TYPE_INT64) \
+            else (str(got) == default), (where, got, default)
+      assert (f.containing_oneof.name if f.containing_oneof else None) == oneof, where
+      checked += 1
+    for ename, values in ref['enums'].items():
+      e = d.enum_types_by_name[ename]
+      assert {v.name: v.number for v in e.values} == values, (full, ename)
+  assert checked >= 95

@@ -821,7 +821,11 @@ def test_every_proto_field_matches_the_reference_proto_sources(golden_dir):
       f = d.fields_by_name[name]
       where = '%s.%s' % (full, name)
       assert f.number == number, where
-      repeated = f.is_repeated() if callable(getattr(f, 'is_repeated', None)) else bool(getattr(f, 'is_repeated', f.label == f.LABEL_REPEATED))
+      repeated = getattr(f, 'is_repeated', None)          # property (protobuf >= 6), method, or absent
+      if repeated is None:
+        repeated = f.label == f.LABEL_REPEATED
+      elif callable(repeated):
+        repeated = repeated()
       assert repeated == (label == 'repeated'), where
       if f.type == f.TYPE_MESSAGE:
         assert f.message_type.full_name.split('.')[-1] == ftype.split('.')[-1], where
